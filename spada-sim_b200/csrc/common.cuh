@@ -1,0 +1,187 @@
+// common.cuh -- shared device helpers and the launcher interface between the kernels (*.cu)
+// and the host engine (engine.cu).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spada {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- bins ---------------------------------------------------------------------------
+// Stage 1 classifies every A row by its intermediate-product count p (Spada's window
+// choice restated for a GPU, rowwise_perf_adjust.rs:121-252 / scheduler.rs:729-753: R rows
+// share a window of L lanes; here a bin fixes how many lanes cooperate on one row).
+//   bin 0          p == 0                 nothing to do, nnz = 0
+//   bin 1          p <= 32                one warp per row, products sorted in registers
+//   bin 2..5       p <= 64,128,256,512    one warp per row, E = N/32 keys per lane
+//   bin 6..8       p <= 1024,2048,4096    one CTA per row, shared-memory sort
+//   bin 9          p  > 4096              one CTA per row, bitmap + rank accumulator
+constexpr int NUM_BINS = 10;
+constexpr int BIN_EMPTY = 0;
+constexpr int BIN_HEAVY = 9;
+constexpr uint32_t ESC_MAX_PRODUCTS = 4096;
+
+__host__ __device__ inline int bin_of(uint32_t p) {
+    if (p == 0) return 0;
+    if (p <= 32) return 1;
+    if (p <= 64) return 2;
+    if (p <= 128) return 3;
+    if (p <= 256) return 4;
+    if (p <= 512) return 5;
+    if (p <= 1024) return 6;
+    if (p <= 2048) return 7;
+    if (p <= 4096) return 8;
+    return 9;
+}
+__host__ __device__ inline uint32_t bin_capacity(int b) { return b == 0 ? 0u : (b >= BIN_HEAVY ? 0u : (32u << (b - 1))); }
+
+struct BinTable {
+    uint32_t offset[NUM_BINS + 1];  // start of each bin inside perm[]
+};
+
+// counters written by stage 1, read back by the host in one copy
+struct PlanCounters {
+    unsigned long long total_products;
+    unsigned long long bin_products[NUM_BINS];
+    uint32_t bin_rows[NUM_BINS];
+    uint32_t bin_cursor[NUM_BINS];
+    uint32_t long_rows;      // rows deferred to the CTA-per-row flop counter
+    uint32_t invalid_rows;   // validation failures
+    uint32_t scan_ticket;    // dynamic tile id of the look-back scan
+    uint32_t pad;
+};
+
+// ---- device-side CSR view ------------------------------------------------------------
+struct DevCsr {
+    const int64_t* ptr;   // rows + 1
+    const int32_t* col;   // nnz
+    const double* val;    // nnz
+    int64_t rows, cols, nnz;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+    int lo = __shfl_sync(FULL, (int)(v & 0xffffffffll), src);
+    int hi = __shfl_sync(FULL, (int)(v >> 32), src);
+    return ((int64_t)hi << 32) | (uint32_t)lo;
+}
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    long long b = __double_as_longlong(v);
+    return __longlong_as_double(shfl_i64(b, src));
+}
+
+// read-only, L1-bypassing streaming loads for operand arrays that are touched once per row
+__device__ __forceinline__ int32_t ldg_i32(const int32_t* p) { return __ldg(p); }
+__device__ __forceinline__ double ldg_f64(const double* p) { return __ldg(p); }
+__device__ __forceinline__ int64_t ldg_i64(const int64_t* p) { return __ldg(p); }
+
+// ---- product expansion ---------------------------------------------------------------------
+// A warp walks 32 A nonzeros (one per lane: lane l owns position p, if p < a_end), scans the
+// B-row lengths and then deals the products to lanes round-robin, so B rows are read with
+// consecutive lanes on consecutive elements (coalesced) whatever their length.  This is the
+// reference's "window" of A scalars fanned out over the lanes (scheduler.rs:551-556,
+// simulator.rs:728-757) with L = 32.
+// emit(seq, q, a_val): seq = arrival index of the product inside the C row (ascending k, then
+// B's stored order), q = position in B's arrays.  BIG: B rows longer than 2^24 are streamed one
+// at a time by the whole warp (keeps the 32-bit scan from overflowing); their seq is unused.
+constexpr int EXPAND_BIG_LEN = 1 << 24;
+template <bool NUMERIC, bool BIG, typename F>
+__device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, int64_t p, int64_t a_end,
+                                             int lane, int seq_base, int& batch_total, F&& emit) {
+    int64_t bs = 0;
+    int len = 0;
+    double av = 0.0;
+    if (p < a_end) {
+        int32_t k = ldg_i32(a.col + p);
+        if (NUMERIC) av = ldg_f64(a.val + p);
+        bs = ldg_i64(b.ptr + k);
+        len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+    }
+    int big_len = 0;
+    unsigned big = 0;
+    if (BIG) {
+        big = __ballot_sync(FULL, len > EXPAND_BIG_LEN);
+        if (len > EXPAND_BIG_LEN) {
+            big_len = len;
+            len = 0;
+        }
+    }
+    int total;
+    int off = warp_excl_scan(len, lane, total);
+    batch_total = total;
+    for (int base = 0; base < total; base += 32) {
+        int t = base + lane;
+        int j = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            int o = __shfl_sync(FULL, off, j + s);
+            if (o <= t) j += s;
+        }
+        int oj = __shfl_sync(FULL, off, j);
+        int64_t bsj = shfl_i64(bs, j);
+        double aj = 0.0;
+        if (NUMERIC) aj = shfl_f64(av, j);
+        if (t < total) emit(seq_base + t, bsj + (t - oj), aj);
+    }
+    if (BIG) {
+        while (big) {
+            int j = __ffs(big) - 1;
+            big &= big - 1;
+            int64_t bsj = shfl_i64(bs, j);
+            int lj = __shfl_sync(FULL, big_len, j);
+            double aj = 0.0;
+            if (NUMERIC) aj = shfl_f64(av, j);
+            for (int t = lane; t < lj; t += 32) emit(-1, bsj + t, aj);
+        }
+    }
+}
+#endif
+
+// ---- launchers (implemented in the .cu files, called by engine.cu) ------------------------
+// stage 1
+void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t row_begin, int64_t m,
+                  uint32_t* flops, uint32_t* long_list, PlanCounters* ctr, cudaStream_t s);
+void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, uint32_t* perm,
+                        PlanCounters* ctr, cudaStream_t s);
+// stage 4
+void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out /* n+1 */, uint64_t* tile_state,
+                         PlanCounters* ctr, cudaStream_t s);
+size_t scan_tile_state_words(int64_t n);
+// conversions / validation
+void launch_widen_u64(const uint64_t* src_ptr, int64_t n_ptr, int64_t* dst_ptr, const uint64_t* src_idx,
+                      int64_t nnz, int32_t* dst_idx, cudaStream_t s);
+void launch_widen_i32(const int32_t* src_ptr, int64_t n_ptr, int64_t* dst_ptr, cudaStream_t s);
+void launch_narrow_result(const int64_t* ptr, int64_t n_ptr, uint64_t* out_ptr, const int32_t* idx,
+                          int64_t nnz, uint64_t* out_idx, cudaStream_t s);
+void launch_validate(const DevCsr& a, PlanCounters* ctr, cudaStream_t s);
+// stage 2 / 3, ESC bins (1..8)
+int esc_grid(int bin, uint32_t rows);
+void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                         uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
+void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                        uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+// stage 2 / 3, heavy bin (9)
+int heavy_grid(uint32_t rows, int sm_count, int64_t b_cols);  // resident CTAs (workspace bounded)
+size_t heavy_workspace_words(int grid, int64_t b_cols);        // uint2 words
+void launch_heavy_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                           uint32_t rows, uint32_t* row_nnz, uint2* ws, int grid, cudaStream_t s);
+void launch_heavy_numeric(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                          uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, uint2* ws,
+                          int grid, cudaStream_t s);
+void setup_kernel_attributes();
+
+}  // namespace spada

@@ -1,0 +1,823 @@
+// engine.cu -- host side of the engine and the C ABI of include/spada_b200.h.
+//
+// One handle owns a device, a stream and a stream-ordered memory pool (cudaMallocAsync with an
+// unlimited release threshold, so steady-state calls never reach the driver allocator).  A call
+// to spada_b200_spgemm_dev runs the four stages of the path on that stream:
+//   1. flop count + binning      (plan.cu)   -- one host read-back of ~200 bytes of counters
+//   2. symbolic, one launch/bin  (esc.cu, heavy.cu)
+//   4. exclusive scan -> row_ptr (plan.cu)   -- one host read-back of nnz(C) to size C
+//   3. numeric, one launch/bin   (esc.cu, heavy.cu)
+// There is no CPU compute path here: if no CUDA device is present every entry point fails with
+// SPADA_B200_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/spada_b200.h"
+#include "common.cuh"
+
+using namespace spada;
+
+// ---- errors -------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? SPADA_B200_OOM                      \
+                         : (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver)       \
+                             ? SPADA_B200_NO_DEVICE                                               \
+                             : SPADA_B200_CUDA_ERROR;                                             \
+            return fail(code__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                \
+        }                                                                                         \
+    } while (0)
+
+// ---- objects ------------------------------------------------------------------------------
+struct spada_b200 {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    spada_b200_opts opts{};
+    PlanCounters* d_ctr = nullptr;
+    PlanCounters* h_ctr = nullptr;  // pinned
+    int64_t* h_scalar = nullptr;    // pinned
+    std::vector<cudaEvent_t> events;
+    size_t ev_used = 0;
+};
+
+struct spada_b200_csr {
+    spada_b200* h;
+    DevCsr d;
+    bool owned;
+};
+
+struct spada_b200_result {
+    spada_b200* h;
+    uint64_t rows, cols, nnz;
+    int64_t* ptr;
+    int32_t* col;
+    double* val;
+    spada_b200_stats stats;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int dalloc(spada_b200* h, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU(cudaMallocAsync((void**)p, count * sizeof(T), h->stream));
+    return 0;
+}
+template <typename T>
+void dfree(spada_b200* h, T* p) {
+    if (p) cudaFreeAsync((void*)p, h->stream);
+}
+
+cudaEvent_t next_event(spada_b200* h) {
+    if (h->ev_used == h->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->events.push_back(e);
+    }
+    cudaEvent_t e = h->events[h->ev_used++];
+    cudaEventRecord(e, h->stream);
+    return e;
+}
+
+struct LaunchRec {
+    char name[32];
+    cudaEvent_t e0, e1;
+    uint32_t grid;
+    uint64_t rows, products, nnz;
+    int stage;  // 1 flops, 2 symbolic, 3 numeric, 4 scan
+};
+
+const char* bin_name(int b) {
+    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy"};
+    return names[b];
+}
+
+int check_csr_args(uint64_t rows, uint64_t cols, uint64_t nnz, const void* indptr, const void* indices,
+                   const void* data) {
+    if (!indptr) return fail(SPADA_B200_INVALID_ARG, "indptr is NULL");
+    if (nnz && (!indices || !data)) return fail(SPADA_B200_INVALID_ARG, "indices/data is NULL with nnz > 0");
+    if (cols >= (1ull << 31)) return fail(SPADA_B200_TOO_LARGE, "cols = %llu >= 2^31", (unsigned long long)cols);
+    if (rows >= (1ull << 32) - 2) return fail(SPADA_B200_TOO_LARGE, "rows = %llu >= 2^32-2", (unsigned long long)rows);
+    return 0;
+}
+
+int validate_device_csr(spada_b200* h, const DevCsr& d) {
+    if (d.rows == 0) {
+        if (d.nnz != 0) return fail(SPADA_B200_UNSORTED_INPUT, "matrix with 0 rows has nnz != 0");
+        return 0;
+    }
+    CU(cudaMemsetAsync(h->d_ctr, 0, sizeof(PlanCounters), h->stream));
+    launch_validate(d, h->d_ctr, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(PlanCounters), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->h_ctr->invalid_rows != 0 || h->h_ctr->long_rows != h->h_ctr->scan_ticket)
+        return fail(SPADA_B200_UNSORTED_INPUT,
+                    "input is not canonical CSR (%u out-of-range entries / bad row pointers, %u unsorted or "
+                    "duplicate column ids inside rows)",
+                    h->h_ctr->invalid_rows, h->h_ctr->long_rows - h->h_ctr->scan_ticket);
+    return 0;
+}
+
+int make_csr(spada_b200* h, uint64_t rows, uint64_t cols, uint64_t nnz, spada_b200_csr** out, int64_t** ptr,
+             int32_t** col, double** val) {
+    int rc;
+    if ((rc = dalloc(h, ptr, rows + 1))) return rc;
+    if ((rc = dalloc(h, col, nnz))) return rc;
+    if ((rc = dalloc(h, val, nnz))) return rc;
+    spada_b200_csr* m = new (std::nothrow) spada_b200_csr;
+    if (!m) return fail(SPADA_B200_OOM, "host allocation failed");
+    m->h = h;
+    m->d = DevCsr{*ptr, *col, *val, (int64_t)rows, (int64_t)cols, (int64_t)nnz};
+    m->owned = true;
+    *out = m;
+    return 0;
+}
+
+}  // namespace
+
+// ---- library ------------------------------------------------------------------------------
+extern "C" int spada_b200_abi_version(void) { return SPADA_B200_ABI_VERSION; }
+extern "C" const char* spada_b200_last_error(void) { return g_err; }
+
+extern "C" int spada_b200_device_count(int* count) {
+    if (!count) return fail(SPADA_B200_INVALID_ARG, "count is NULL");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(SPADA_B200_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+extern "C" int spada_b200_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(SPADA_B200_INVALID_ARG, "ptr is NULL");
+    CU(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return 0;
+}
+extern "C" int spada_b200_host_free(void* ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+// ---- handle -------------------------------------------------------------------------------
+extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out) {
+    if (!out) return fail(SPADA_B200_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SPADA_B200_NO_DEVICE, "no CUDA device (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    spada_b200* h = new (std::nothrow) spada_b200;
+    if (!h) return fail(SPADA_B200_OOM, "host allocation failed");
+    if (opts) h->opts = *opts;
+    else {
+        h->opts.device = -1;
+        h->opts.accelerator = SPADA_B200_ACC_SPADA;
+        h->opts.flags = SPADA_B200_FLAG_VALIDATE;
+    }
+    if (h->opts.lane_num == 0) h->opts.lane_num = 8;
+    if (h->opts.device < 0) {
+        CU(cudaGetDevice(&h->device));
+    } else {
+        if (h->opts.device >= n) {
+            int bad = h->opts.device;
+            delete h;
+            return fail(SPADA_B200_INVALID_ARG, "device %d out of range (count %d)", bad, n);
+        }
+        h->device = h->opts.device;
+    }
+    DeviceGuard g(h->device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) {
+        int dev = h->device;
+        delete h;
+        return fail(SPADA_B200_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a only", dev, prop.major,
+                    prop.minor);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if (h->opts.stream) {
+        h->stream = (cudaStream_t)h->opts.stream;
+    } else {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, h->device));
+    uint64_t thr = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CU(cudaMalloc((void**)&h->d_ctr, sizeof(PlanCounters)));
+    CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
+    CU(cudaMallocHost((void**)&h->h_scalar, 64));
+    setup_kernel_attributes();
+    *out = h;
+    return 0;
+}
+
+extern "C" void spada_b200_destroy(spada_b200_t* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    cudaFree(h->d_ctr);
+    cudaFreeHost(h->h_ctr);
+    cudaFreeHost(h->h_scalar);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int spada_b200_set_stream(spada_b200_t* h, void* cuda_stream) {
+    if (!h) return fail(SPADA_B200_INVALID_ARG, "handle is NULL");
+    DeviceGuard g(h->device);
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) {
+        cudaStreamDestroy(h->stream);
+        h->own_stream = false;
+    }
+    if (cuda_stream) {
+        h->stream = (cudaStream_t)cuda_stream;
+    } else {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return 0;
+}
+
+extern "C" int spada_b200_synchronize(spada_b200_t* h) {
+    if (!h) return fail(SPADA_B200_INVALID_ARG, "handle is NULL");
+    DeviceGuard g(h->device);
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int spada_b200_trim(spada_b200_t* h) {
+    if (!h) return fail(SPADA_B200_INVALID_ARG, "handle is NULL");
+    DeviceGuard g(h->device);
+    CU(cudaStreamSynchronize(h->stream));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, h->device));
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return 0;
+}
+
+// ---- operands -----------------------------------------------------------------------------
+extern "C" int spada_b200_upload(spada_b200_t* h, const spada_csr_view* m, spada_b200_csr_t** out) {
+    if (!h || !m || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    int rc;
+    if ((rc = check_csr_args(m->rows, m->cols, m->nnz, m->indptr, m->indices, m->data))) return rc;
+    if (m->indptr[m->rows] != m->nnz)
+        return fail(SPADA_B200_INVALID_ARG, "indptr[rows] = %llu != nnz = %llu", (unsigned long long)m->indptr[m->rows],
+                    (unsigned long long)m->nnz);
+    DeviceGuard g(h->device);
+    int64_t* ptr;
+    int32_t* col;
+    double* val;
+    spada_b200_csr* c;
+    if ((rc = make_csr(h, m->rows, m->cols, m->nnz, &c, &ptr, &col, &val))) return rc;
+    // usize row pointers are bit-identical to i64 below 2^63; column ids are narrowed on the device
+    CU(cudaMemcpyAsync(ptr, m->indptr, (m->rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (m->nnz) {
+        uint64_t* tmp;
+        if ((rc = dalloc(h, &tmp, m->nnz))) return rc;
+        CU(cudaMemcpyAsync(tmp, m->indices, m->nnz * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        launch_widen_u64(nullptr, 0, nullptr, tmp, (int64_t)m->nnz, col, h->stream);
+        CU(cudaGetLastError());
+        dfree(h, tmp);
+        CU(cudaMemcpyAsync(val, m->data, m->nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->opts.flags & SPADA_B200_FLAG_VALIDATE) {
+        // a u64 column id >= 2^31 would alias after narrowing: check on the host side of the copy
+        for (uint64_t i = 0; i < m->nnz; ++i)
+            if (m->indices[i] >= m->cols) {
+                spada_b200_csr_free(c);
+                return fail(SPADA_B200_UNSORTED_INPUT, "column id %llu out of range at position %llu",
+                            (unsigned long long)m->indices[i], (unsigned long long)i);
+            }
+        if ((rc = validate_device_csr(h, c->d))) {
+            spada_b200_csr_free(c);
+            return rc;
+        }
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int spada_b200_upload32(spada_b200_t* h, const spada_csr_view32* m, spada_b200_csr_t** out) {
+    if (!h || !m || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    int rc;
+    if ((rc = check_csr_args(m->rows, m->cols, m->nnz, m->indptr, m->indices, m->data))) return rc;
+    if (m->nnz >= (1ull << 31)) return fail(SPADA_B200_TOO_LARGE, "nnz >= 2^31 needs the 64-bit view");
+    if ((uint64_t)(int64_t)m->indptr[m->rows] != m->nnz)
+        return fail(SPADA_B200_INVALID_ARG, "indptr[rows] = %d != nnz = %llu", m->indptr[m->rows],
+                    (unsigned long long)m->nnz);
+    DeviceGuard g(h->device);
+    int64_t* ptr;
+    int32_t* col;
+    double* val;
+    spada_b200_csr* c;
+    if ((rc = make_csr(h, m->rows, m->cols, m->nnz, &c, &ptr, &col, &val))) return rc;
+    int32_t* tmp;
+    if ((rc = dalloc(h, &tmp, m->rows + 1))) return rc;
+    CU(cudaMemcpyAsync(tmp, m->indptr, (m->rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    launch_widen_i32(tmp, (int64_t)m->rows + 1, ptr, h->stream);
+    CU(cudaGetLastError());
+    dfree(h, tmp);
+    if (m->nnz) {
+        CU(cudaMemcpyAsync(col, m->indices, m->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(val, m->data, m->nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->opts.flags & SPADA_B200_FLAG_VALIDATE) {
+        if ((rc = validate_device_csr(h, c->d))) {
+            spada_b200_csr_free(c);
+            return rc;
+        }
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int spada_b200_csr_wrap_device(spada_b200_t* h, uint64_t rows, uint64_t cols, uint64_t nnz,
+                                          const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                                          spada_b200_csr_t** out) {
+    if (!h || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    int rc;
+    if ((rc = check_csr_args(rows, cols, nnz, d_indptr, d_indices, d_data))) return rc;
+    spada_b200_csr* c = new (std::nothrow) spada_b200_csr;
+    if (!c) return fail(SPADA_B200_OOM, "host allocation failed");
+    c->h = h;
+    c->d = DevCsr{d_indptr, d_indices, d_data, (int64_t)rows, (int64_t)cols, (int64_t)nnz};
+    c->owned = false;
+    *out = c;
+    return 0;
+}
+
+extern "C" int spada_b200_csr_shape(const spada_b200_csr_t* m, uint64_t* rows, uint64_t* cols, uint64_t* nnz) {
+    if (!m) return fail(SPADA_B200_INVALID_ARG, "matrix is NULL");
+    if (rows) *rows = (uint64_t)m->d.rows;
+    if (cols) *cols = (uint64_t)m->d.cols;
+    if (nnz) *nnz = (uint64_t)m->d.nnz;
+    return 0;
+}
+
+extern "C" int spada_b200_csr_device_ptrs(const spada_b200_csr_t* m, const int64_t** d_indptr,
+                                          const int32_t** d_indices, const double** d_data) {
+    if (!m) return fail(SPADA_B200_INVALID_ARG, "matrix is NULL");
+    if (d_indptr) *d_indptr = m->d.ptr;
+    if (d_indices) *d_indices = m->d.col;
+    if (d_data) *d_data = m->d.val;
+    return 0;
+}
+
+extern "C" void spada_b200_csr_free(spada_b200_csr_t* m) {
+    if (!m) return;
+    if (m->owned) {
+        DeviceGuard g(m->h->device);
+        dfree(m->h, const_cast<int64_t*>(m->d.ptr));
+        dfree(m->h, const_cast<int32_t*>(m->d.col));
+        dfree(m->h, const_cast<double*>(m->d.val));
+    }
+    delete m;
+}
+
+// ---- stage 1 alone ------------------------------------------------------------------------
+namespace {
+int run_flops(spada_b200* h, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m, uint32_t* d_flops,
+              uint32_t* d_long) {
+    CU(cudaMemsetAsync(h->d_ctr, 0, sizeof(PlanCounters), h->stream));
+    launch_flops(a, b.ptr, row_begin, m, d_flops, d_long, h->d_ctr, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(PlanCounters), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+}  // namespace
+
+extern "C" int spada_b200_flops(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
+                                uint64_t* total_products, uint64_t* host_flops) {
+    if (!h || !a || !b) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    if (a->d.cols != b->d.rows)
+        return fail(SPADA_B200_DIM_MISMATCH, "A is %lld x %lld but B has %lld rows", (long long)a->d.rows,
+                    (long long)a->d.cols, (long long)b->d.rows);
+    DeviceGuard g(h->device);
+    int64_t m = a->d.rows;
+    uint32_t *d_flops, *d_long;
+    int rc;
+    if ((rc = dalloc(h, &d_flops, (size_t)m))) return rc;
+    if ((rc = dalloc(h, &d_long, (size_t)(a->d.nnz / 256 + 2)))) return rc;
+    if ((rc = run_flops(h, a->d, b->d, 0, m, d_flops, d_long))) return rc;
+    std::vector<uint32_t> tmp;
+    if (host_flops && m) {
+        tmp.resize((size_t)m);
+        CU(cudaMemcpyAsync(tmp.data(), d_flops, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, d_flops);
+    dfree(h, d_long);
+    if (total_products) *total_products = h->h_ctr->total_products;
+    if (host_flops)
+        for (int64_t i = 0; i < m; ++i) host_flops[i] = tmp[(size_t)i];
+    return 0;
+}
+
+extern "C" int spada_b200_plan_shards(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
+                                      uint32_t n_shards, uint64_t* bounds) {
+    if (!h || !a || !b || !bounds || n_shards == 0) return fail(SPADA_B200_INVALID_ARG, "bad argument");
+    uint64_t m = (uint64_t)a->d.rows;
+    std::vector<uint64_t> f((size_t)m);
+    uint64_t total = 0;
+    int rc = spada_b200_flops(h, a, b, &total, f.data());
+    if (rc) return rc;
+    // contiguous ranges with (as near as rows allow) equal intermediate-product counts; rows that
+    // produce nothing still cost their A entries, so weigh every row by flops + 1
+    uint64_t weight_total = total + m;
+    bounds[0] = 0;
+    uint64_t acc = 0, row = 0;
+    for (uint32_t s = 1; s < n_shards; ++s) {
+        uint64_t target = (uint64_t)((__uint128_t)weight_total * s / n_shards);
+        while (row < m && acc + f[(size_t)row] + 1 <= target) {
+            acc += f[(size_t)row] + 1;
+            ++row;
+        }
+        bounds[s] = row;
+    }
+    bounds[n_shards] = m;
+    return 0;
+}
+
+// ---- the hot path -------------------------------------------------------------------------
+extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
+                                     uint64_t row_begin, uint64_t row_end, spada_b200_result_t** out) {
+    if (!h || !a || !b || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    if (a->d.cols != b->d.rows)
+        return fail(SPADA_B200_DIM_MISMATCH, "A is %lld x %lld but B has %lld rows", (long long)a->d.rows,
+                    (long long)a->d.cols, (long long)b->d.rows);
+    if (row_end == UINT64_MAX) row_end = (uint64_t)a->d.rows;
+    if (row_begin > row_end || row_end > (uint64_t)a->d.rows)
+        return fail(SPADA_B200_INVALID_ARG, "row range [%llu, %llu) outside A.rows = %lld", (unsigned long long)row_begin,
+                    (unsigned long long)row_end, (long long)a->d.rows);
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    const DevCsr& A = a->d;
+    const DevCsr& B = b->d;
+    const int64_t m = (int64_t)(row_end - row_begin);
+    int rc;
+
+    spada_b200_result* R = new (std::nothrow) spada_b200_result;
+    if (!R) return fail(SPADA_B200_OOM, "host allocation failed");
+    memset(R, 0, sizeof(*R));
+    R->h = h;
+    R->rows = (uint64_t)m;
+    R->cols = (uint64_t)B.cols;
+    spada_b200_stats& st = R->stats;
+    st.rows = (uint64_t)m;
+    st.cols = (uint64_t)B.cols;
+    st.nnz_b = (uint64_t)B.nnz;
+    if ((rc = dalloc(h, &R->ptr, (size_t)m + 1))) { delete R; return rc; }
+
+    h->ev_used = 0;
+    std::vector<LaunchRec> recs;
+    auto begin_rec = [&](const char* name, int stage, uint32_t grid, uint64_t rows, uint64_t products) {
+        LaunchRec r{};
+        snprintf(r.name, sizeof(r.name), "%s", name);
+        r.stage = stage;
+        r.grid = grid;
+        r.rows = rows;
+        r.products = products;
+        r.e0 = next_event(h);
+        recs.push_back(r);
+    };
+    auto end_rec = [&]() { recs.back().e1 = next_event(h); };
+
+    uint32_t *d_flops = nullptr, *d_long = nullptr, *d_perm = nullptr, *d_nnz = nullptr;
+    uint64_t* d_tiles = nullptr;
+    uint2* d_heavy_ws = nullptr;
+    auto cleanup = [&]() {
+        dfree(h, d_flops);
+        dfree(h, d_long);
+        dfree(h, d_perm);
+        dfree(h, d_nnz);
+        dfree(h, d_tiles);
+        dfree(h, d_heavy_ws);
+    };
+#define TRY(x)                    \
+    do {                          \
+        if ((rc = (x))) {         \
+            cleanup();            \
+            spada_b200_result_free(R); \
+            return rc;            \
+        }                         \
+    } while (0)
+#define CUT(expr)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            cleanup();                                                                            \
+            spada_b200_result_free(R);                                                            \
+            return fail(e__ == cudaErrorMemoryAllocation ? SPADA_B200_OOM : SPADA_B200_CUDA_ERROR, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                         \
+    } while (0)
+
+    if (m == 0) {
+        CUT(cudaMemsetAsync(R->ptr, 0, sizeof(int64_t), s));
+        TRY(dalloc(h, &R->col, 1));
+        TRY(dalloc(h, &R->val, 1));
+        CUT(cudaStreamSynchronize(s));
+        *out = R;
+        return 0;
+    }
+
+    // ---- stage 1: flop count, bins (the window choice) --------------------------------------
+    int64_t a_nnz_shard_bound = A.nnz;  // long-row list capacity: rows longer than 256 nonzeros
+    TRY(dalloc(h, &d_flops, (size_t)m));
+    TRY(dalloc(h, &d_long, (size_t)(a_nnz_shard_bound / 256 + 2)));
+    TRY(dalloc(h, &d_perm, (size_t)m));
+    TRY(dalloc(h, &d_nnz, (size_t)m));
+    TRY(dalloc(h, &d_tiles, scan_tile_state_words(m)));
+    begin_rec("flop_count", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
+    TRY(run_flops(h, A, B, (int64_t)row_begin, m, d_flops, d_long));
+    end_rec();
+    CUT(cudaMemsetAsync(d_nnz, 0, (size_t)m * sizeof(uint32_t), s));
+    CUT(cudaStreamSynchronize(s));  // host read-back #1: bin sizes
+    PlanCounters pc = *h->h_ctr;
+    st.products = pc.total_products;
+    recs[0].products = pc.total_products;
+    BinTable tbl;
+    uint32_t off = 0;
+    for (int bnum = 0; bnum < NUM_BINS; ++bnum) {
+        tbl.offset[bnum] = off;
+        if (bnum != BIN_EMPTY) off += pc.bin_rows[bnum];
+        st.bin_rows[bnum] = pc.bin_rows[bnum];
+        st.bin_products[bnum] = pc.bin_products[bnum];
+        st.bin_window_rows[bnum] = (bnum >= 1 && bnum <= 5) ? 4u : (bnum == 0 ? 0u : 1u);
+        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : (bnum == BIN_HEAVY ? 512u : 256u));
+    }
+    tbl.offset[NUM_BINS] = off;
+    // a single non-empty bin holding every row needs no permutation
+    const uint32_t* perm_of_bin[NUM_BINS];
+    bool identity = false;
+    for (int bnum = 1; bnum < NUM_BINS; ++bnum)
+        if (pc.bin_rows[bnum] == (uint64_t)m) identity = true;
+    if (!identity && off > 0) {
+        begin_rec("bin_scatter", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
+        launch_bin_scatter(d_flops, m, tbl, d_perm, h->d_ctr, s);
+        CUT(cudaGetLastError());
+        end_rec();
+    }
+    for (int bnum = 0; bnum < NUM_BINS; ++bnum) perm_of_bin[bnum] = identity ? nullptr : d_perm + tbl.offset[bnum];
+
+    int hgrid = 0;
+    if (pc.bin_rows[BIN_HEAVY]) {
+        hgrid = heavy_grid(pc.bin_rows[BIN_HEAVY], h->sm_count, B.cols);
+        size_t words = heavy_workspace_words(hgrid, B.cols);
+        TRY(dalloc(h, &d_heavy_ws, words));
+        CUT(cudaMemsetAsync(d_heavy_ws, 0, words * sizeof(uint2), s));
+    }
+
+    // ---- stage 2: symbolic ------------------------------------------------------------------
+    for (int bnum = 1; bnum < NUM_BINS; ++bnum) {
+        uint32_t rows = pc.bin_rows[bnum];
+        if (!rows) continue;
+        char name[32];
+        snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
+        if (bnum == BIN_HEAVY) {
+            begin_rec(name, 2, (uint32_t)hgrid, rows, pc.bin_products[bnum]);
+            launch_heavy_symbolic(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, d_heavy_ws, hgrid, s);
+        } else {
+            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
+            launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
+        }
+        CUT(cudaGetLastError());
+        end_rec();
+    }
+
+    // ---- stage 4: row_ptr -------------------------------------------------------------------
+    begin_rec("row_ptr_scan", 4, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
+    launch_scan_u32_i64(d_nnz, m, R->ptr, d_tiles, h->d_ctr, s);
+    CUT(cudaGetLastError());
+    end_rec();
+    CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CUT(cudaStreamSynchronize(s));  // host read-back #2: nnz(C) sizes the output
+    const int64_t nnz_c = h->h_scalar[0];
+    R->nnz = (uint64_t)nnz_c;
+    st.nnz_c = (uint64_t)nnz_c;
+    TRY(dalloc(h, &R->col, (size_t)nnz_c));
+    TRY(dalloc(h, &R->val, (size_t)nnz_c));
+
+    // ---- stage 3: numeric -------------------------------------------------------------------
+    for (int bnum = 1; bnum < NUM_BINS; ++bnum) {
+        uint32_t rows = pc.bin_rows[bnum];
+        if (!rows) continue;
+        char name[32];
+        snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
+        if (bnum == BIN_HEAVY) {
+            begin_rec(name, 3, (uint32_t)hgrid, rows, pc.bin_products[bnum]);
+            launch_heavy_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val,
+                                 d_heavy_ws, hgrid, s);
+        } else {
+            begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
+            launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
+        }
+        CUT(cudaGetLastError());
+        end_rec();
+    }
+    cleanup();
+    CUT(cudaStreamSynchronize(s));
+    CUT(cudaGetLastError());
+
+    // ---- stats ------------------------------------------------------------------------------
+    st.nnz_a = 0;  // filled by the caller-facing wrappers when the whole of A is used
+    if (row_begin == 0 && row_end == (uint64_t)A.rows) st.nnz_a = (uint64_t)A.nnz;
+    st.n_launches = (uint32_t)recs.size() + 1;  // + k_flops_long inside flop_count
+    st.n_recorded = 0;
+    for (const LaunchRec& r : recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (r.stage == 1) st.ms_flops += ms;
+        if (r.stage == 2) st.ms_symbolic += ms;
+        if (r.stage == 3) st.ms_numeric += ms;
+        if (r.stage == 4) st.ms_scan += ms;
+        if (st.n_recorded < SPADA_B200_MAX_LAUNCHES) {
+            spada_b200_launch& L = st.launches[st.n_recorded++];
+            memcpy(L.name, r.name, sizeof(L.name));
+            L.ms = ms;
+            L.grid = r.grid;
+            L.rows = r.rows;
+            L.products = r.products;
+            L.nnz = 0;
+        }
+    }
+    if (!recs.empty()) cudaEventElapsedTime(&st.ms_total, recs.front().e0, recs.back().e1);
+#undef TRY
+#undef CUT
+    *out = R;
+    return 0;
+}
+
+namespace {
+template <typename View, typename UploadFn>
+int spgemm_host(spada_b200_t* h, const View* a, const View* b, spada_b200_result_t** out, UploadFn upload) {
+    if (!h || !a || !b || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    if (a->cols != b->rows)
+        return fail(SPADA_B200_DIM_MISMATCH, "A is %llu x %llu but B has %llu rows", (unsigned long long)a->rows,
+                    (unsigned long long)a->cols, (unsigned long long)b->rows);
+    DeviceGuard g(h->device);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    spada_b200_csr_t *da = nullptr, *db = nullptr;
+    int rc = upload(h, a, &da);
+    if (rc) return rc;
+    // the reference clones A into B for square workloads (gemm.rs:42-43); the same host arrays
+    // uploaded once are enough
+    bool alias = (const void*)a == (const void*)b ||
+                 (a->indptr == b->indptr && a->indices == b->indices && a->data == b->data && a->rows == b->rows &&
+                  a->cols == b->cols);
+    if (alias) db = da;
+    else if ((rc = upload(h, b, &db))) {
+        spada_b200_csr_free(da);
+        return rc;
+    }
+    cudaEventRecord(e1, h->stream);
+    rc = spada_b200_spgemm_dev(h, da, db, 0, UINT64_MAX, out);
+    if (rc == 0) {
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&(*out)->stats.ms_h2d, e0, e1);
+        (*out)->stats.nnz_a = a->nnz;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (db != da) spada_b200_csr_free(db);
+    spada_b200_csr_free(da);
+    return rc;
+}
+}  // namespace
+
+extern "C" int spada_b200_spgemm(spada_b200_t* h, const spada_csr_view* a, const spada_csr_view* b,
+                                 spada_b200_result_t** out) {
+    return spgemm_host(h, a, b, out, spada_b200_upload);
+}
+extern "C" int spada_b200_spgemm32(spada_b200_t* h, const spada_csr_view32* a, const spada_csr_view32* b,
+                                   spada_b200_result_t** out) {
+    return spgemm_host(h, a, b, out, spada_b200_upload32);
+}
+
+// ---- results ------------------------------------------------------------------------------
+extern "C" int spada_b200_result_shape(const spada_b200_result_t* r, uint64_t* rows, uint64_t* cols, uint64_t* nnz) {
+    if (!r) return fail(SPADA_B200_INVALID_ARG, "result is NULL");
+    if (rows) *rows = r->rows;
+    if (cols) *cols = r->cols;
+    if (nnz) *nnz = r->nnz;
+    return 0;
+}
+
+extern "C" int spada_b200_result_copy32(const spada_b200_result_t* r, int64_t* indptr, int32_t* indices, double* data) {
+    if (!r) return fail(SPADA_B200_INVALID_ARG, "result is NULL");
+    spada_b200* h = r->h;
+    DeviceGuard g(h->device);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    if (indptr) CU(cudaMemcpyAsync(indptr, r->ptr, (r->rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (indices && r->nnz) CU(cudaMemcpyAsync(indices, r->col, r->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (data && r->nnz) CU(cudaMemcpyAsync(data, r->val, r->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    cudaEventRecord(e1, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&const_cast<spada_b200_result_t*>(r)->stats.ms_d2h, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+extern "C" int spada_b200_result_copy(const spada_b200_result_t* r, uint64_t* indptr, uint64_t* indices, double* data) {
+    if (!r) return fail(SPADA_B200_INVALID_ARG, "result is NULL");
+    spada_b200* h = r->h;
+    DeviceGuard g(h->device);
+    if (indptr) CU(cudaMemcpyAsync(indptr, r->ptr, (r->rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (data && r->nnz) CU(cudaMemcpyAsync(data, r->val, r->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (indices && r->nnz) {
+        const uint64_t chunk = 1ull << 25;  // widen i32 -> usize on the device, 256 MB at a time
+        uint64_t* tmp;
+        int rc;
+        if ((rc = dalloc(h, &tmp, (size_t)std::min<uint64_t>(chunk, r->nnz)))) return rc;
+        for (uint64_t o = 0; o < r->nnz; o += chunk) {
+            uint64_t n = std::min<uint64_t>(chunk, r->nnz - o);
+            launch_narrow_result(nullptr, 0, nullptr, r->col + o, (int64_t)n, tmp, h->stream);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(indices + o, tmp, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+        }
+        dfree(h, tmp);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int spada_b200_result_device_ptrs(const spada_b200_result_t* r, const int64_t** d_indptr,
+                                             const int32_t** d_indices, const double** d_data) {
+    if (!r) return fail(SPADA_B200_INVALID_ARG, "result is NULL");
+    if (d_indptr) *d_indptr = r->ptr;
+    if (d_indices) *d_indices = r->col;
+    if (d_data) *d_data = r->val;
+    return 0;
+}
+
+extern "C" int spada_b200_result_stats(const spada_b200_result_t* r, spada_b200_stats* out) {
+    if (!r || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = r->stats;
+    return 0;
+}
+
+extern "C" void spada_b200_result_free(spada_b200_result_t* r) {
+    if (!r) return;
+    DeviceGuard g(r->h->device);
+    dfree(r->h, r->ptr);
+    dfree(r->h, r->col);
+    dfree(r->h, r->val);
+    delete r;
+}

@@ -1,0 +1,311 @@
+// plan.cu -- stage 1 (flop count + binning = the window choice) and stage 4 (row_ptr scan),
+// plus operand conversion / validation kernels.
+//
+// Reference logic replaced:
+//   * row-length tables of the scheduler (scheduler.rs:197-202) and the per-window
+//     product counts they imply (b_row_lens lookups, scheduler.rs:654),
+//   * the adaptive window shape [R, lane_num/R] of rowwise_perf_adjust.rs:121-252: there R is
+//     picked per row group from simulated latency; here each row's intermediate-product
+//     count picks the bin, and the bin fixes how many lanes cooperate on a row,
+//   * CsrMatStorage::write's indptr maintenance (storage.rs:196-210) -> exclusive scan.
+#include "common.cuh"
+
+namespace spada {
+
+constexpr int FLOPS_THREADS = 256;
+constexpr int LONG_ROW = 256;  // A rows longer than this are counted by a whole CTA
+
+// ---------------------------------------------------------------------------------------
+// K1a: one thread per A row.  HBM traffic: A.row_ptr + A.col streamed once, B.row_ptr gathered
+// (8 B x 2 per A nonzero, L2 resident for the benchmark sizes: 8(k+1) <= 34 MB).
+__global__ void __launch_bounds__(FLOPS_THREADS)
+k_flops(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin, int64_t m,
+        uint32_t* __restrict__ flops, uint32_t* __restrict__ long_list, PlanCounters* ctr) {
+    __shared__ uint32_t s_rows[NUM_BINS];
+    __shared__ unsigned long long s_prod[NUM_BINS];
+    if (threadIdx.x < NUM_BINS) {
+        s_rows[threadIdx.x] = 0;
+        s_prod[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * FLOPS_THREADS + threadIdx.x;
+    if (i < m) {
+        int64_t s = a.ptr[row_begin + i], e = a.ptr[row_begin + i + 1];
+        if (e - s > LONG_ROW) {
+            uint32_t slot = atomicAdd(&ctr->long_rows, 1u);
+            long_list[slot] = (uint32_t)i;
+        } else {
+            unsigned long long f = 0;
+            for (int64_t p = s; p < e; ++p) {
+                int32_t k = ldg_i32(a.col + p);
+                f += (unsigned long long)(ldg_i64(b_ptr + k + 1) - ldg_i64(b_ptr + k));
+            }
+            uint32_t f32 = f > 0xffffffffull ? 0xffffffffu : (uint32_t)f;
+            flops[i] = f32;
+            int b = bin_of(f32);
+            atomicAdd(&s_rows[b], 1u);
+            atomicAdd(&s_prod[b], f);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NUM_BINS && s_rows[threadIdx.x]) {
+        atomicAdd(&ctr->bin_rows[threadIdx.x], s_rows[threadIdx.x]);
+        atomicAdd(&ctr->bin_products[threadIdx.x], s_prod[threadIdx.x]);
+        atomicAdd(&ctr->total_products, s_prod[threadIdx.x]);
+    }
+}
+
+// K1b: long A rows, one CTA per row (persistent over the deferred list).
+__global__ void __launch_bounds__(FLOPS_THREADS)
+k_flops_long(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin,
+             uint32_t* __restrict__ flops, const uint32_t* __restrict__ long_list, PlanCounters* ctr) {
+    __shared__ unsigned long long s_warp[FLOPS_THREADS / 32];
+    uint32_t n_long = ctr->long_rows;
+    for (uint32_t idx = blockIdx.x; idx < n_long; idx += gridDim.x) {
+        uint32_t i = long_list[idx];
+        int64_t s = a.ptr[row_begin + i], e = a.ptr[row_begin + i + 1];
+        unsigned long long f = 0;
+        for (int64_t p = s + threadIdx.x; p < e; p += FLOPS_THREADS) {
+            int32_t k = ldg_i32(a.col + p);
+            f += (unsigned long long)(ldg_i64(b_ptr + k + 1) - ldg_i64(b_ptr + k));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
+        if (lane_id() == 0) s_warp[threadIdx.x >> 5] = f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int w = 0; w < FLOPS_THREADS / 32; ++w) t += s_warp[w];
+            uint32_t f32 = t > 0xffffffffull ? 0xffffffffu : (uint32_t)t;
+            flops[i] = f32;
+            int b = bin_of(f32);
+            atomicAdd(&ctr->bin_rows[b], 1u);
+            atomicAdd(&ctr->bin_products[b], t);
+            atomicAdd(&ctr->total_products, t);
+        }
+        __syncthreads();
+    }
+}
+
+void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t row_begin, int64_t m, uint32_t* flops,
+                  uint32_t* long_list, PlanCounters* ctr, cudaStream_t s) {
+    if (m <= 0) return;
+    unsigned grid = (unsigned)((m + FLOPS_THREADS - 1) / FLOPS_THREADS);
+    k_flops<<<grid, FLOPS_THREADS, 0, s>>>(a, b_ptr, row_begin, m, flops, long_list, ctr);
+    k_flops_long<<<148 * 4, FLOPS_THREADS, 0, s>>>(a, b_ptr, row_begin, flops, long_list, ctr);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1c: scatter row ids into per-bin lists.  One smem histogram per CTA, one global
+// reservation per (CTA, bin).
+__global__ void __launch_bounds__(256)
+k_bin_scatter(const uint32_t* __restrict__ flops, int64_t m, BinTable tbl, uint32_t* __restrict__ perm,
+              PlanCounters* ctr) {
+    __shared__ uint32_t s_cnt[NUM_BINS];
+    __shared__ uint32_t s_base[NUM_BINS];
+    if (threadIdx.x < NUM_BINS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int b = 0;
+    uint32_t rank = 0;
+    if (i < m) {
+        b = bin_of(flops[i]);
+        if (b != BIN_EMPTY) rank = atomicAdd(&s_cnt[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < NUM_BINS && threadIdx.x != BIN_EMPTY && s_cnt[threadIdx.x])
+        s_base[threadIdx.x] = tbl.offset[threadIdx.x] + atomicAdd(&ctr->bin_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (i < m && b != BIN_EMPTY) perm[s_base[b] + rank] = (uint32_t)i;
+}
+
+void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, uint32_t* perm,
+                        PlanCounters* ctr, cudaStream_t s) {
+    if (m <= 0) return;
+    unsigned grid = (unsigned)((m + 255) / 256);
+    k_bin_scatter<<<grid, 256, 0, s>>>(flops, m, tbl, perm, ctr);
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: single-pass exclusive scan (decoupled look-back), u32 per-row nnz -> i64 row_ptr.
+// HBM traffic: 4 B read + 8 B written per row.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+#define ST_AGG (1ull << 62)
+#define ST_PREFIX (2ull << 62)
+#define ST_MASK (3ull << 62)
+
+size_t scan_tile_state_words(int64_t n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1; }
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_u32_i64(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out,
+               unsigned long long* tile_state, uint32_t* ticket) {
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+
+    uint32_t v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(in + base);
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS / 4; ++j) {
+            uint4 q = p4[j];
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (base + j < n) ? in[base + j] : 0u;
+    }
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) tsum += v[j];
+    // warp inclusive scan of the per-thread sums
+    unsigned long long x = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    unsigned long long warp_off = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        unsigned long long t = s_warp[w];
+        if (w < warp) warp_off += t;
+        tile_total += t;
+    }
+    // look-back by warp 0
+    if (warp == 0) {
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(&tile_state[0], ST_PREFIX | tile_total);
+        } else {
+            if (lane == 0) atomicExch(&tile_state[tile], ST_AGG | tile_total);
+            int64_t p = (int64_t)tile - 1;
+            while (true) {
+                int64_t idx = p - lane;
+                unsigned long long s;
+                do {
+                    s = (idx >= 0) ? *((volatile unsigned long long*)&tile_state[idx]) : ST_PREFIX;
+                } while (__any_sync(FULL, (s & ST_MASK) == 0));
+                unsigned has_prefix = __ballot_sync(FULL, (s & ST_MASK) == ST_PREFIX);
+                unsigned long long val = s & ~ST_MASK;
+                if (has_prefix) {
+                    int first = __ffs(has_prefix) - 1;
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
+                excl += val;
+                if (has_prefix) break;
+                p -= 32;
+            }
+            if (lane == 0) atomicExch(&tile_state[tile], ST_PREFIX | (excl + tile_total));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    unsigned long long run = s_excl + warp_off + (x - tsum);
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        if (base + j < n) {
+            out[base + j] = (int64_t)run;
+            run += v[j];
+            if (base + j == n - 1) out[n] = (int64_t)run;
+        }
+    }
+}
+
+void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out, uint64_t* tile_state,
+                         PlanCounters* ctr, cudaStream_t s) {
+    if (n <= 0) {
+        cudaMemsetAsync(out, 0, sizeof(int64_t), s);
+        return;
+    }
+    size_t tiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
+    cudaMemsetAsync(&ctr->scan_ticket, 0, sizeof(uint32_t), s);
+    k_scan_u32_i64<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(in, n, out, (unsigned long long*)tile_state,
+                                                            &ctr->scan_ticket);
+}
+
+// ---------------------------------------------------------------------------------------
+// operand conversion: the reference holds usize (u64) indices (storage.rs:150-160); the device
+// layout is i64 row_ptr / i32 col (12 B per nonzero instead of 16).
+__global__ void k_narrow_u64_i32(const uint64_t* __restrict__ src, int64_t n, int32_t* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (int32_t)src[i];
+}
+__global__ void k_widen_i32_i64(const int32_t* __restrict__ src, int64_t n, int64_t* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (int64_t)src[i];
+}
+__global__ void k_widen_i32_u64(const int32_t* __restrict__ src, int64_t n, uint64_t* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (uint64_t)(uint32_t)src[i];
+}
+static unsigned grid_for(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+void launch_widen_u64(const uint64_t*, int64_t, int64_t*, const uint64_t* src_idx, int64_t nnz,
+                      int32_t* dst_idx, cudaStream_t s) {
+    if (nnz > 0) k_narrow_u64_i32<<<grid_for(nnz), 256, 0, s>>>(src_idx, nnz, dst_idx);
+}
+void launch_widen_i32(const int32_t* src_ptr, int64_t n_ptr, int64_t* dst_ptr, cudaStream_t s) {
+    if (n_ptr > 0) k_widen_i32_i64<<<grid_for(n_ptr), 256, 0, s>>>(src_ptr, n_ptr, dst_ptr);
+}
+void launch_narrow_result(const int64_t*, int64_t, uint64_t*, const int32_t* idx, int64_t nnz,
+                          uint64_t* out_idx, cudaStream_t s) {
+    if (nnz > 0) k_widen_i32_u64<<<grid_for(nnz), 256, 0, s>>>(idx, nnz, out_idx);
+}
+
+// ---------------------------------------------------------------------------------------
+// canonical-CSR validation (SURVEY.md 8a edge cases: the reference's sort/merge units assume
+// ascending unique columns, simulator.rs:28, adder_tree.rs:182).  nnz-parallel: every
+// descent col[p] <= col[p-1] must coincide with the first stored element of a non-empty row.
+__global__ void k_validate_nnz(DevCsr a, PlanCounters* ctr) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t bad = 0, descents = 0;
+    for (; p < a.nnz; p += stride) {
+        int32_t c = a.col[p];
+        if (c < 0 || c >= a.cols) ++bad;
+        if (p > 0 && c <= a.col[p - 1]) ++descents;
+    }
+    if (bad) atomicAdd(&ctr->invalid_rows, bad);
+    if (descents) atomicAdd(&ctr->long_rows, descents);  // long_rows reused as the descent counter
+}
+__global__ void k_validate_rows(DevCsr a, PlanCounters* ctr) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t bad = 0, starts = 0;
+    for (; i < a.rows; i += stride) {
+        int64_t s = a.ptr[i], e = a.ptr[i + 1];
+        if (e < s || s < 0 || e > a.nnz) { ++bad; continue; }
+        if (i == 0 && s != 0) ++bad;
+        if (i == a.rows - 1 && e != a.nnz) ++bad;
+        if (e > s && s > 0 && a.col[s] <= a.col[s - 1]) ++starts;
+    }
+    if (bad) atomicAdd(&ctr->invalid_rows, bad);
+    if (starts) atomicAdd(&ctr->scan_ticket, starts);  // scan_ticket reused as the allowed-descent counter
+}
+void launch_validate(const DevCsr& a, PlanCounters* ctr, cudaStream_t s) {
+    // caller zeroes *ctr first and afterwards checks invalid_rows == 0 && long_rows == scan_ticket
+    if (a.nnz > 0) k_validate_nnz<<<grid_for(a.nnz), 256, 0, s>>>(a, ctr);
+    if (a.rows > 0) k_validate_rows<<<grid_for(a.rows), 256, 0, s>>>(a, ctr);
+}
+
+}  // namespace spada

@@ -1,0 +1,135 @@
+"""Multi-GPU plumbing for the row-sharded path: one process per GPU,
+torch.distributed (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+
+  * B (and A) replicated from rank 0 with ``dist.broadcast``            -> ``broadcast_csr``
+  * A row-sharded into contiguous ranges of equal intermediate-product
+    count: the C ABI's ``spada_b200_plan_shards`` on rank 0, broadcast   -> ``plan_bounds``
+  * C shards all-gathered in place at their final offsets
+    (NCCL has no all-gather-v: one broadcast per shard)                 -> ``allgather_csr``
+
+torch is plumbing only (device memory views, streams, collectives); every SpGEMM kernel is in
+libspada_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _DevArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, owner=None):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr if n else 0, False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+def device_view(ptr: int, n: int, dtype: torch.dtype, device, owner=None) -> torch.Tensor:
+    """Zero-copy torch view of ``n`` elements at device address ``ptr`` (kept alive by ``owner``)."""
+    if n == 0:
+        return torch.empty(0, dtype=dtype, device=device)
+    typestr = {torch.int64: "<i8", torch.int32: "<i4", torch.float64: "<f8"}[dtype]
+    t = torch.as_tensor(_DevArray(ptr, n, typestr, owner), device=device)
+    t._spada_owner = owner
+    return t
+
+
+def result_views(result, device):
+    """(row_ptr int64 [rows+1], col int32 [nnz], val float64 [nnz]) views of an engine Result."""
+    p, c, v = result.device_ptrs()
+    rows = result.shape[0]
+    return (device_view(p, rows + 1, torch.int64, device, result), device_view(c, result.nnz, torch.int32, device, result),
+            device_view(v, result.nnz, torch.float64, device, result))
+
+
+def broadcast_csr(engine, mat, device, src: int = 0, group=None):
+    """Replicate a host scipy CSR held by ``src`` to every rank's device.  Returns
+    (DeviceCsr, (ptr, col, val) tensors).  Device layout: i64 row_ptr, i32 col, f64 val."""
+    rank = dist.get_rank(group)
+    meta = [None]
+    if rank == src:
+        meta = [(int(mat.shape[0]), int(mat.shape[1]), int(mat.nnz))]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    rows, cols, nnz = meta[0]
+    if rank == src:
+        ptr = torch.from_numpy(np.ascontiguousarray(mat.indptr, dtype=np.int64)).to(device)
+        col = torch.from_numpy(np.ascontiguousarray(mat.indices, dtype=np.int32)).to(device)
+        val = torch.from_numpy(np.ascontiguousarray(mat.data, dtype=np.float64)).to(device)
+    else:
+        ptr = torch.empty(rows + 1, dtype=torch.int64, device=device)
+        col = torch.empty(nnz, dtype=torch.int32, device=device)
+        val = torch.empty(nnz, dtype=torch.float64, device=device)
+    for t in (ptr, col, val):
+        dist.broadcast(t, src=src, group=group)
+    if engine is None:  # CPU tests
+        return None, (ptr, col, val)
+    torch.cuda.current_stream().synchronize()
+    d = engine.wrap_device(rows, cols, nnz, ptr.data_ptr(), col.data_ptr(), val.data_ptr(), keepalive=(ptr, col, val))
+    return d, (ptr, col, val)
+
+
+def balanced_bounds(weights: np.ndarray, n_shards: int) -> np.ndarray:
+    """Host restatement of spada_b200_plan_shards' split rule (weights = flops + 1 per row); used by
+    the CPU tests to check the C ABI's answer and by the gloo tests to shard without a GPU."""
+    total = int(weights.sum())
+    csum = np.concatenate([[0], np.cumsum(weights.astype(np.int64))])
+    bounds = [0]
+    for s in range(1, n_shards):
+        target = total * s // n_shards
+        bounds.append(int(np.searchsorted(csum, target, side="right") - 1))
+    bounds.append(len(weights))
+    return np.asarray(bounds, dtype=np.int64)
+
+
+def plan_bounds(engine, da, db, world: int, device, src: int = 0, group=None) -> np.ndarray:
+    rank = dist.get_rank(group)
+    t = torch.zeros(world + 1, dtype=torch.int64, device=device)
+    if rank == src:
+        t.copy_(torch.from_numpy(engine.plan_shards(da, db, world)))
+    dist.broadcast(t, src=src, group=group)
+    return t.cpu().numpy()
+
+
+def allgather_csr(local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: torch.Tensor,
+                  group=None, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+    """All ranks end with the whole C.  Shard r holds rows [b_r, b_{r+1}) with a row_ptr that
+    starts at 0; the global row_ptr is local + (nnz of the shards before)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = local_ptr.device
+    mine = torch.tensor([local_ptr.numel() - 1, local_col.numel()], dtype=torch.int64, device=dev)
+    sizes = torch.empty(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, mine, group=group)
+    sizes = sizes.view(world, 2).cpu()
+    rows = sizes[:, 0].tolist()
+    nnzs = sizes[:, 1].tolist()
+    row_off = np.concatenate([[0], np.cumsum(rows)])
+    nnz_off = np.concatenate([[0], np.cumsum(nnzs)])
+    if out is None:
+        out = (torch.empty(int(row_off[-1]) + 1, dtype=torch.int64, device=dev),
+               torch.empty(int(nnz_off[-1]), dtype=torch.int32, device=dev),
+               torch.empty(int(nnz_off[-1]), dtype=torch.float64, device=dev))
+    g_ptr, g_col, g_val = out
+    g_ptr[:1] = 0
+    r0, n0 = int(row_off[rank]), int(nnz_off[rank])
+    g_ptr[r0 + 1:r0 + 1 + rows[rank]] = local_ptr[1:] + n0
+    g_col[n0:n0 + nnzs[rank]] = local_col
+    g_val[n0:n0 + nnzs[rank]] = local_val
+    works = []
+    for r in range(world):
+        rs, ns = int(row_off[r]), int(nnz_off[r])
+        if rows[r]:
+            works.append(dist.broadcast(g_ptr[rs + 1:rs + 1 + rows[r]], src=dist.get_global_rank(group, r) if group else r,
+                                        group=group, async_op=True))
+        if nnzs[r]:
+            works.append(dist.broadcast(g_col[ns:ns + nnzs[r]], src=dist.get_global_rank(group, r) if group else r,
+                                        group=group, async_op=True))
+            works.append(dist.broadcast(g_val[ns:ns + nnzs[r]], src=dist.get_global_rank(group, r) if group else r,
+                                        group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return g_ptr, g_col, g_val

@@ -1,0 +1,225 @@
+"""Python host mirror over the C ABI: handles, device operands, results.
+
+Everything here is plumbing around libspada_b200.so (ctypes); all arithmetic happens in the
+CUDA kernels.  The object model follows include/spada_b200.h one to one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _abi
+from ._abi import check, lib
+
+U64_MAX = (1 << 64) - 1
+BIN_NAMES = ["empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy"]
+
+
+def _ptr(a: np.ndarray, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+class DeviceCsr:
+    """A CSR operand resident on the device (spada_b200_csr_t)."""
+
+    def __init__(self, engine: "Engine", handle: C.c_void_p, keepalive=None):
+        self.engine = engine
+        self._h = handle
+        self._keep = keepalive
+        r, c, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().spada_b200_csr_shape(self._h, C.byref(r), C.byref(c), C.byref(n)))
+        self.shape = (r.value, c.value)
+        self.nnz = n.value
+
+    def device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().spada_b200_csr_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def free(self):
+        if self._h is not None:
+            lib().spada_b200_csr_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Result:
+    """C = A x B resident on the device (spada_b200_result_t)."""
+
+    def __init__(self, engine: "Engine", handle: C.c_void_p):
+        self.engine = engine
+        self._h = handle
+        r, c, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().spada_b200_result_shape(self._h, C.byref(r), C.byref(c), C.byref(n)))
+        self.shape = (r.value, c.value)
+        self.nnz = n.value
+
+    def stats(self) -> dict:
+        st = _abi.Stats()
+        check(lib().spada_b200_result_stats(self._h, C.byref(st)))
+        out = {k: getattr(st, k) for k in ("rows", "cols", "nnz_a", "nnz_b", "products", "nnz_c", "ms_total",
+                                            "ms_flops", "ms_symbolic", "ms_scan", "ms_numeric", "ms_h2d", "ms_d2h",
+                                            "n_launches")}
+        out["bins"] = {BIN_NAMES[i]: {"rows": st.bin_rows[i], "products": st.bin_products[i],
+                                      "window": [st.bin_window_rows[i], st.bin_window_lanes[i]]}
+                       for i in range(len(BIN_NAMES)) if st.bin_rows[i]}
+        out["launches"] = [{"name": st.launches[i].name.decode(), "ms": st.launches[i].ms,
+                            "grid": st.launches[i].grid, "rows": st.launches[i].rows,
+                            "products": st.launches[i].products} for i in range(st.n_recorded)]
+        return out
+
+    def device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().spada_b200_result_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def to_host(self, out=None):
+        """(indptr int64, indices int32, data float64) on the host; `out` = preallocated triple."""
+        if out is None:
+            out = (np.empty(self.shape[0] + 1, dtype=np.int64), np.empty(self.nnz, dtype=np.int32),
+                   np.empty(self.nnz, dtype=np.float64))
+        ip, ix, dx = out
+        check(lib().spada_b200_result_copy32(self._h, _ptr(ip, C.c_int64), _ptr(ix, C.c_int32), _ptr(dx, C.c_double)))
+        return ip, ix, dx
+
+    def to_host_usize(self):
+        """The reference's layout: usize indptr / usize indices / f64 data (storage.rs:150-160)."""
+        ip = np.empty(self.shape[0] + 1, dtype=np.uint64)
+        ix = np.empty(self.nnz, dtype=np.uint64)
+        dx = np.empty(self.nnz, dtype=np.float64)
+        check(lib().spada_b200_result_copy(self._h, _ptr(ip, C.c_uint64), _ptr(ix, C.c_uint64), _ptr(dx, C.c_double)))
+        return ip, ix, dx
+
+    def to_scipy(self) -> sp.csr_matrix:
+        ip, ix, dx = self.to_host()
+        return sp.csr_matrix((dx, ix, ip), shape=self.shape)
+
+    def free(self):
+        if self._h is not None:
+            lib().spada_b200_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One engine handle = one device + stream + memory pool (spada_b200_t)."""
+
+    def __init__(self, device: int = -1, accelerator: str = "spada", lane_num: int = 8,
+                 block_shape=(1, 10000000), validate: bool = True, stream: Optional[int] = None):
+        opts = _abi.Opts()
+        opts.device = device
+        opts.accelerator = _abi.ACCELERATORS[accelerator.lower()]
+        opts.lane_num = lane_num
+        opts.block_shape[0] = min(int(block_shape[0]), 0xffffffff)
+        opts.block_shape[1] = min(int(block_shape[1]), 0xffffffff)
+        opts.flags = _abi.FLAG_VALIDATE if validate else 0
+        opts.stream = stream
+        h = C.c_void_p()
+        check(lib().spada_b200_create(C.byref(opts), C.byref(h)))
+        self._h = h
+
+    # -- lifetime --
+    def close(self):
+        if self._h is not None:
+            lib().spada_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream: Optional[int]):
+        check(lib().spada_b200_set_stream(self._h, stream))
+
+    def synchronize(self):
+        check(lib().spada_b200_synchronize(self._h))
+
+    def trim(self):
+        check(lib().spada_b200_trim(self._h))
+
+    # -- operands --
+    @staticmethod
+    def _view32(m: sp.csr_matrix):
+        ip = np.ascontiguousarray(m.indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(m.indices, dtype=np.int32)
+        dx = np.ascontiguousarray(m.data, dtype=np.float64)
+        v = _abi.CsrView32(m.shape[0], m.shape[1], int(ip[-1]) if len(ip) else 0, _ptr(ip, C.c_int32),
+                           _ptr(ix, C.c_int32), _ptr(dx, C.c_double))
+        return v, (ip, ix, dx)
+
+    @staticmethod
+    def _view64(m: sp.csr_matrix):
+        ip = np.ascontiguousarray(m.indptr, dtype=np.uint64)
+        ix = np.ascontiguousarray(m.indices, dtype=np.uint64)
+        dx = np.ascontiguousarray(m.data, dtype=np.float64)
+        v = _abi.CsrView(m.shape[0], m.shape[1], int(ip[-1]) if len(ip) else 0, _ptr(ip, C.c_uint64),
+                         _ptr(ix, C.c_uint64), _ptr(dx, C.c_double))
+        return v, (ip, ix, dx)
+
+    def upload(self, m: sp.csr_matrix, usize: bool = False) -> DeviceCsr:
+        """Host CSR -> device.  usize=True goes through the reference's Vec<usize> layout."""
+        out = C.c_void_p()
+        if usize or m.nnz >= (1 << 31):
+            v, keep = self._view64(m)
+            check(lib().spada_b200_upload(self._h, C.byref(v), C.byref(out)))
+        else:
+            v, keep = self._view32(m)
+            check(lib().spada_b200_upload32(self._h, C.byref(v), C.byref(out)))
+        return DeviceCsr(self, out)
+
+    def wrap_device(self, rows, cols, nnz, d_indptr: int, d_indices: int, d_data: int, keepalive=None) -> DeviceCsr:
+        out = C.c_void_p()
+        check(lib().spada_b200_csr_wrap_device(self._h, rows, cols, nnz, d_indptr, d_indices, d_data, C.byref(out)))
+        return DeviceCsr(self, out, keepalive)
+
+    # -- the hot path --
+    def spgemm_dev(self, a: DeviceCsr, b: DeviceCsr, row_begin: int = 0, row_end: Optional[int] = None) -> Result:
+        out = C.c_void_p()
+        check(lib().spada_b200_spgemm_dev(self._h, a._h, b._h, row_begin, U64_MAX if row_end is None else row_end,
+                                          C.byref(out)))
+        return Result(self, out)
+
+    def spgemm(self, a: sp.csr_matrix, b: sp.csr_matrix, usize: bool = False) -> Result:
+        """Host operands in, device result out, through the host-level ABI entry point."""
+        out = C.c_void_p()
+        if usize:
+            va, ka = self._view64(a)
+            vb, kb = (va, ka) if b is a else self._view64(b)
+            check(lib().spada_b200_spgemm(self._h, C.byref(va), C.byref(vb), C.byref(out)))
+        else:
+            va, ka = self._view32(a)
+            vb, kb = (va, ka) if b is a else self._view32(b)
+            check(lib().spada_b200_spgemm32(self._h, C.byref(va), C.byref(vb), C.byref(out)))
+        return Result(self, out)
+
+    def flops(self, a: DeviceCsr, b: DeviceCsr, per_row: bool = False):
+        total = C.c_uint64()
+        arr = np.zeros(a.shape[0], dtype=np.uint64) if per_row else None
+        check(lib().spada_b200_flops(self._h, a._h, b._h, C.byref(total), _ptr(arr, C.c_uint64) if per_row else None))
+        return (total.value, arr) if per_row else total.value
+
+    def plan_shards(self, a: DeviceCsr, b: DeviceCsr, n_shards: int) -> np.ndarray:
+        bounds = np.zeros(n_shards + 1, dtype=np.uint64)
+        check(lib().spada_b200_plan_shards(self._h, a._h, b._h, n_shards, _ptr(bounds, C.c_uint64)))
+        return bounds.astype(np.int64)
+
+
+def device_count() -> int:
+    n = C.c_int()
+    rc = lib().spada_b200_device_count(C.byref(n))
+    return n.value if rc == 0 else 0

@@ -1,0 +1,279 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle -- needs a B200.
+
+Bar: row_ptr and col_idx bit-exact; values within relative 1e-12 per
+entry in f64 (TOL below).  The sort-based bins (<= 4096 intermediate products per row) fix the
+oracle's summation order, so there the values are checked bit-exact as well.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN, random_csr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # relative, per entry (north_star)
+
+
+def check(result, ref, exact_values):
+    ip, ix, dx = result.to_host()
+    cp, cj, cx = ref
+    assert ip.dtype == np.int64 and ix.dtype == np.int32 and dx.dtype == np.float64
+    assert np.array_equal(ip, cp), "row_ptr differs"
+    assert np.array_equal(ix, cj), "col_idx differs"
+    if exact_values:
+        same = (dx.view(np.uint64) == cx.view(np.uint64)) | (np.isnan(dx) & np.isnan(cx))
+        assert same.all(), f"{(~same).sum()} values differ in bits"
+    else:
+        finite = np.isfinite(cx)
+        assert np.array_equal(np.isnan(dx), np.isnan(cx))
+        assert np.array_equal(dx[~finite & ~np.isnan(cx)], cx[~finite & ~np.isnan(cx)])
+        err = np.abs(dx[finite] - cx[finite])
+        assert (err <= TOL * np.abs(cx[finite])).all(), f"max rel err {np.max(err / np.maximum(np.abs(cx[finite]), 1e-300))}"
+
+
+def run(engine, oracle, a, b, exact=True, usize=False):
+    r = engine.spgemm(a, b, usize=usize)
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    check(r, ref, exact)
+    st = r.stats()
+    assert st["nnz_c"] == len(ref[1])
+    assert st["products"] == int(oracle.flops(a, b).sum())
+    return r, st
+
+
+# ---- every bin, forced individually ---------------------------------------------------------
+@pytest.mark.parametrize("ka,lb,expect_bin", [
+    (1, 1, "32"), (4, 8, "32"), (5, 5, "32"), (8, 8, "64"), (10, 12, "128"), (16, 16, "256"),
+    (20, 25, "512"), (32, 32, "1024"), (40, 50, "2048"), (64, 64, "4096"), (70, 100, "heavy"),
+    (300, 40, "heavy"),
+])
+def test_each_bin(engine, oracle, ka, lb, expect_bin):
+    m, k, n = 257, 600, 5000
+    vals = "uniform" if expect_bin == "heavy" else "signed"   # heavy bin: order not fixed -> no cancellation
+    a = random_csr(m, k, row_nnz=ka, seed=ka * 7 + lb, values=vals)
+    b = random_csr(k, n, row_nnz=lb, seed=ka * 11 + lb, values=vals)
+    _, st = run(engine, oracle, a, b, exact=(expect_bin != "heavy"))
+    assert list(st["bins"].keys()) == [expect_bin], st["bins"]
+    assert st["bins"][expect_bin]["rows"] == m
+
+
+@pytest.mark.parametrize("n_cols", [1 << 10, 1 << 21, (1 << 28) + 5])
+def test_key_width_paths(engine, oracle, n_cols):
+    # 32-bit packed (column, arrival) keys when they fit, 64-bit keys otherwise
+    for ka, lb in [(4, 6), (16, 16), (40, 50)]:
+        a = random_csr(130, 300, row_nnz=ka, seed=3)
+        b = random_csr(300, n_cols, row_nnz=lb, seed=4)
+        run(engine, oracle, a, b)
+
+
+def test_mixed_bins_and_permutation(engine, oracle):
+    rng = np.random.default_rng(5)
+    lens = rng.choice([0, 1, 3, 8, 20, 60, 150, 400], size=3000, p=[.1, .2, .2, .2, .15, .1, .04, .01])
+    a = random_csr(3000, 2000, row_nnz=lens, seed=6)
+    b = random_csr(2000, 4000, row_nnz=rng.choice([0, 2, 9, 30], size=2000), seed=7)
+    r = engine.spgemm(a, b)
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    st = r.stats()
+    ip, ix, dx = r.to_host()
+    assert np.array_equal(ip, ref[0]) and np.array_equal(ix, ref[1])
+    assert len(st["bins"]) >= 5
+    # rows handled by the sort-based bins are bit-exact; the heavy bin is within TOL
+    f = oracle.flops(a, b)
+    light = np.repeat(f <= 4096, np.diff(ref[0]))
+    assert np.array_equal(dx[light].view(np.uint64), ref[2][light].view(np.uint64))
+    assert (np.abs(dx[~light] - ref[2][~light]) <= TOL * np.abs(ref[2][~light])).all()
+
+
+# ---- the reference's own operand ------------------------------------------------------------
+def test_cari_golden(engine, oracle, cari, spada):
+    known = json.load(open(os.path.join(GOLDEN, "cari_known_answers.json")))
+    g = spada.GEMM.from_mat("cari", cari)
+    assert g.b.shape == (1200, 400)
+    r, st = run(engine, oracle, g.a, g.b, exact=False)  # 144k products per row -> heavy bin
+    ip, ix, dx = r.to_host()
+    sha = lambda x: hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()
+    assert sha(ip.astype("<i8")) == known["sha256_indptr_i64"]
+    assert sha(ix.astype("<i8")) == known["sha256_indices_i64"]
+    assert st["products"] == known["products"] and st["nnz_c"] == known["c_nnz"]
+    assert abs(dx.sum() - known["c_data_sum"]) <= 1e-9
+    assert np.allclose(dx[:5], known["row0_vals"], rtol=TOL, atol=0)
+
+
+# ---- edge cases of SURVEY.md 8a ---------------------------------------------------------------
+def test_empty_rows_empty_b_rows_explicit_zeros(engine, oracle):
+    a = sp.csr_matrix((np.array([0.0, 1.0, 1.0, 2.0]), np.array([0, 0, 1, 2]), np.array([0, 0, 1, 3, 4])), shape=(4, 3))
+    b = sp.csr_matrix((np.array([2.0, 3.0, -3.0]), np.array([0, 1, 1]), np.array([0, 2, 3, 3])), shape=(3, 2))
+    r, _ = run(engine, oracle, a, b)
+    ip, ix, dx = r.to_host()
+    assert ip.tolist() == [0, 0, 2, 4, 4]          # row 0 empty; row 3 only hits the empty B row
+    assert dx.tolist() == [0.0, 0.0, 2.0, 0.0]     # explicit / cancelled zeros stay structural
+
+
+def test_zero_sized(engine, oracle, spada):
+    a = sp.csr_matrix((0, 5)); b = sp.csr_matrix((5, 7))
+    r = engine.spgemm(a, b)
+    assert r.shape == (0, 7) and r.nnz == 0 and r.to_host()[0].tolist() == [0]
+    a = sp.csr_matrix((6, 5)); r = engine.spgemm(a, b)
+    assert r.nnz == 0 and r.to_host()[0].tolist() == [0] * 7
+    a = sp.csr_matrix((3, 0)); b = sp.csr_matrix((0, 4))
+    assert engine.spgemm(a, b).nnz == 0
+
+
+def test_nan_inf_propagate(engine, oracle):
+    a = sp.csr_matrix((np.array([np.nan, np.inf, 1.0]), np.array([0, 1, 1]), np.array([0, 1, 2, 3])), shape=(3, 2))
+    b = sp.csr_matrix((np.array([1.0, -1.0, 0.0]), np.array([0, 0, 1]), np.array([0, 1, 3])), shape=(2, 2))
+    run(engine, oracle, a, b)
+
+
+def test_no_fma(engine, oracle):
+    a1 = 1.0 + 2.0 ** -30
+    a = sp.csr_matrix((np.array([a1, 1.0]), np.array([0, 1]), np.array([0, 2])), shape=(1, 2))
+    b = sp.csr_matrix((np.array([a1, -1.0]), np.array([0, 0]), np.array([0, 1, 2])), shape=(2, 1))
+    r, _ = run(engine, oracle, a, b)
+    assert r.to_host()[2][0] == np.float64(a1 * a1) + np.float64(-1.0)
+
+
+def test_errors(engine, spada):
+    a = random_csr(10, 7, density=0.3, seed=1)
+    b = random_csr(8, 5, density=0.3, seed=2)
+    with pytest.raises(spada.SpadaB200Error) as e:
+        engine.spgemm(a, b)
+    assert e.value.status == "DIM_MISMATCH"
+    bad = random_csr(10, 8, row_nnz=4, seed=3)
+    s = bad.indptr[2]
+    bad.indices[s], bad.indices[s + 1] = bad.indices[s + 1], bad.indices[s]
+    for usize in (False, True):
+        with pytest.raises(spada.SpadaB200Error) as e:
+            engine.spgemm(bad, b, usize=usize)
+        assert e.value.status == "UNSORTED_INPUT"
+    dup = random_csr(10, 8, row_nnz=4, seed=3)
+    dup.indices[dup.indptr[5] + 1] = dup.indices[dup.indptr[5]]
+    with pytest.raises(spada.SpadaB200Error) as e:
+        engine.upload(dup)
+    assert e.value.status == "UNSORTED_INPUT"
+    oob = random_csr(10, 8, row_nnz=2, seed=4)
+    oob.indices[-1] = 8
+    with pytest.raises(spada.SpadaB200Error):
+        engine.upload(oob)
+
+
+def test_long_rows_and_first_last(engine, oracle):
+    # one A row far longer than 256 nonzeros (CTA-per-row flop counter), first and last rows non-trivial
+    lens = np.full(64, 3); lens[0] = 1500; lens[-1] = 700; lens[10] = 0
+    a = random_csr(64, 4000, row_nnz=lens, seed=8)
+    b = random_csr(4000, 30000, row_nnz=np.random.default_rng(9).integers(0, 12, size=4000), seed=10)
+    run(engine, oracle, a, b, exact=False)
+
+
+def test_many_empty_b_rows_in_a_row(engine, oracle):
+    # an A row with > 32 nonzeros whose B rows are mostly empty: products <= 32 but several expansion batches
+    a = random_csr(40, 500, row_nnz=100, seed=11)
+    lb = np.zeros(500, dtype=np.int64); lb[::37] = 2
+    b = random_csr(500, 64, row_nnz=lb, seed=12)
+    _, st = run(engine, oracle, a, b)
+    assert set(st["bins"]) <= {"empty", "32"}
+
+
+def test_high_compression_row(engine, oracle):
+    # every product of a row lands on few columns (long equal-column runs in the segmented sum)
+    a = random_csr(50, 64, row_nnz=60, seed=13, values="signed")
+    b = random_csr(64, 8, row_nnz=8, seed=14, values="signed")
+    run(engine, oracle, a, b)
+    b2 = random_csr(64, 40, row_nnz=40, seed=15, values="signed")   # 2400 products -> 40 outputs
+    run(engine, oracle, a, b2)
+
+
+def test_usize_layout_matches(engine, oracle):
+    a = random_csr(300, 200, density=0.05, seed=16)
+    b = random_csr(200, 250, density=0.05, seed=17)
+    r32 = engine.spgemm(a, b)
+    r64 = engine.spgemm(a, b, usize=True)
+    ip, ix, dx = r64.to_host_usize()
+    jp, jx, ex = r32.to_host()
+    assert ip.dtype == np.uint64 and ix.dtype == np.uint64
+    assert np.array_equal(ip.astype(np.int64), jp) and np.array_equal(ix.astype(np.int32), jx)
+    assert np.array_equal(dx, ex)
+
+
+def test_square_alias_a_times_a(engine, oracle):
+    a = random_csr(500, 500, density=0.02, seed=18)
+    run(engine, oracle, a, a)
+
+
+def test_row_shards_concatenate(engine, oracle):
+    a = random_csr(1000, 800, density=0.01, seed=19)
+    b = random_csr(800, 900, density=0.01, seed=20)
+    da, db = engine.upload(a), engine.upload(b)
+    full = engine.spgemm_dev(da, db).to_host()
+    bounds = engine.plan_shards(da, db, 4)
+    assert bounds[0] == 0 and bounds[-1] == 1000 and np.all(np.diff(bounds) >= 0)
+    total, f = engine.flops(da, db, per_row=True)
+    assert np.array_equal(f.astype(np.int64), oracle.flops(a, b)) and total == f.sum()
+    w = f.astype(np.int64) + 1
+    shard_w = [w[bounds[i]:bounds[i + 1]].sum() for i in range(4)]
+    assert max(shard_w) - min(shard_w) <= 2 * w.max()
+    parts = [engine.spgemm_dev(da, db, int(bounds[i]), int(bounds[i + 1])).to_host() for i in range(4)]
+    ip = np.concatenate([[0]] + [p[0][1:] + off for p, off in
+                                 zip(parts, np.cumsum([0] + [p[0][-1] for p in parts[:-1]]))])
+    assert np.array_equal(ip, full[0])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), full[2])
+
+
+# ---- BASELINE configs, scaled down, against the oracle ------------------------------------------
+@pytest.mark.parametrize("name,scale,exact", [("poisson", 1 / 16, True), ("er", 1 / 64, True),
+                                              ("rmat", 1 / 128, False), ("rect", 1 / 64, False)])
+def test_configs_scaled(engine, oracle, spada, name, scale, exact):
+    a, b = spada.workloads.build(name, scale)
+    run(engine, oracle, a, b, exact=exact)
+
+
+# ---- full size: properties that need no CPU product ------------------------------------------------
+def _linearity(a, b, ip, ix, dx):
+    # C 1 = A (B 1), row by row
+    lhs = np.add.reduceat(np.append(dx, 0.0), ip[:-1])
+    lhs[np.diff(ip) == 0] = 0.0
+    rhs = a @ np.asarray(b.sum(axis=1)).ravel()
+    assert np.allclose(lhs, rhs, rtol=1e-9, atol=1e-12)
+
+
+def test_poisson_full_size(engine, spada):
+    a, b = spada.workloads.build("poisson")
+    m, k, nnz_a, products, nnz_c = spada.workloads.KNOWN["poisson"]
+    r = engine.spgemm(a, b)
+    st = r.stats()
+    assert st["products"] == products and st["nnz_c"] == nnz_c
+    ip, ix, dx = r.to_host()
+    ref = (a @ b).tocsr(); ref.sort_indices()   # exact small integers: any association is bit-identical
+    assert np.array_equal(ip, ref.indptr) and np.array_equal(ix, ref.indices) and np.array_equal(dx, ref.data)
+
+
+def test_rect_full_size_properties(engine, spada):
+    a, b = spada.workloads.build("rect")
+    m, k, nnz_a, products, nnz_c = spada.workloads.KNOWN["rect"]
+    assert a.nnz == nnz_a
+    r = engine.spgemm(a, b)
+    st = r.stats()
+    assert st["products"] == products and st["nnz_c"] == nnz_c
+    ip, ix, dx = r.to_host()
+    assert ip[0] == 0 and ip[-1] == nnz_c and np.all(np.diff(ip) >= 0)
+    ok = np.diff(ix.astype(np.int64)) > 0
+    inner = ip[1:-1]
+    ok[inner[(inner > 0) & (inner < len(ix))] - 1] = True   # a descent is allowed only across a row boundary
+    assert ok.all(), "columns not strictly ascending inside a row"
+    assert ix.min() >= 0 and ix.max() < b.shape[1]
+    _linearity(a, b, ip, ix, dx)
+    # A x A^T is symmetric: spot-check C[i,j] == C[j,i] on sampled entries
+    rng = np.random.default_rng(0)
+    c = sp.csr_matrix((dx, ix, ip), shape=(m, m))
+    rows = rng.integers(0, m, size=200)
+    for i in rows:
+        s, e = ip[i], ip[i + 1]
+        if e > s:
+            j = ix[s + (e - s) // 2]
+            assert abs(c[i, j] - c[j, i]) <= 1e-12 * abs(c[i, j])
