@@ -329,7 +329,7 @@ def main():
 
     # ---- e2e: host-level C-ABI call with pinned host operands, C copied back (rank 0, N = 1) ---------
     e2e = None
-    if world == 1:
+    if world == 1 and args.e2e_steps > 0:
         eng.synchronize()
         abi = pkg._abi
         lib = abi.lib()

@@ -174,14 +174,29 @@ void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_
                          uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
 void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                         uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
-// stage 2 / 3, heavy bin (9)
-int heavy_grid(uint32_t rows, int sm_count, int64_t b_cols);  // resident CTAs (workspace bounded)
-size_t heavy_workspace_words(int grid, int64_t b_cols);        // uint2 words
-void launch_heavy_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                           uint32_t rows, uint32_t* row_nnz, uint2* ws, int grid, cudaStream_t s);
-void launch_heavy_numeric(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                          uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, uint2* ws,
-                          int grid, cudaStream_t s);
+// stage 2 / 3, heavy bin (9): rows are cut into items (~8192 products) spread over the grid
+struct HeavyPlan {
+    uint32_t words;      // bitmap words per row = ceil(B.cols / 32)
+    uint32_t wave_rows;  // heavy rows whose bitmaps fit the workspace at once
+    uint32_t n_waves;
+    uint64_t max_items;  // capacity of the item list
+    size_t ws_words;     // uint2 words of workspace
+};
+HeavyPlan heavy_plan_sizes(uint32_t n_rows, uint64_t products, int64_t b_cols, size_t ws_budget_bytes);
+void launch_heavy_items(const DevCsr& a, int64_t row_begin, const uint32_t* rows_list, uint32_t n_rows,
+                        const uint32_t* flops, uint32_t* items_per_row, int64_t* item_off, uint32_t* item_row,
+                        uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s);
+void launch_heavy_bits(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
+                       const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
+                       uint32_t wave_hi, uint2* ws, const HeavyPlan& P, int sm_count, cudaStream_t s);
+void launch_heavy_rank(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, uint2* ws, const HeavyPlan& P,
+                       uint32_t* row_nnz /* or NULL */, cudaStream_t s);
+void launch_heavy_emit(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, const uint2* ws,
+                       const HeavyPlan& P, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
+                        const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
+                        uint32_t wave_hi, const uint2* ws, const HeavyPlan& P, const int64_t* c_ptr, double* c_val,
+                        int sm_count, cudaStream_t s);
 void setup_kernel_attributes();
 
 }  // namespace spada

@@ -1,8 +1,9 @@
 // engine.cu -- host side of the engine and the C ABI of include/spada_b200.h.
 //
-// One handle owns a device, a stream and a stream-ordered memory pool (cudaMallocAsync with an
-// unlimited release threshold, so steady-state calls never reach the driver allocator).  A call
-// to spada_b200_spgemm_dev runs the four stages of the path on that stream:
+// One handle owns a device, a stream and a caching device-memory pool (freed blocks are kept and
+// handed out again by size, so steady-state calls never reach the driver allocator; all work is
+// ordered on the one stream, which makes immediate reuse safe).  A call to
+// spada_b200_spgemm_dev runs the four stages of the path on that stream:
 //   1. flop count + binning      (plan.cu)   -- one host read-back of ~200 bytes of counters
 //   2. symbolic, one launch/bin  (esc.cu, heavy.cu)
 //   4. exclusive scan -> row_ptr (plan.cu)   -- one host read-back of nnz(C) to size C
@@ -12,8 +13,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <unordered_map>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -57,6 +61,11 @@ struct spada_b200 {
     int64_t* h_scalar = nullptr;    // pinned
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
+    // caching pool: free blocks by capacity, live blocks by address
+    std::multimap<size_t, void*> pool_free;
+    std::unordered_map<void*, size_t> pool_live;
+    size_t pool_bytes = 0;
+    size_t heavy_ws_budget = (size_t)2 << 30;  // bitmap workspace for the heavy bin (SPADA_B200_HEAVY_WS_MB)
 };
 
 struct spada_b200_csr {
@@ -88,16 +97,61 @@ struct DeviceGuard {
     }
 };
 
+// Pool policy: capacities are rounded up (512 B below 1 MiB, 2 MiB above); a request takes the
+// smallest cached block that fits and wastes at most 25 % (or 1 MiB); otherwise cudaMalloc, and
+// on out-of-memory the cache is released once and the allocation retried.
+size_t pool_round(size_t bytes) {
+    if (bytes < (1u << 20)) return (bytes + 511) & ~(size_t)511;
+    return (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+}
+void pool_release_cached(spada_b200* h) {
+    cudaStreamSynchronize(h->stream);
+    for (auto& kv : h->pool_free) {
+        cudaFree(kv.second);
+        h->pool_bytes -= kv.first;
+    }
+    h->pool_free.clear();
+}
+int pool_alloc(spada_b200* h, void** p, size_t bytes) {
+    *p = nullptr;
+    size_t cap = pool_round(bytes ? bytes : 1);
+    auto it = h->pool_free.lower_bound(cap);
+    if (it != h->pool_free.end() && it->first <= cap + std::max<size_t>(cap / 4, 1u << 20)) {
+        *p = it->second;
+        h->pool_live[*p] = it->first;
+        h->pool_free.erase(it);
+        return 0;
+    }
+    cudaError_t e = cudaMalloc(p, cap);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_release_cached(h);
+        e = cudaMalloc(p, cap);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? SPADA_B200_OOM : SPADA_B200_CUDA_ERROR,
+                    "cudaMalloc(%zu bytes) failed: %s", cap, cudaGetErrorString(e));
+    }
+    h->pool_live[*p] = cap;
+    h->pool_bytes += cap;
+    return 0;
+}
+void pool_free(spada_b200* h, void* p) {
+    if (!p) return;
+    auto it = h->pool_live.find(p);
+    if (it == h->pool_live.end()) return;
+    h->pool_free.emplace(it->second, p);
+    h->pool_live.erase(it);
+}
 template <typename T>
 int dalloc(spada_b200* h, T** p, size_t count) {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    CU(cudaMallocAsync((void**)p, count * sizeof(T), h->stream));
-    return 0;
+    return pool_alloc(h, (void**)p, count * sizeof(T));
 }
 template <typename T>
 void dfree(spada_b200* h, T* p) {
-    if (p) cudaFreeAsync((void*)p, h->stream);
+    pool_free(h, (void*)p);
 }
 
 cudaEvent_t next_event(spada_b200* h) {
@@ -240,14 +294,14 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
     }
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, h->device));
-    uint64_t thr = UINT64_MAX;
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     CU(cudaMalloc((void**)&h->d_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_scalar, 64));
     setup_kernel_attributes();
+    if (const char* e = getenv("SPADA_B200_HEAVY_WS_MB")) {
+        long mb = atol(e);
+        if (mb > 0) h->heavy_ws_budget = (size_t)mb << 20;
+    }
     *out = h;
     return 0;
 }
@@ -256,6 +310,8 @@ extern "C" void spada_b200_destroy(spada_b200_t* h) {
     if (!h) return;
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
+    pool_release_cached(h);
+    for (auto& kv : h->pool_live) cudaFree(kv.first);  // objects the caller never freed
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     cudaFree(h->d_ctr);
     cudaFreeHost(h->h_ctr);
@@ -291,10 +347,7 @@ extern "C" int spada_b200_synchronize(spada_b200_t* h) {
 extern "C" int spada_b200_trim(spada_b200_t* h) {
     if (!h) return fail(SPADA_B200_INVALID_ARG, "handle is NULL");
     DeviceGuard g(h->device);
-    CU(cudaStreamSynchronize(h->stream));
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, h->device));
-    CU(cudaMemPoolTrimTo(pool, 0));
+    pool_release_cached(h);
     return 0;
 }
 
@@ -534,6 +587,9 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     uint32_t *d_flops = nullptr, *d_long = nullptr, *d_perm = nullptr, *d_nnz = nullptr;
     uint64_t* d_tiles = nullptr;
     uint2* d_heavy_ws = nullptr;
+    uint32_t *d_items_per_row = nullptr, *d_item_row = nullptr;
+    int64_t* d_item_off = nullptr;
+    uint32_t kernels = 0;
     auto cleanup = [&]() {
         dfree(h, d_flops);
         dfree(h, d_long);
@@ -541,6 +597,9 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         dfree(h, d_nnz);
         dfree(h, d_tiles);
         dfree(h, d_heavy_ws);
+        dfree(h, d_items_per_row);
+        dfree(h, d_item_row);
+        dfree(h, d_item_off);
     };
 #define TRY(x)                    \
     do {                          \
@@ -579,6 +638,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     TRY(dalloc(h, &d_tiles, scan_tile_state_words(m)));
     begin_rec("flop_count", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
     TRY(run_flops(h, A, B, (int64_t)row_begin, m, d_flops, d_long));
+    kernels += 2;
     end_rec();
     CUT(cudaMemsetAsync(d_nnz, 0, (size_t)m * sizeof(uint32_t), s));
     CUT(cudaStreamSynchronize(s));  // host read-back #1: bin sizes
@@ -605,16 +665,26 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         begin_rec("bin_scatter", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
         launch_bin_scatter(d_flops, m, tbl, d_perm, h->d_ctr, s);
         CUT(cudaGetLastError());
+        kernels += 1;
         end_rec();
     }
     for (int bnum = 0; bnum < NUM_BINS; ++bnum) perm_of_bin[bnum] = identity ? nullptr : d_perm + tbl.offset[bnum];
 
-    int hgrid = 0;
-    if (pc.bin_rows[BIN_HEAVY]) {
-        hgrid = heavy_grid(pc.bin_rows[BIN_HEAVY], h->sm_count, B.cols);
-        size_t words = heavy_workspace_words(hgrid, B.cols);
-        TRY(dalloc(h, &d_heavy_ws, words));
-        CUT(cudaMemsetAsync(d_heavy_ws, 0, words * sizeof(uint2), s));
+    // heavy rows: cut into items, bitmaps for one wave of rows at a time
+    HeavyPlan HP{};
+    const uint32_t n_heavy = pc.bin_rows[BIN_HEAVY];
+    if (n_heavy) {
+        HP = heavy_plan_sizes(n_heavy, pc.bin_products[BIN_HEAVY], B.cols, h->heavy_ws_budget);
+        TRY(dalloc(h, &d_items_per_row, (size_t)n_heavy));
+        TRY(dalloc(h, &d_item_off, (size_t)n_heavy + 1));
+        TRY(dalloc(h, &d_item_row, (size_t)HP.max_items));
+        TRY(dalloc(h, &d_heavy_ws, HP.ws_words));
+        begin_rec("heavy_items", 1, (n_heavy + 255) / 256, n_heavy, pc.bin_products[BIN_HEAVY]);
+        launch_heavy_items(A, (int64_t)row_begin, perm_of_bin[BIN_HEAVY], n_heavy, d_flops, d_items_per_row,
+                           d_item_off, d_item_row, d_tiles, h->d_ctr, s);
+        CUT(cudaGetLastError());
+        kernels += 3;
+        end_rec();
     }
 
     // ---- stage 2: symbolic ------------------------------------------------------------------
@@ -624,11 +694,25 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         char name[32];
         snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
         if (bnum == BIN_HEAVY) {
-            begin_rec(name, 2, (uint32_t)hgrid, rows, pc.bin_products[bnum]);
-            launch_heavy_symbolic(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, d_heavy_ws, hgrid, s);
+            const uint32_t* hl = perm_of_bin[bnum];
+            for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
+                uint32_t hi = std::min(rows, lo + HP.wave_rows);
+                begin_rec("sym_heavy_clear", 2, 0, hi - lo, 0);
+                CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), s));
+                end_rec();
+                begin_rec("sym_heavy_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
+                                  h->sm_count, s);
+                end_rec();
+                begin_rec("sym_heavy_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum]);
+                launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, s);
+                kernels += 2;
+                if (hi < rows) end_rec();
+            }
         } else {
             begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
             launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
+            kernels += 1;
         }
         CUT(cudaGetLastError());
         end_rec();
@@ -638,6 +722,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     begin_rec("row_ptr_scan", 4, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
     launch_scan_u32_i64(d_nnz, m, R->ptr, d_tiles, h->d_ctr, s);
     CUT(cudaGetLastError());
+    kernels += 1;
     end_rec();
     CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CUT(cudaStreamSynchronize(s));  // host read-back #2: nnz(C) sizes the output
@@ -654,12 +739,32 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         char name[32];
         snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
         if (bnum == BIN_HEAVY) {
-            begin_rec(name, 3, (uint32_t)hgrid, rows, pc.bin_products[bnum]);
-            launch_heavy_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val,
-                                 d_heavy_ws, hgrid, s);
+            const uint32_t* hl = perm_of_bin[bnum];
+            const bool ws_valid = HP.n_waves == 1;  // bitmaps + ranks of the symbolic stage are still resident
+            for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
+                uint32_t hi = std::min(rows, lo + HP.wave_rows);
+                if (!ws_valid) {
+                    begin_rec("num_heavy_bits", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                    CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), s));
+                    launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws,
+                                      HP, h->sm_count, s);
+                    launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, nullptr, s);
+                    kernels += 2;
+                    end_rec();
+                }
+                begin_rec("num_heavy_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum]);
+                launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, R->ptr, R->col, R->val, s);
+                end_rec();
+                begin_rec("num_heavy_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                launch_heavy_accum(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
+                                   R->ptr, R->val, h->sm_count, s);
+                kernels += 2;
+                if (hi < rows) end_rec();
+            }
         } else {
             begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
             launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
+            kernels += 1;
         }
         CUT(cudaGetLastError());
         end_rec();
@@ -671,7 +776,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     // ---- stats ------------------------------------------------------------------------------
     st.nnz_a = 0;  // filled by the caller-facing wrappers when the whole of A is used
     if (row_begin == 0 && row_end == (uint64_t)A.rows) st.nnz_a = (uint64_t)A.nnz;
-    st.n_launches = (uint32_t)recs.size() + 1;  // + k_flops_long inside flop_count
+    st.n_launches = kernels;
     st.n_recorded = 0;
     for (const LaunchRec& r : recs) {
         float ms = 0.f;

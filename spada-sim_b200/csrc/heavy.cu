@@ -1,10 +1,12 @@
-// heavy.cu -- stages 2 and 3 for rows with more than 4096 intermediate products (bin 9): one
-// CTA per row, an occupancy bitmap over B's column space plus per-word ranks, so every product
-// finds its slot in the (sorted) output row directly -- no hash probing and no sort.
+// heavy.cu -- stages 2 and 3 for rows with more than 4096 intermediate products (bin 9): an
+// occupancy bitmap over B's column space plus per-word ranks per row, so every product finds
+// its slot in the (sorted) output row directly -- no hash probing and no sort.
 //
 // Reference logic replaced: rows longer than a window are K-tiled into several partial rows
 // that the adder trees merge later (scheduler.rs:522-524, merge_task :381-480,
-// in_cache_merge_task :820-920; adder_tree.rs:73-83, 145-188).  Here the merge happens in
+// in_cache_merge_task :820-920; adder_tree.rs:73-83, 145-188).  Here the K tiles are "items"
+// (a contiguous slice of the A row worth ~8192 products) spread over the whole grid -- a row
+// with half a million products no longer serialises on one CTA -- and the merge happens in
 // place: bitmap bit j set <=> some product lands on column j; rank(j) = number of set bits
 // below j = position of C[i,j] inside the row.
 //
@@ -13,170 +15,219 @@
 // (scheduler.rs:386, 396, 827); results agree with the oracle to within a few ulp (tested at
 // rel 1e-12), structure is exact.
 //
-// Workspace: per resident CTA one uint2 {bits, rank} per 32 columns of B, kept all-zero between
-// rows (each row clears what it set).
+// Workspace: one uint2 {bits, rank} per 32 columns of B per heavy row of the current wave.
 #include "common.cuh"
 
 namespace spada {
 
-constexpr int HEAVY_THREADS = 512;
+constexpr int HEAVY_THREADS = 256;
 constexpr int HEAVY_WARPS = HEAVY_THREADS / 32;
-constexpr int HEAVY_ACC = 12288;  // f64 accumulators in shared memory (96 KB): rows up to this many nnz
-constexpr size_t HEAVY_WS_BUDGET_WORDS = (size_t)1 << 27;  // 1 GiB of uint2
+constexpr uint32_t HEAVY_ITEM_PRODUCTS = 8192;
 
-static size_t words_per_cta(int64_t b_cols) { return (size_t)((b_cols + 31) / 32) + 1; }
-int heavy_grid(uint32_t rows, int sm_count, int64_t b_cols) {
-    size_t g = 2 * (size_t)sm_count;
-    if (g > rows) g = rows;
-    size_t maxg = HEAVY_WS_BUDGET_WORDS / words_per_cta(b_cols);
-    if (g > maxg) g = maxg;
-    return g < 1 ? 1 : (int)g;
-}
-size_t heavy_workspace_words(int grid, int64_t b_cols) { return (size_t)grid * words_per_cta(b_cols); }
+__host__ __device__ inline uint32_t heavy_words(int64_t b_cols) { return (uint32_t)((b_cols + 31) / 32); }
 
-__device__ __forceinline__ void set_bits(const DevCsr& a, const DevCsr& b, int64_t a_begin, int64_t a_end,
-                                         uint2* ws) {
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    for (int64_t pb = a_begin + warp * 32; pb < a_end; pb += HEAVY_THREADS) {
-        int bt;
-        expand_batch<false, true>(a, b, pb + lane, a_end, lane, 0, bt, [&](int, int64_t q, double) {
-            uint32_t c = (uint32_t)ldg_i32(b.col + q);
-            atomicOr(&ws[c >> 5].x, 1u << (c & 31));
-        });
-    }
+// items of one heavy row: n = min(ceil(p / 8192), ceil(len / 32)) slices of `chunk` A entries each
+__device__ __forceinline__ void item_shape(uint32_t p, int64_t a_len, uint32_t& n_items, int64_t& chunk) {
+    uint32_t by_p = (p + HEAVY_ITEM_PRODUCTS - 1) / HEAVY_ITEM_PRODUCTS;
+    int64_t by_len = (a_len + 31) / 32;
+    n_items = (uint32_t)(by_p < by_len ? by_p : by_len);
+    if (n_items < 1) n_items = 1;
+    chunk = ((a_len + n_items - 1) / n_items + 31) & ~(int64_t)31;
+    n_items = (uint32_t)((a_len + chunk - 1) / chunk);
+    if (n_items < 1) n_items = 1;
 }
 
+__global__ void k_heavy_plan(DevCsr a, int64_t row_begin, const uint32_t* __restrict__ rows_list, uint32_t n_rows,
+                             const uint32_t* __restrict__ flops, uint32_t* __restrict__ items_per_row) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    uint32_t r = rows_list ? rows_list[i] : i;
+    int64_t len = a.ptr[row_begin + r + 1] - a.ptr[row_begin + r];
+    uint32_t n;
+    int64_t chunk;
+    item_shape(flops[r], len, n, chunk);
+    items_per_row[i] = n;
+}
+
+__global__ void k_heavy_fill(const int64_t* __restrict__ item_off, uint32_t n_rows, uint32_t* __restrict__ item_row) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    for (int64_t t = item_off[i]; t < item_off[i + 1]; ++t) item_row[t] = i;
+}
+
+// the slice of A row entries an item covers
+struct ItemRange {
+    uint32_t hrow;  // index into the heavy list
+    uint32_t row;   // row of A (relative to row_begin)
+    int64_t a0, a1;
+};
+__device__ __forceinline__ ItemRange item_range(const DevCsr& a, int64_t row_begin, const uint32_t* rows_list,
+                                                const uint32_t* flops, const int64_t* item_off,
+                                                const uint32_t* item_row, int64_t it) {
+    ItemRange R;
+    R.hrow = item_row[it];
+    R.row = rows_list ? rows_list[R.hrow] : R.hrow;
+    int64_t s = a.ptr[row_begin + R.row], e = a.ptr[row_begin + R.row + 1];
+    uint32_t n;
+    int64_t chunk;
+    item_shape(flops[R.row], e - s, n, chunk);
+    int64_t j = it - item_off[R.hrow];
+    R.a0 = s + j * chunk;
+    R.a1 = R.a0 + chunk < e ? R.a0 + chunk : e;
+    return R;
+}
+
+// ---- bits: every product sets its column's bit in the row's bitmap ------------------------------
 __global__ void __launch_bounds__(HEAVY_THREADS)
-k_heavy_symbolic(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
-                 uint32_t* __restrict__ row_nnz, uint2* ws_all, uint32_t words) {
-    __shared__ int s_cnt[HEAVY_WARPS];
-    uint2* ws = ws_all + (size_t)blockIdx.x * (words + 1);
-    for (uint32_t idx = blockIdx.x; idx < rows; idx += gridDim.x) {
-        const uint32_t r = perm ? perm[idx] : idx;
-        set_bits(a, b, a.ptr[row_begin + r], a.ptr[row_begin + r + 1], ws);
-        __syncthreads();
-        int cnt = 0;
-        for (uint32_t w = threadIdx.x; w < words; w += HEAVY_THREADS) {
-            uint32_t bits = __ldcg(&ws[w].x);
-            if (bits) {
-                cnt += __popc(bits);
-                ws[w].x = 0u;
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-        if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = cnt;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w = 0; w < HEAVY_WARPS; ++w) t += s_cnt[w];
-            row_nnz[r] = (uint32_t)t;
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(HEAVY_THREADS)
-k_heavy_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
-                const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val,
-                uint2* ws_all, uint32_t words) {
-    extern __shared__ __align__(16) double s_acc[];
-    __shared__ uint32_t s_wtot[HEAVY_WARPS];
+k_heavy_bits(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list,
+             const uint32_t* __restrict__ flops, const int64_t* __restrict__ item_off,
+             const uint32_t* __restrict__ item_row, uint32_t wave_lo, uint32_t wave_hi, uint2* ws, uint32_t words) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    uint2* ws = ws_all + (size_t)blockIdx.x * (words + 1);
-    for (uint32_t idx = blockIdx.x; idx < rows; idx += gridDim.x) {
-        const uint32_t r = perm ? perm[idx] : idx;
-        const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
-        const int64_t cbase = c_ptr[r];
-        const int64_t z = c_ptr[r + 1] - cbase;
-        const bool in_smem = z <= HEAVY_ACC;
-        // 1. occupancy bitmap
-        set_bits(a, b, a_begin, a_end, ws);
-        if (in_smem) {
-            for (int i = threadIdx.x; i < (int)z; i += HEAVY_THREADS) s_acc[i] = 0.0;
-        } else {
-            for (int64_t i = threadIdx.x; i < z; i += HEAVY_THREADS) c_val[cbase + i] = 0.0;
-        }
-        __syncthreads();
-        // 2. per-word ranks (exclusive prefix of popcounts) and the row's column ids
-        uint32_t run = 0;
-        for (uint32_t wb = 0; wb < words; wb += HEAVY_THREADS) {
-            uint32_t w = wb + threadIdx.x;
-            uint32_t bits = (w < words) ? __ldcg(&ws[w].x) : 0u;
-            uint32_t pc = __popc(bits);
-            uint32_t x = pc;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(FULL, x, d);
-                if (lane >= d) x += y;
-            }
-            if (lane == 31) s_wtot[warp] = x;
-            __syncthreads();
-            uint32_t wbase = run, all = 0;
-#pragma unroll
-            for (int q = 0; q < HEAVY_WARPS; ++q) {
-                uint32_t t = s_wtot[q];
-                if (q < warp) wbase += t;
-                all += t;
-            }
-            if (bits) {
-                uint32_t rank = wbase + x - pc;
-                ws[w].y = rank;
-                uint32_t bb = bits;
-                int64_t o = cbase + rank;
-                while (bb) {
-                    int bit = __ffs(bb) - 1;
-                    bb &= bb - 1;
-                    c_col[o++] = (int32_t)(w * 32u + bit);
-                }
-            }
-            run += all;
-            __syncthreads();
-        }
-        // 3. products -> slots
-        for (int64_t pb = a_begin + warp * 32; pb < a_end; pb += HEAVY_THREADS) {
+    const int64_t it_end = item_off[wave_hi];
+    for (int64_t it = item_off[wave_lo] + blockIdx.x; it < it_end; it += gridDim.x) {
+        ItemRange R = item_range(a, row_begin, rows_list, flops, item_off, item_row, it);
+        uint2* w = ws + (size_t)(R.hrow - wave_lo) * words;
+        // more products than columns => most bits are already set when a product arrives: test first,
+        // the (idempotent) atomic only for new bits
+        const bool dense = (int64_t)flops[R.row] > b.cols;
+        for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
             int bt;
-            expand_batch<true, true>(a, b, pb + lane, a_end, lane, 0, bt, [&](int, int64_t q, double av) {
+            expand_batch<false, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, int64_t q, double) {
                 uint32_t c = (uint32_t)ldg_i32(b.col + q);
-                double prod = __dmul_rn(av, ldg_f64(b.val + q));
-                uint2 e = __ldcg(&ws[c >> 5]);
-                uint32_t pos = e.y + __popc(e.x & ((1u << (c & 31)) - 1u));
-                if (in_smem)
-                    atomicAdd(&s_acc[pos], prod);
-                else
-                    atomicAdd(&c_val[cbase + pos], prod);
+                uint32_t bit = 1u << (c & 31);
+                if (!dense || !(__ldcg(&w[c >> 5].x) & bit)) atomicOr(&w[c >> 5].x, bit);
             });
         }
-        __syncthreads();
-        // 4. store values, clear the bitmap for the next row
-        if (in_smem)
-            for (int i = threadIdx.x; i < (int)z; i += HEAVY_THREADS) c_val[cbase + i] = s_acc[i];
-        for (uint32_t w = threadIdx.x; w < words; w += HEAVY_THREADS)
-            if (__ldcg(&ws[w].x)) ws[w] = make_uint2(0u, 0u);
-        __syncthreads();
     }
 }
 
-void launch_heavy_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                           uint32_t rows, uint32_t* row_nnz, uint2* ws, int grid, cudaStream_t s) {
-    if (rows == 0) return;
-    uint32_t words = (uint32_t)((b.cols + 31) / 32);
-    k_heavy_symbolic<<<grid, HEAVY_THREADS, 0, s>>>(a, b, row_begin, perm, rows, row_nnz, ws, words);
+// ---- rank: per row, exclusive prefix of the words' popcounts; total = nnz of the row -----------
+__global__ void __launch_bounds__(HEAVY_THREADS)
+k_heavy_rank(const uint32_t* __restrict__ rows_list, uint32_t wave_lo, uint2* ws, uint32_t words,
+             uint32_t* __restrict__ row_nnz) {
+    __shared__ uint32_t s_wtot[HEAVY_WARPS];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t hrow = wave_lo + blockIdx.x;
+    uint2* w = ws + (size_t)blockIdx.x * words;
+    uint32_t run = 0;
+    for (uint32_t wb = 0; wb < words; wb += HEAVY_THREADS) {
+        uint32_t i = wb + threadIdx.x;
+        uint32_t bits = (i < words) ? __ldcg(&w[i].x) : 0u;
+        uint32_t pc = __popc(bits);
+        uint32_t x = pc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_wtot[warp] = x;
+        __syncthreads();
+        uint32_t wbase = run, all = 0;
+#pragma unroll
+        for (int q = 0; q < HEAVY_WARPS; ++q) {
+            uint32_t t = s_wtot[q];
+            if (q < warp) wbase += t;
+            all += t;
+        }
+        if (bits) w[i].y = wbase + x - pc;
+        run += all;
+        __syncthreads();
+    }
+    if (row_nnz && threadIdx.x == 0) row_nnz[rows_list ? rows_list[hrow] : hrow] = run;
 }
 
-void launch_heavy_numeric(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                          uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, uint2* ws, int grid,
-                          cudaStream_t s) {
-    if (rows == 0) return;
-    uint32_t words = (uint32_t)((b.cols + 31) / 32);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_heavy_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(HEAVY_ACC * sizeof(double)));
-        attr = true;
+// ---- emit: column ids of the row from the bitmap, values zeroed for the accumulation -----------
+__global__ void __launch_bounds__(HEAVY_THREADS)
+k_heavy_emit(const uint32_t* __restrict__ rows_list, uint32_t wave_lo, const uint2* ws, uint32_t words,
+             const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+    const uint32_t hrow = wave_lo + blockIdx.x;
+    const uint32_t r = rows_list ? rows_list[hrow] : hrow;
+    const uint2* w = ws + (size_t)blockIdx.x * words;
+    const int64_t cbase = c_ptr[r], z = c_ptr[r + 1] - cbase;
+    for (int64_t i = threadIdx.x; i < z; i += HEAVY_THREADS) c_val[cbase + i] = 0.0;
+    for (uint32_t i = threadIdx.x; i < words; i += HEAVY_THREADS) {
+        uint2 e = __ldcg(&w[i]);
+        uint32_t bb = e.x;
+        int64_t o = cbase + e.y;
+        while (bb) {
+            int bit = __ffs(bb) - 1;
+            bb &= bb - 1;
+            c_col[o++] = (int32_t)(i * 32u + bit);
+        }
     }
-    k_heavy_numeric<<<grid, HEAVY_THREADS, HEAVY_ACC * sizeof(double), s>>>(a, b, row_begin, perm, rows, c_ptr,
-                                                                          c_col, c_val, ws, words);
+}
+
+// ---- accumulate: products -> slots ---------------------------------------------------------------
+__global__ void __launch_bounds__(HEAVY_THREADS)
+k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list,
+              const uint32_t* __restrict__ flops, const int64_t* __restrict__ item_off,
+              const uint32_t* __restrict__ item_row, uint32_t wave_lo, uint32_t wave_hi, const uint2* ws,
+              uint32_t words, const int64_t* __restrict__ c_ptr, double* __restrict__ c_val) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int64_t it_end = item_off[wave_hi];
+    for (int64_t it = item_off[wave_lo] + blockIdx.x; it < it_end; it += gridDim.x) {
+        ItemRange R = item_range(a, row_begin, rows_list, flops, item_off, item_row, it);
+        const uint2* w = ws + (size_t)(R.hrow - wave_lo) * words;
+        double* out = c_val + c_ptr[R.row];
+        for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
+            int bt;
+            expand_batch<true, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, int64_t q, double av) {
+                uint32_t c = (uint32_t)ldg_i32(b.col + q);
+                double prod = __dmul_rn(av, ldg_f64(b.val + q));
+                uint2 e = __ldcg(&w[c >> 5]);
+                uint32_t pos = e.y + __popc(e.x & ((1u << (c & 31)) - 1u));
+                atomicAdd(out + pos, prod);
+            });
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+HeavyPlan heavy_plan_sizes(uint32_t n_rows, uint64_t products, int64_t b_cols, size_t ws_budget_bytes) {
+    HeavyPlan P;
+    P.words = heavy_words(b_cols);
+    P.max_items = products / HEAVY_ITEM_PRODUCTS + (uint64_t)n_rows + 1;
+    size_t per_row = (size_t)P.words * sizeof(uint2);
+    size_t rows_fit = per_row ? ws_budget_bytes / per_row : n_rows;
+    if (rows_fit < 1) rows_fit = 1;
+    P.wave_rows = (uint32_t)(rows_fit < n_rows ? rows_fit : n_rows);
+    P.n_waves = (n_rows + P.wave_rows - 1) / P.wave_rows;
+    P.ws_words = (size_t)P.wave_rows * P.words;
+    return P;
+}
+
+void launch_heavy_items(const DevCsr& a, int64_t row_begin, const uint32_t* rows_list, uint32_t n_rows,
+                        const uint32_t* flops, uint32_t* items_per_row, int64_t* item_off, uint32_t* item_row,
+                        uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s) {
+    unsigned g = (n_rows + 255) / 256;
+    k_heavy_plan<<<g, 256, 0, s>>>(a, row_begin, rows_list, n_rows, flops, items_per_row);
+    launch_scan_u32_i64(items_per_row, n_rows, item_off, tile_state, ctr, s);
+    k_heavy_fill<<<g, 256, 0, s>>>(item_off, n_rows, item_row);
+}
+
+static int persistent_grid(int sm_count) { return sm_count * 8; }
+
+void launch_heavy_bits(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
+                       const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
+                       uint32_t wave_hi, uint2* ws, const HeavyPlan& P, int sm_count, cudaStream_t s) {
+    k_heavy_bits<<<persistent_grid(sm_count), HEAVY_THREADS, 0, s>>>(a, b, row_begin, rows_list, flops, item_off,
+                                                                    item_row, wave_lo, wave_hi, ws, P.words);
+}
+void launch_heavy_rank(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, uint2* ws, const HeavyPlan& P,
+                       uint32_t* row_nnz, cudaStream_t s) {
+    k_heavy_rank<<<wave_hi - wave_lo, HEAVY_THREADS, 0, s>>>(rows_list, wave_lo, ws, P.words, row_nnz);
+}
+void launch_heavy_emit(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, const uint2* ws,
+                       const HeavyPlan& P, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+    k_heavy_emit<<<wave_hi - wave_lo, HEAVY_THREADS, 0, s>>>(rows_list, wave_lo, ws, P.words, c_ptr, c_col, c_val);
+}
+void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
+                        const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
+                        uint32_t wave_hi, const uint2* ws, const HeavyPlan& P, const int64_t* c_ptr, double* c_val,
+                        int sm_count, cudaStream_t s) {
+    k_heavy_accum<<<persistent_grid(sm_count), HEAVY_THREADS, 0, s>>>(a, b, row_begin, rows_list, flops, item_off,
+                                                                     item_row, wave_lo, wave_hi, ws, P.words, c_ptr,
+                                                                     c_val);
 }
 
 }  // namespace spada

@@ -41,7 +41,8 @@ class DeviceCsr:
 
     def free(self):
         if self._h is not None:
-            lib().spada_b200_csr_free(self._h)
+            if self.engine._h is not None:   # a destroyed engine already released every device block
+                lib().spada_b200_csr_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -104,7 +105,8 @@ class Result:
 
     def free(self):
         if self._h is not None:
-            lib().spada_b200_result_free(self._h)
+            if self.engine._h is not None:
+                lib().spada_b200_result_free(self._h)
             self._h = None
 
     def __del__(self):
