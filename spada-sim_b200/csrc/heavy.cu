@@ -16,6 +16,8 @@
 // rel 1e-12), structure is exact.
 //
 // Workspace: one uint2 {bits, rank} per 32 columns of B per heavy row of the current wave.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace spada {
@@ -87,15 +89,15 @@ k_heavy_bits(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__
     for (int64_t it = item_off[wave_lo] + blockIdx.x; it < it_end; it += gridDim.x) {
         ItemRange R = item_range(a, row_begin, rows_list, flops, item_off, item_row, it);
         uint2* w = ws + (size_t)(R.hrow - wave_lo) * words;
-        // more products than columns => most bits are already set when a product arrives: test first,
-        // the (idempotent) atomic only for new bits
-        const bool dense = (int64_t)flops[R.row] > b.cols;
+        // Test the word with a plain load first: the load brings the sector into L2 with full
+        // memory-level parallelism (an atomic that misses L2 is served far more slowly), and bits
+        // that are already set need no atomic at all (the OR is idempotent).
         for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
             int bt;
             expand_batch<false, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, int64_t q, double) {
                 uint32_t c = (uint32_t)ldg_i32(b.col + q);
                 uint32_t bit = 1u << (c & 31);
-                if (!dense || !(__ldcg(&w[c >> 5].x) & bit)) atomicOr(&w[c >> 5].x, bit);
+                if (!(__ldcg(&w[c >> 5].x) & bit)) atomicOr(&w[c >> 5].x, bit);
             });
         }
     }
@@ -169,6 +171,11 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
         ItemRange R = item_range(a, row_begin, rows_list, flops, item_off, item_row, it);
         const uint2* w = ws + (size_t)(R.hrow - wave_lo) * words;
         double* out = c_val + c_ptr[R.row];
+        // The add of one step is issued one step late: its slot was prefetched into L2 a full
+        // memory round trip earlier, so the atomic hits L2 instead of waiting on an HBM fill.
+        double pend_v = 0.0;
+        uint32_t pend_pos = 0;
+        bool pend = false;
         for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
             int bt;
             expand_batch<true, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, int64_t q, double av) {
@@ -176,9 +183,14 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
                 double prod = __dmul_rn(av, ldg_f64(b.val + q));
                 uint2 e = __ldcg(&w[c >> 5]);
                 uint32_t pos = e.y + __popc(e.x & ((1u << (c & 31)) - 1u));
-                atomicAdd(out + pos, prod);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(out + pos));
+                if (pend) atomicAdd(out + pend_pos, pend_v);
+                pend = true;
+                pend_pos = pos;
+                pend_v = prod;
             });
         }
+        if (pend) atomicAdd(out + pend_pos, pend_v);
     }
 }
 
@@ -205,7 +217,16 @@ void launch_heavy_items(const DevCsr& a, int64_t row_begin, const uint32_t* rows
     k_heavy_fill<<<g, 256, 0, s>>>(item_off, n_rows, item_row);
 }
 
-static int persistent_grid(int sm_count) { return sm_count * 8; }
+// resident CTAs of the item kernels: few enough that the bitmaps of the rows in flight stay in L2
+static int persistent_grid(int sm_count) {
+    static int per_sm = 0;
+    if (!per_sm) {
+        const char* e = getenv("SPADA_B200_HEAVY_CTAS_PER_SM");
+        per_sm = e ? atoi(e) : 8;
+        if (per_sm < 1 || per_sm > 8) per_sm = 8;
+    }
+    return sm_count * per_sm;
+}
 
 void launch_heavy_bits(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
                        const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
