@@ -1,0 +1,99 @@
+"""CLI drop-in: `spada-sim <simulator> <accelerator> <category> <workload> <configuration> [-p]`
+(frontend.rs:52-75, main.rs:30-121) reproduced by `python -m spada-sim_b200`."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.io
+
+from conftest import GOLDEN, ROOT
+
+CFG = {"ss_filepath": "./matrices", "nn_filepath": "./matrices/nn_gemm.pkl", "pe_num": 2, "at_num": 16, "lane_num": 8,
+       "cache_size": 1572864, "word_byte": 8, "block_shape": [1, 10000000], "mem_latency": 30, "cache_latency": 0,
+       "freq": 1.0, "channel": 16, "bandwidth_per_channel": 8.0}   # = the reference's config/config_1mb_row1.json
+
+
+@pytest.fixture()
+def workdir(tmp_path, cari):
+    (tmp_path / "matrices").mkdir()
+    scipy.io.mmwrite(str(tmp_path / "matrices" / "cari.mtx"), cari, precision=17)   # round-trips every f64
+    (tmp_path / "config").mkdir()
+    (tmp_path / "config" / "config_1mb_row1.json").write_text(json.dumps(CFG))
+    return tmp_path
+
+
+def run_cli(workdir, *args):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    return subprocess.run([sys.executable, "-W", "ignore", "-m", "spada-sim_b200", *args], cwd=workdir, env=env,
+                          capture_output=True, text=True, timeout=600)
+
+
+HEAD = """config/config_1mb_row1.json
+---- Python Interface ----
+% Load cari from ./matrices
+Get GEMM cari
+---- cari ----
+--A: (400, 1200)
+data: [0.052016, 0.038102, 0.024245, 0.01071, 0.003553] .. 
+indices: [0, 1, 2, 3, 4] ...
+indptr: [0, 382, 764, 1146, 1528] ...
+--B: (1200, 400)
+data: [0.052016, 0.038102, 0.024245, 0.01071, 0.003553] ...
+indices: [0, 1, 2, 3, 4] ...
+indptr: [0, 380, 760, 1140, 1520] ...
+
+Avg row len of A: 382, Avg row len of B: 127
+"""
+
+
+def test_cli_loads_and_fails_loudly_without_gpu(workdir, spada):
+    if spada.device_count() > 0:
+        pytest.skip("a GPU is present")
+    p = run_cli(workdir, "accuratesimu", "spada", "ss", "cari", "config/config_1mb_row1.json")
+    assert p.returncode != 0
+    assert p.stdout == HEAD                      # everything up to the engine matches the reference transcript
+    assert "NO_DEVICE" in p.stderr and "no CPU fallback" in p.stderr
+
+
+def test_cli_rejects_bad_enum(workdir):
+    p = run_cli(workdir, "accuratesimu", "tpu", "ss", "cari", "config/config_1mb_row1.json")
+    assert p.returncode == 2 and "isn't a valid value" in p.stderr
+
+
+def test_rust_binding_lists_every_abi_symbol():
+    hdr = open(os.path.join(ROOT, "include", "spada_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(spada_b200_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(ROOT, "spada-sim_b200", "rust", "spada-b200-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (spada_b200_[a-z0-9_]+)\s*\(", rs))
+    assert bound == declared
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["-p"]])
+def test_cli_cari_transcript(workdir, oracle, cari, spada, extra):
+    p = run_cli(workdir, "accuratesimu", "spada", "ss", "cari", "config/config_1mb_row1.json", *extra)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.startswith(HEAD)
+    tail = p.stdout[len(HEAD):].splitlines()
+    assert tail[0] == "-----Result-----" and tail[1] == "-----Access count"
+    assert tail[2] == "Execution count: 0"
+    assert tail[3] == "A matrix count: read 305600 write 0"                 # 2 x nnz(A)
+    assert tail[4] == "B matrix count: read 115521600 write 0"             # 2 x 57 760 800 products
+    assert tail[5] == "C matrix count: read 0 write 320400"                # 2 x 160 000 + 400 rows
+    assert tail[6] == "Cache count: read 0 write 0"
+    assert tail[7] == "-----Output product matrix"
+    rows = tail[8:]
+    assert len(rows) == 10                                                  # min(result.len(), 10), main.rs:114
+    g = spada.GEMM.from_mat("cari", cari)
+    cp, cj, cx = oracle.spgemm(g.a, g.b)
+    for r, line in enumerate(rows):
+        m = re.fullmatch(r"rowptr: (\d+) indptr: \[(.*)\] data: \[(.*)\]", line)
+        assert m and int(m.group(1)) == r
+        assert [int(x) for x in m.group(2).split(", ")] == cj[cp[r]:cp[r] + 5].tolist()
+        vals = np.array([float(x) for x in m.group(3).split(", ")])
+        assert np.allclose(vals, cx[cp[r]:cp[r] + 5], rtol=1e-12, atol=0)   # -p never changes C (simulator.rs:1039-1060)
