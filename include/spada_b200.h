@@ -97,7 +97,10 @@ typedef struct spada_b200_opts {
     void *stream;            /* cudaStream_t to launch on; NULL = engine-owned stream */
 } spada_b200_opts;
 
-#define SPADA_B200_FLAG_VALIDATE 1u /* check canonical CSR on upload (UNSORTED_INPUT) */
+#define SPADA_B200_FLAG_VALIDATE 1u  /* check canonical CSR on upload (UNSORTED_INPUT) */
+#define SPADA_B200_FLAG_TWO_PHASE 2u /* always run the separate symbolic + numeric passes (exact-size C);
+                                        default: rows with <= 512 products are done in one fused pass and C is
+                                        allocated with capacity = intermediate-product count */
 
 typedef struct spada_b200 spada_b200_t;               /* engine handle (streams, workspace pool) */
 typedef struct spada_b200_csr spada_b200_csr_t;       /* device-resident operand */

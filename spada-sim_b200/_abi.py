@@ -18,6 +18,7 @@ STATUS = {0: "OK", 1: "INVALID_ARG", 2: "UNSORTED_INPUT", 3: "DIM_MISMATCH", 4: 
           5: "NCCL_ERROR", 6: "OOM", 7: "NO_DEVICE", 8: "TOO_LARGE"}
 ACCELERATORS = {"ip": 0, "op": 1, "multirow": 2, "spada": 3}
 FLAG_VALIDATE = 1
+FLAG_TWO_PHASE = 2
 
 
 class CsrView(C.Structure):

@@ -197,6 +197,11 @@ void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, con
                         const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
                         uint32_t wave_hi, const uint2* ws, const HeavyPlan& P, const int64_t* c_ptr, double* c_val,
                         int sm_count, cudaStream_t s);
+// stages 2+3+4 fused for the warp-per-row bins (fused.cu)
+size_t fused_tile_state_words(int64_t m);
+void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
+                        const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,
+                        uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s);
 void setup_kernel_attributes();
 
 }  // namespace spada

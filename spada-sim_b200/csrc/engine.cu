@@ -65,6 +65,7 @@ struct spada_b200 {
     std::multimap<size_t, void*> pool_free;
     std::unordered_map<void*, size_t> pool_live;
     size_t pool_bytes = 0;
+    size_t dev_total_mem = 0;
     size_t heavy_ws_budget = (size_t)2 << 30;  // bitmap workspace for the heavy bin (SPADA_B200_HEAVY_WS_MB)
 };
 
@@ -288,6 +289,7 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
                     prop.minor);
     }
     h->sm_count = prop.multiProcessorCount;
+    h->dev_total_mem = prop.totalGlobalMem;
     if (h->opts.stream) {
         h->stream = (cudaStream_t)h->opts.stream;
     } else {
@@ -635,7 +637,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     TRY(dalloc(h, &d_long, (size_t)(a_nnz_shard_bound / 256 + 2)));
     TRY(dalloc(h, &d_perm, (size_t)m));
     TRY(dalloc(h, &d_nnz, (size_t)m));
-    TRY(dalloc(h, &d_tiles, scan_tile_state_words(m)));
+    TRY(dalloc(h, &d_tiles, std::max(scan_tile_state_words(m), fused_tile_state_words(m))));
     begin_rec("flop_count", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
     TRY(run_flops(h, A, B, (int64_t)row_begin, m, d_flops, d_long));
     kernels += 2;
@@ -670,6 +672,19 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     }
     for (int bnum = 0; bnum < NUM_BINS; ++bnum) perm_of_bin[bnum] = identity ? nullptr : d_perm + tbl.offset[bnum];
 
+    // Single-pass mode: rows of the warp-per-row bins are computed once and placed by a look-back
+    // scan inside the same kernel; C then has to be sized by its upper bound (the product count).
+    int max_light_bin = 0;
+    uint64_t light_rows = 0;
+    for (int bnum = 1; bnum <= 5; ++bnum)
+        if (pc.bin_rows[bnum]) {
+            max_light_bin = bnum;
+            light_rows += pc.bin_rows[bnum];
+        }
+    const bool fused = !(h->opts.flags & SPADA_B200_FLAG_TWO_PHASE) && light_rows > 0 &&
+                       (double)pc.total_products * 12.0 <= 0.45 * (double)h->dev_total_mem;
+    const int first_sym_bin = fused ? 6 : 1;
+
     // heavy rows: cut into items, bitmaps for one wave of rows at a time
     HeavyPlan HP{};
     const uint32_t n_heavy = pc.bin_rows[BIN_HEAVY];
@@ -688,7 +703,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     }
 
     // ---- stage 2: symbolic ------------------------------------------------------------------
-    for (int bnum = 1; bnum < NUM_BINS; ++bnum) {
+    for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
         uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
         char name[32];
@@ -718,22 +733,38 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         end_rec();
     }
 
-    // ---- stage 4: row_ptr -------------------------------------------------------------------
-    begin_rec("row_ptr_scan", 4, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
-    launch_scan_u32_i64(d_nnz, m, R->ptr, d_tiles, h->d_ctr, s);
-    CUT(cudaGetLastError());
-    kernels += 1;
-    end_rec();
-    CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    CUT(cudaStreamSynchronize(s));  // host read-back #2: nnz(C) sizes the output
-    const int64_t nnz_c = h->h_scalar[0];
-    R->nnz = (uint64_t)nnz_c;
-    st.nnz_c = (uint64_t)nnz_c;
-    TRY(dalloc(h, &R->col, (size_t)nnz_c));
-    TRY(dalloc(h, &R->val, (size_t)nnz_c));
+    int64_t nnz_c = 0;
+    if (!fused) {
+        // ---- stage 4: row_ptr ---------------------------------------------------------------
+        begin_rec("row_ptr_scan", 4, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
+        launch_scan_u32_i64(d_nnz, m, R->ptr, d_tiles, h->d_ctr, s);
+        CUT(cudaGetLastError());
+        kernels += 1;
+        end_rec();
+        CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CUT(cudaStreamSynchronize(s));  // host read-back #2: nnz(C) sizes the output
+        nnz_c = h->h_scalar[0];
+        TRY(dalloc(h, &R->col, (size_t)nnz_c));
+        TRY(dalloc(h, &R->val, (size_t)nnz_c));
+    } else {
+        // ---- stages 2+3+4 fused for the warp-per-row bins ----------------------------------------
+        TRY(dalloc(h, &R->col, (size_t)pc.total_products));
+        TRY(dalloc(h, &R->val, (size_t)pc.total_products));
+        char name[32];
+        snprintf(name, sizeof(name), "fused<%s>", bin_name(max_light_bin));
+        uint64_t light_products = 0;
+        for (int bnum = 1; bnum <= 5; ++bnum) light_products += pc.bin_products[bnum];
+        begin_rec(name, 3, (uint32_t)((m + 7) / 8), light_rows, light_products);
+        launch_fused_light(max_light_bin, A, B, (int64_t)row_begin, m, d_flops, d_nnz, R->ptr, R->col, R->val, d_tiles,
+                           h->d_ctr, s);
+        CUT(cudaGetLastError());
+        kernels += 1;
+        end_rec();
+        CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    }
 
     // ---- stage 3: numeric -------------------------------------------------------------------
-    for (int bnum = 1; bnum < NUM_BINS; ++bnum) {
+    for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
         uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
         char name[32];
@@ -772,6 +803,9 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     cleanup();
     CUT(cudaStreamSynchronize(s));
     CUT(cudaGetLastError());
+    if (fused) nnz_c = h->h_scalar[0];
+    R->nnz = (uint64_t)nnz_c;
+    st.nnz_c = (uint64_t)nnz_c;
 
     // ---- stats ------------------------------------------------------------------------------
     st.nnz_a = 0;  // filled by the caller-facing wrappers when the whole of A is used

@@ -1,0 +1,254 @@
+// fused.cu -- stages 2+3+4 in ONE pass for rows with at most 512 intermediate products (bins 1..5).
+//
+// The two-phase path sorts every such row twice (once to count, once to compute).  Here a row is
+// expanded, sorted and reduced once; the reduced row waits in the warp's shared memory while the
+// CTA learns where it goes: eight consecutive rows form a tile, the tile's nnz total is
+// published and the exclusive prefix over all earlier tiles is obtained by decoupled look-back
+// (the same single-pass scan as plan.cu, one tile per CTA; tile id = blockIdx.x -- a global
+// ticket counter would serialise half a million same-address atomics on the Poisson config).
+// Then row_ptr is written and the rows are copied to their final place with coalesced stores.
+//
+// Rows of the CTA-per-row and bitmap bins (> 512 products) are counted beforehand by their own
+// symbolic kernels; the tile sums simply include their counts, and their numeric kernels run
+// afterwards against the finished row_ptr.
+//
+// C is allocated with capacity = number of intermediate products (an upper bound on nnz(C))
+// because nnz(C) is only known when this kernel ends; the engine falls back to the two-phase
+// path when that bound does not fit.
+//
+// Reference logic replaced: one PE pass (simulator.rs:86-111, 143-171, 199-230), write_psums
+// (simulator.rs:955-983) and the indptr maintenance of CsrMatStorage::write (storage.rs:196-210).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace spada {
+
+constexpr int FUSED_WARPS = 8;  // warps per tile; each warp owns RPW consecutive rows of the tile
+
+#define FST_AGG (1ull << 62)
+#define FST_PREFIX (2ull << 62)
+#define FST_MASK (3ull << 62)
+
+// sort the warp's N = 32*E packed keys, bring the products into sorted order, then sum equal
+// columns left to right and compact in place: on return ocol[0..nnz) / vals[0..nnz) hold the row.
+template <typename K, int E, int SBK>
+__device__ __forceinline__ int sort_reduce_in_place(K* keys, double* vals, int p, int lane) {
+    constexpr int N = 32 * E;
+    for (int t = p + lane; t < N; t += 32) keys[t] = KeyTraits<K>::sentinel;
+    __syncwarp();
+    K x[E];
+    load_blocked<K, E>(x, keys, lane);
+    warp_sort<K, E>(x, lane, false);
+    double v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        int sq = (int)(x[r] & (K)((1u << SBK) - 1u));
+        v[r] = (lane * E + r < p) ? vals[sq] : 0.0;
+    }
+    __syncwarp();
+    store_blocked<K, E>(x, keys, lane);
+#pragma unroll
+    for (int r = 0; r < E; ++r) vals[lane * E + r] = v[r];
+    __syncwarp();
+    uint32_t* ocol = reinterpret_cast<uint32_t*>(keys);
+    int out = 0;
+    uint32_t prev_last = 0;
+    for (int base = 0; base < p; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < p;
+        const uint32_t col = valid ? (uint32_t)(keys[i] >> SBK) : 0xffffffffu;
+        uint32_t col_prev = __shfl_up_sync(FULL, col, 1);
+        if (lane == 0) col_prev = prev_last;
+        const bool head = valid && (i == 0 || col_prev != col);
+        const unsigned hm = __ballot_sync(FULL, head);
+        double sum = 0.0;
+        if (head) {
+            sum = vals[i];
+            for (int j = i + 1; j < p; ++j) {
+                if ((uint32_t)(keys[j] >> SBK) != col) break;
+                sum = __dadd_rn(sum, vals[j]);
+            }
+        }
+        prev_last = __shfl_sync(FULL, col, 31);
+        __syncwarp();  // every read of this chunk (and its forward runs) is done before the compaction writes
+        if (head) {
+            int o = out + __popc(hm & ((1u << lane) - 1u));
+            ocol[o] = col;
+            vals[o] = sum;
+        }
+        out += __popc(hm);
+        __syncwarp();
+    }
+    return out;
+}
+
+template <typename K, int NMAX, int RPW>
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
+k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
+              const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
+              double* __restrict__ c_val, unsigned long long* tile_state) {
+    constexpr int SBK = Log2<NMAX>::v;
+    constexpr int TILE_ROWS = FUSED_WARPS * RPW;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ uint32_t s_nnz[TILE_ROWS];
+    __shared__ unsigned long long s_excl;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    K* keys_w = reinterpret_cast<K*>(s_raw) + (size_t)warp * RPW * NMAX;
+    double* vals_w = reinterpret_cast<double*>(s_raw + sizeof(K) * NMAX * TILE_ROWS) + (size_t)warp * RPW * NMAX;
+
+    // Tile id = blockIdx.x: CTAs of a 1-D grid are dispatched in index order, so every tile this one
+    // looks back at is already resident or finished (the usual decoupled look-back assumption).
+    const uint32_t tile = blockIdx.x;
+    const int64_t r0 = (int64_t)tile * TILE_ROWS + warp * RPW;
+
+    int nnz[RPW];
+    bool light[RPW];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+        nnz[q] = 0;
+        light[q] = false;
+        const int64_t r = r0 + q;
+        K* keys = keys_w + q * NMAX;
+        double* vals = vals_w + q * NMAX;
+        if (r < m) {
+            const uint32_t pf = flops[r];
+            const int bn = bin_of(pf);
+            if (bn >= 1 && bn <= 5) {
+                light[q] = true;
+                const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+                int seq = 0;
+                for (int64_t pb = a_begin; pb < a_end; pb += 32) {
+                    int bt;
+                    expand_batch<true, false>(a, b, pb + lane, a_end, lane, seq, bt, [&](int sq, int64_t qq, double av) {
+                        uint32_t c = (uint32_t)ldg_i32(b.col + qq);
+                        keys[sq] = ((K)c << SBK) | (K)sq;
+                        vals[sq] = __dmul_rn(av, ldg_f64(b.val + qq));
+                    });
+                    seq += bt;
+                }
+                // the window shape of this row: 32 lanes x E keys per lane, E picked by its product count
+                switch (bn) {
+                    case 1: nnz[q] = sort_reduce_in_place<K, 1, SBK>(keys, vals, seq, lane); break;
+                    case 2: if constexpr (NMAX >= 64) nnz[q] = sort_reduce_in_place<K, 2, SBK>(keys, vals, seq, lane); break;
+                    case 3: if constexpr (NMAX >= 128) nnz[q] = sort_reduce_in_place<K, 4, SBK>(keys, vals, seq, lane); break;
+                    case 4: if constexpr (NMAX >= 256) nnz[q] = sort_reduce_in_place<K, 8, SBK>(keys, vals, seq, lane); break;
+                    default: if constexpr (NMAX >= 512) nnz[q] = sort_reduce_in_place<K, 16, SBK>(keys, vals, seq, lane); break;
+                }
+            } else if (bn >= 6) {
+                nnz[q] = (int)pre_nnz[r];
+            }
+        }
+        if (lane == 0) s_nnz[warp * RPW + q] = (uint32_t)nnz[q];
+    }
+    __syncthreads();
+    unsigned long long tile_total = 0, my_off = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_ROWS; ++w) {
+        unsigned long long t = s_nnz[w];
+        if (w < warp * RPW) my_off += t;
+        tile_total += t;
+    }
+    if (warp == 0) {
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(&tile_state[0], FST_PREFIX | tile_total);
+        } else {
+            if (lane == 0) atomicExch(&tile_state[tile], FST_AGG | tile_total);
+            int64_t pidx = (int64_t)tile - 1;
+            while (true) {
+                int64_t idx = pidx - lane;
+                unsigned long long s;
+                do {
+                    s = (idx >= 0) ? *((volatile unsigned long long*)&tile_state[idx]) : FST_PREFIX;
+                } while (__any_sync(FULL, (s & FST_MASK) == 0));
+                unsigned has_prefix = __ballot_sync(FULL, (s & FST_MASK) == FST_PREFIX);
+                unsigned long long val = s & ~FST_MASK;
+                if (has_prefix) {
+                    int first = __ffs(has_prefix) - 1;
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
+                excl += val;
+                if (has_prefix) break;
+                pidx -= 32;
+            }
+            if (lane == 0) atomicExch(&tile_state[tile], FST_PREFIX | (excl + tile_total));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    int64_t base = (int64_t)(s_excl + my_off);
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+        const int64_t r = r0 + q;
+        if (r < m) {
+            if (lane == 0) {
+                c_ptr[r] = base;
+                if (r == m - 1) c_ptr[m] = base + nnz[q];
+            }
+            if (light[q]) {
+                const uint32_t* ocol = reinterpret_cast<const uint32_t*>(keys_w + q * NMAX);
+                const double* vals = vals_w + q * NMAX;
+                for (int j = lane; j < nnz[q]; j += 32) {
+                    c_col[base + j] = (int32_t)ocol[j];
+                    c_val[base + j] = vals[j];
+                }
+            }
+        }
+        base += nnz[q];
+    }
+}
+
+constexpr int fused_rpw(int nmax) { return nmax <= 32 ? 4 : (nmax <= 64 ? 2 : 1); }
+
+template <typename K, int NMAX>
+static void fused_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m, const uint32_t* flops,
+                         const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val, uint64_t* tile_state,
+                         cudaStream_t s) {
+    constexpr int RPW = fused_rpw(NMAX);
+    constexpr int TILE_ROWS = FUSED_WARPS * RPW;
+    size_t smem = (sizeof(K) + sizeof(double)) * NMAX * TILE_ROWS;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_fused_light<K, NMAX, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    size_t tiles = (size_t)((m + TILE_ROWS - 1) / TILE_ROWS);
+    cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
+    k_fused_light<K, NMAX, RPW><<<(unsigned)tiles, FUSED_WARPS * 32, smem, s>>>(
+        a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+}
+
+size_t fused_tile_state_words(int64_t m) { return (size_t)((m + FUSED_WARPS - 1) / FUSED_WARPS) + 1; }
+
+template <typename K>
+static void fused_dispatch(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
+                           const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,
+                           uint64_t* tile_state, cudaStream_t s) {
+    switch (max_bin) {
+        case 1: fused_launch<K, 32>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
+        case 2: fused_launch<K, 64>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
+        case 3: fused_launch<K, 128>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
+        case 4: fused_launch<K, 256>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
+        default: fused_launch<K, 512>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
+    }
+}
+
+// max_bin: the largest warp-per-row bin (1..5) that holds rows; it sizes the shared memory of a tile.
+void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
+                        const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,
+                        uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s) {
+    if (m <= 0) return;
+    if (max_bin < 1) max_bin = 1;
+    if (max_bin > 5) max_bin = 5;
+    (void)ctr;
+    int sbk = 4 + max_bin;
+    bool narrow = (uint64_t)b.cols <= (1ull << (32 - sbk));
+    if (narrow)
+        fused_dispatch<uint32_t>(max_bin, a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s);
+    else
+        fused_dispatch<uint64_t>(max_bin, a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s);
+}
+
+}  // namespace spada

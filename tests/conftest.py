@@ -39,11 +39,12 @@ def cari():
     return a
 
 
-@pytest.fixture(scope="session")
-def engine(spada):
+@pytest.fixture(scope="session", params=["fused", "two_phase"])
+def engine(spada, request):
+    """Both engine modes: single-pass (fused light rows + look-back) and separate symbolic/numeric passes."""
     if spada.device_count() == 0:
         pytest.skip("no CUDA device")
-    e = spada.Engine()
+    e = spada.Engine(two_phase=(request.param == "two_phase"))
     yield e
     e.close()
 
