@@ -15,12 +15,12 @@ constexpr unsigned FULL = 0xffffffffu;
 //   bin 0          p == 0                 nothing to do, nnz = 0
 //   bin 1          p <= 32                one warp per row, products sorted in registers
 //   bin 2..5       p <= 64,128,256,512    one warp per row, E = N/32 keys per lane
-//   bin 6..8       p <= 1024,2048,4096    one CTA per row, shared-memory sort
-//   bin 9          p  > 4096              one CTA per row, bitmap + rank accumulator
-constexpr int NUM_BINS = 10;
+//   bin 6..9       p <= 1024 .. 8192      one CTA per row, shared-memory radix sort
+//   bin 10         p  > 8192              items of ~8192 products over the grid, bitmap + rank
+constexpr int NUM_BINS = 11;
 constexpr int BIN_EMPTY = 0;
-constexpr int BIN_HEAVY = 9;
-constexpr uint32_t ESC_MAX_PRODUCTS = 4096;
+constexpr int BIN_HEAVY = 10;
+constexpr uint32_t ESC_MAX_PRODUCTS = 8192;
 
 __host__ __device__ inline int bin_of(uint32_t p) {
     if (p == 0) return 0;
@@ -32,7 +32,8 @@ __host__ __device__ inline int bin_of(uint32_t p) {
     if (p <= 1024) return 6;
     if (p <= 2048) return 7;
     if (p <= 4096) return 8;
-    return 9;
+    if (p <= 8192) return 9;
+    return 10;
 }
 __host__ __device__ inline uint32_t bin_capacity(int b) { return b == 0 ? 0u : (b >= BIN_HEAVY ? 0u : (32u << (b - 1))); }
 
@@ -95,10 +96,14 @@ __device__ __forceinline__ int64_t ldg_i64(const int64_t* p) { return __ldg(p); 
 // consecutive lanes on consecutive elements (coalesced) whatever their length.  This is the
 // reference's "window" of A scalars fanned out over the lanes (scheduler.rs:551-556,
 // simulator.rs:728-757) with L = 32.
-// emit(seq, q, a_val): seq = arrival index of the product inside the C row (ascending k, then
-// B's stored order), q = position in B's arrays.  BIG: B rows longer than 2^24 are streamed one
-// at a time by the whole warp (keeps the 32-bit scan from overflowing); their seq is unused.
+// seq = arrival index of the product inside the C row (ascending k, then B's stored order).
+// BIG: B rows longer than 2^24 are streamed one at a time by the whole warp (keeps the 32-bit
+// scan from overflowing); their seq is unused.
 constexpr int EXPAND_BIG_LEN = 1 << 24;
+constexpr int EXPAND_UNROLL = 4;  // independent B gathers in flight per lane
+// emit(seq, col, a_val, b_val): the B column id (and value when NUMERIC) are already loaded.  The loads
+// of EXPAND_UNROLL consecutive steps are issued back to back before any of them is consumed, so a
+// warp keeps several HBM/L2 round trips in flight instead of one.
 template <bool NUMERIC, bool BIG, typename F>
 __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, int64_t p, int64_t a_end,
                                              int lane, int seq_base, int& batch_total, F&& emit) {
@@ -123,19 +128,43 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
     int total;
     int off = warp_excl_scan(len, lane, total);
     batch_total = total;
-    for (int base = 0; base < total; base += 32) {
-        int t = base + lane;
-        int j = 0;
+    for (int base = 0; base < total; base += 32 * EXPAND_UNROLL) {
+        int64_t q[EXPAND_UNROLL];
+        double aj[EXPAND_UNROLL];
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            int o = __shfl_sync(FULL, off, j + s);
-            if (o <= t) j += s;
+        for (int u = 0; u < EXPAND_UNROLL; ++u) {
+            q[u] = 0;
+            aj[u] = 0.0;
+            if (base + u * 32 < total) {  // warp-uniform
+                int t = base + u * 32 + lane;
+                int j = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    int o = __shfl_sync(FULL, off, j + s);
+                    if (o <= t) j += s;
+                }
+                int oj = __shfl_sync(FULL, off, j);
+                int64_t bsj = shfl_i64(bs, j);
+                if (NUMERIC) aj[u] = shfl_f64(av, j);
+                q[u] = bsj + (t - oj);
+            }
         }
-        int oj = __shfl_sync(FULL, off, j);
-        int64_t bsj = shfl_i64(bs, j);
-        double aj = 0.0;
-        if (NUMERIC) aj = shfl_f64(av, j);
-        if (t < total) emit(seq_base + t, bsj + (t - oj), aj);
+        uint32_t c[EXPAND_UNROLL];
+        double bv[EXPAND_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EXPAND_UNROLL; ++u) {
+            c[u] = 0;
+            bv[u] = 0.0;
+            if (base + u * 32 + lane < total) {
+                c[u] = (uint32_t)ldg_i32(b.col + q[u]);
+                if (NUMERIC) bv[u] = ldg_f64(b.val + q[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EXPAND_UNROLL; ++u) {
+            int t = base + u * 32 + lane;
+            if (t < total) emit(seq_base + t, c[u], aj[u], bv[u]);
+        }
     }
     if (BIG) {
         while (big) {
@@ -145,7 +174,8 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
             int lj = __shfl_sync(FULL, big_len, j);
             double aj = 0.0;
             if (NUMERIC) aj = shfl_f64(av, j);
-            for (int t = lane; t < lj; t += 32) emit(-1, bsj + t, aj);
+            for (int t = lane; t < lj; t += 32)
+                emit(-1, (uint32_t)ldg_i32(b.col + bsj + t), aj, NUMERIC ? ldg_f64(b.val + bsj + t) : 0.0);
         }
     }
 }
@@ -197,6 +227,11 @@ void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, con
                         const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
                         uint32_t wave_hi, const uint2* ws, const HeavyPlan& P, const int64_t* c_ptr, double* c_val,
                         int sm_count, cudaStream_t s);
+// bitonic variant of the CTA-per-row bins 6..8 (esc_cta_bitonic.cu)
+void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                                 uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
+void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                                uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
 void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,

@@ -66,6 +66,7 @@ struct spada_b200 {
     std::unordered_map<void*, size_t> pool_live;
     size_t pool_bytes = 0;
     size_t dev_total_mem = 0;
+    bool cta_bitonic = true;  // sort of the CTA-per-row bins 1024..4096: bitonic (default) or radix
     size_t heavy_ws_budget = (size_t)2 << 30;  // bitmap workspace for the heavy bin (SPADA_B200_HEAVY_WS_MB)
 };
 
@@ -175,7 +176,7 @@ struct LaunchRec {
 };
 
 const char* bin_name(int b) {
-    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy"};
+    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "8192", "heavy"};
     return names[b];
 }
 
@@ -300,6 +301,7 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
     CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_scalar, 64));
     setup_kernel_attributes();
+    if (const char* e = getenv("SPADA_B200_CTA_SORT")) h->cta_bitonic = strcmp(e, "radix") != 0;
     if (const char* e = getenv("SPADA_B200_HEAVY_WS_MB")) {
         long mb = atol(e);
         if (mb > 0) h->heavy_ws_budget = (size_t)mb << 20;
@@ -655,7 +657,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         st.bin_rows[bnum] = pc.bin_rows[bnum];
         st.bin_products[bnum] = pc.bin_products[bnum];
         st.bin_window_rows[bnum] = (bnum >= 1 && bnum <= 5) ? 4u : (bnum == 0 ? 0u : 1u);
-        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : (bnum == BIN_HEAVY ? 512u : 256u));
+        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : (bnum == BIN_HEAVY ? 256u : (bnum == 9 ? 512u : 256u)));
     }
     tbl.offset[NUM_BINS] = off;
     // a single non-empty bin holding every row needs no permutation
@@ -726,7 +728,10 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             }
         } else {
             begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
-            launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
+            if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
+                launch_bitonic_cta_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
+            else
+                launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
             kernels += 1;
         }
         CUT(cudaGetLastError());
@@ -794,7 +799,11 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             }
         } else {
             begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
-            launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
+            if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
+                launch_bitonic_cta_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col,
+                                           R->val, s);
+            else
+                launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
             kernels += 1;
         }
         CUT(cudaGetLastError());

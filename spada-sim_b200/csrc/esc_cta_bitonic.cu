@@ -1,0 +1,265 @@
+// esc_cta_bitonic.cu -- CTA-per-row ESC kernels (1024 / 2048 / 4096 products) with the hybrid
+// bitonic sort: every warp sorts its chunk in registers, chunks are merged through shared memory.
+// Kept beside the radix-sort variant of esc.cu; SPADA_B200_CTA_SORT picks one (see engine.cu).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace spada {
+
+constexpr int ESC_CTA_THREADS = 256;
+
+// =============================================================================================
+// CTA-per-row kernels, N = 1024 / 2048 / 4096 products at most; 8 warps, chunk = N/8 keys per warp
+// =============================================================================================
+
+// Shared staging of one batch of A entries (one per thread): arrival offset, start of the B row,
+// A value.  The products of the batch are then dealt to ALL threads of the CTA (thread t takes
+// products t, t+256, ...), each finding its A entry by binary search over the offsets -- the
+// expansion stays busy on every warp even when the A row has few, long-ish B rows to visit.
+struct CtaStage {
+    int off[ESC_CTA_THREADS + 1];
+    int64_t bs[ESC_CTA_THREADS];
+    double av[ESC_CTA_THREADS];
+    int wtot[ESC_CTA_THREADS / 32];
+};
+
+template <typename K, int N, bool NUMERIC>
+__device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr& b, int64_t a_begin, int64_t a_end,
+                                                  K* keys, double* vals, CtaStage& st) {
+    constexpr int SB = Log2<N>::v;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    int seq_base = 0;
+    for (int64_t pb = a_begin; pb < a_end; pb += ESC_CTA_THREADS) {
+        const int64_t p = pb + threadIdx.x;
+        int len = 0;
+        int64_t bs = 0;
+        double av = 0.0;
+        if (p < a_end) {
+            int32_t k = ldg_i32(a.col + p);
+            if (NUMERIC) av = ldg_f64(a.val + p);
+            bs = ldg_i64(b.ptr + k);
+            len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+        }
+        int wtotal;
+        int woff = warp_excl_scan(len, lane, wtotal);
+        if (lane == 0) st.wtot[warp] = wtotal;
+        __syncthreads();
+        int base = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < ESC_CTA_THREADS / 32; ++w) {
+            int t = st.wtot[w];
+            if (w < warp) base += t;
+            all += t;
+        }
+        st.off[threadIdx.x] = base + woff;
+        st.bs[threadIdx.x] = bs;
+        if (NUMERIC) st.av[threadIdx.x] = av;
+        if (threadIdx.x == 0) st.off[ESC_CTA_THREADS] = all;
+        __syncthreads();
+        const int n_ent = (int)((a_end - pb) < ESC_CTA_THREADS ? (a_end - pb) : ESC_CTA_THREADS);
+        for (int t0 = threadIdx.x; t0 < all; t0 += 2 * ESC_CTA_THREADS) {
+            // two products per step: independent searches and gathers in flight
+            int t[2] = {t0, t0 + ESC_CTA_THREADS};
+            int64_t q[2];
+            int j[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                int lo = 0, hi = n_ent;  // largest j in [0, n_ent) with off[j] <= t
+                if (t[u] < all) {
+                    while (hi - lo > 1) {
+                        int mid = (lo + hi) >> 1;
+                        if (st.off[mid] <= t[u]) lo = mid; else hi = mid;
+                    }
+                }
+                j[u] = lo;
+                q[u] = st.bs[lo] + (t[u] - st.off[lo]);
+            }
+            uint32_t c[2];
+            double bv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                c[u] = 0;
+                bv[u] = 0.0;
+                if (t[u] < all) {
+                    c[u] = (uint32_t)ldg_i32(b.col + q[u]);
+                    if (NUMERIC) bv[u] = ldg_f64(b.val + q[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (t[u] < all) {
+                    int sq = seq_base + t[u];
+                    if (NUMERIC) {
+                        keys[sq] = ((K)c[u] << SB) | (K)sq;
+                        vals[sq] = __dmul_rn(st.av[j[u]], bv[u]);
+                    } else {
+                        keys[sq] = (K)c[u];
+                    }
+                }
+            }
+        }
+        seq_base += all;
+        __syncthreads();
+    }
+    return seq_base;
+}
+
+template <typename K, int N>
+__device__ __forceinline__ void bitonic_cta_sort(K* keys) {
+    constexpr int WARPS = ESC_CTA_THREADS / 32;
+    constexpr int CH = N / WARPS;  // keys per warp chunk
+    constexpr int E = CH / 32;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    K x[E];
+    load_blocked<K, E>(x, keys + warp * CH, lane);
+    warp_sort<K, E>(x, lane, (warp & 1) != 0);
+    store_blocked<K, E>(x, keys + warp * CH, lane);
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 2 * CH; k <= N; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j >= CH; j >>= 1) {
+            for (int t = threadIdx.x; t < N / 2; t += ESC_CTA_THREADS) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int l = i | j;
+                bool up = (i & k) == 0;
+                K ka = keys[i], kb = keys[l];
+                if ((ka > kb) == up) {
+                    keys[i] = kb;
+                    keys[l] = ka;
+                }
+            }
+            __syncthreads();
+        }
+        load_blocked<K, E>(x, keys + warp * CH, lane);
+        warp_merge_tail<K, E>(x, lane, ((warp * CH) & k) == 0);
+        store_blocked<K, E>(x, keys + warp * CH, lane);
+        __syncthreads();
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(ESC_CTA_THREADS)
+k_bitonic_symbolic_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
+                   uint32_t* __restrict__ row_nnz) {
+    __shared__ __align__(16) uint32_t s_keys[N];
+    __shared__ CtaStage st;
+    int* s_wtot = st.wtot;
+    const uint32_t r = perm ? perm[blockIdx.x] : blockIdx.x;
+    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+    const int p = bitonic_cta_expand<uint32_t, N, false>(a, b, a_begin, a_end, s_keys, nullptr, st);
+    for (int t = p + threadIdx.x; t < N; t += ESC_CTA_THREADS) s_keys[t] = 0xffffffffu;
+    __syncthreads();
+    bitonic_cta_sort<uint32_t, N>(s_keys);
+    int cnt = 0;
+    for (int i = threadIdx.x; i < p; i += ESC_CTA_THREADS)
+        if (i == 0 || s_keys[i] != s_keys[i - 1]) ++cnt;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+    if (lane_id() == 0) s_wtot[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < ESC_CTA_THREADS / 32; ++w) t += s_wtot[w];
+        row_nnz[r] = (uint32_t)t;
+    }
+}
+
+template <typename K, int N>
+__global__ void __launch_bounds__(ESC_CTA_THREADS)
+k_bitonic_numeric_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
+                      const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+    constexpr int SB = Log2<N>::v;
+    constexpr int ITEMS = N / ESC_CTA_THREADS;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    K* keys = reinterpret_cast<K*>(s_raw);
+    double* vals = reinterpret_cast<double*>(s_raw + sizeof(K) * N);
+    __shared__ CtaStage st;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t r = perm ? perm[blockIdx.x] : blockIdx.x;
+    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+    const int p = bitonic_cta_expand<K, N, true>(a, b, a_begin, a_end, keys, vals, st);
+    for (int t = p + threadIdx.x; t < N; t += ESC_CTA_THREADS) keys[t] = KeyTraits<K>::sentinel;
+    __syncthreads();
+    bitonic_cta_sort<K, N>(keys);
+    // thread t owns the sorted positions [t*ITEMS, (t+1)*ITEMS): count the run heads among them, one
+    // block scan places them, then every head sums its run left to right (runs may reach into the
+    // next thread's positions; a thread skips the tail of a run that started before its range)
+    const int i0 = threadIdx.x * ITEMS;
+    uint32_t col[ITEMS];
+    bool head[ITEMS];
+    int cnt = 0;
+    uint32_t prev = (i0 > 0 && i0 <= p) ? (uint32_t)(keys[i0 - 1] >> SB) : 0xffffffffu;
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        const int i = i0 + e;
+        col[e] = (i < p) ? (uint32_t)(keys[i] >> SB) : 0xffffffffu;
+        head[e] = (i < p) && (i == 0 || col[e] != prev);
+        prev = col[e];
+        cnt += head[e] ? 1 : 0;
+    }
+    int wtotal;
+    int woff = warp_excl_scan(cnt, lane, wtotal);
+    __syncthreads();
+    if (lane == 0) st.wtot[warp] = wtotal;
+    __syncthreads();
+    int o = woff;
+#pragma unroll
+    for (int w = 0; w < ESC_CTA_THREADS / 32; ++w)
+        if (w < warp) o += st.wtot[w];
+    const int64_t cbase = c_ptr[r];
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        if (head[e]) {
+            const int i = i0 + e;
+            double sum = vals[(int)(keys[i] & (K)(N - 1))];
+            for (int j = i + 1; j < p; ++j) {
+                K kj = keys[j];
+                if ((uint32_t)(kj >> SB) != col[e]) break;
+                sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
+            }
+            c_col[cbase + o] = (int32_t)col[e];
+            c_val[cbase + o] = sum;
+            ++o;
+        }
+    }
+}
+
+template <typename K, int N>
+static void bitonic_numeric_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                                   uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+    size_t smem = (sizeof(K) + sizeof(double)) * N;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_bitonic_numeric_cta<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    k_bitonic_numeric_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val);
+}
+
+void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                                 uint32_t rows, uint32_t* row_nnz, cudaStream_t s) {
+    if (rows == 0) return;
+    switch (bin) {
+        case 6: k_bitonic_symbolic_cta<1024><<<rows, ESC_CTA_THREADS, 0, s>>>(a, b, row_begin, perm, rows, row_nnz); break;
+        case 7: k_bitonic_symbolic_cta<2048><<<rows, ESC_CTA_THREADS, 0, s>>>(a, b, row_begin, perm, rows, row_nnz); break;
+        default: k_bitonic_symbolic_cta<4096><<<rows, ESC_CTA_THREADS, 0, s>>>(a, b, row_begin, perm, rows, row_nnz); break;
+    }
+}
+
+void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                                uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+    if (rows == 0) return;
+    int sb = 4 + bin;
+    bool narrow = (uint64_t)b.cols <= (1ull << (32 - sb));
+#define BITONIC_CASE(K)                                                                                      \
+    switch (bin) {                                                                                            \
+        case 6: bitonic_numeric_launch<K, 1024>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;  \
+        case 7: bitonic_numeric_launch<K, 2048>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;  \
+        default: bitonic_numeric_launch<K, 4096>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break; \
+    }
+    if (narrow) { BITONIC_CASE(uint32_t) } else { BITONIC_CASE(uint64_t) }
+#undef BITONIC_CASE
+}
+
+}  // namespace spada

@@ -119,11 +119,11 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
                 int seq = 0;
                 for (int64_t pb = a_begin; pb < a_end; pb += 32) {
                     int bt;
-                    expand_batch<true, false>(a, b, pb + lane, a_end, lane, seq, bt, [&](int sq, int64_t qq, double av) {
-                        uint32_t c = (uint32_t)ldg_i32(b.col + qq);
-                        keys[sq] = ((K)c << SBK) | (K)sq;
-                        vals[sq] = __dmul_rn(av, ldg_f64(b.val + qq));
-                    });
+                    expand_batch<true, false>(a, b, pb + lane, a_end, lane, seq, bt,
+                                              [&](int sq, uint32_t c, double av, double bv) {
+                                                  keys[sq] = ((K)c << SBK) | (K)sq;
+                                                  vals[sq] = __dmul_rn(av, bv);
+                                              });
                     seq += bt;
                 }
                 // the window shape of this row: 32 lanes x E keys per lane, E picked by its product count

@@ -94,8 +94,7 @@ k_heavy_bits(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__
         // that are already set need no atomic at all (the OR is idempotent).
         for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
             int bt;
-            expand_batch<false, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, int64_t q, double) {
-                uint32_t c = (uint32_t)ldg_i32(b.col + q);
+            expand_batch<false, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, uint32_t c, double, double) {
                 uint32_t bit = 1u << (c & 31);
                 if (!(__ldcg(&w[c >> 5].x) & bit)) atomicOr(&w[c >> 5].x, bit);
             });
@@ -178,9 +177,8 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
         bool pend = false;
         for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
             int bt;
-            expand_batch<true, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, int64_t q, double av) {
-                uint32_t c = (uint32_t)ldg_i32(b.col + q);
-                double prod = __dmul_rn(av, ldg_f64(b.val + q));
+            expand_batch<true, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, uint32_t c, double av, double bv) {
+                double prod = __dmul_rn(av, bv);
                 uint2 e = __ldcg(&w[c >> 5]);
                 uint32_t pos = e.y + __popc(e.x & ((1u << (c & 31)) - 1u));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(out + pos));
