@@ -128,6 +128,23 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
     int total;
     int off = warp_excl_scan(len, lane, total);
     batch_total = total;
+    if (total <= 32) {
+        // short batch (tiny rows): one step, no unrolling overhead
+        int j = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            int o = __shfl_sync(FULL, off, j + s);
+            if (o <= lane) j += s;
+        }
+        int oj = __shfl_sync(FULL, off, j);
+        int64_t bsj = shfl_i64(bs, j);
+        double aj = 0.0;
+        if (NUMERIC) aj = shfl_f64(av, j);
+        if (lane < total) {
+            int64_t q = bsj + (lane - oj);
+            emit(seq_base + lane, (uint32_t)ldg_i32(b.col + q), aj, NUMERIC ? ldg_f64(b.val + q) : 0.0);
+        }
+    } else
     for (int base = 0; base < total; base += 32 * EXPAND_UNROLL) {
         int64_t q[EXPAND_UNROLL];
         double aj[EXPAND_UNROLL];

@@ -200,6 +200,153 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiny rows (at most 32 products, e.g. the 5-point stencil: 25 products, 13 outputs per row): the
+// column-wise end of Spada's window shapes.  One product per lane, the whole row lives in
+// registers: a 32-key bitonic network (15 compare-exchange steps), shuffles for the values, a
+// ballot for the run heads.  32 consecutive rows form a tile (8 warps x 4 rows) that is placed by
+// the same decoupled look-back as above.
+constexpr int TINY_RPW = 4;
+constexpr int TINY_TILE = FUSED_WARPS * TINY_RPW;
+
+template <typename K>
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
+k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
+             const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
+             double* __restrict__ c_val, unsigned long long* tile_state) {
+    __shared__ uint32_t s_col[TINY_TILE][32];
+    __shared__ double s_val[TINY_TILE][32];
+    __shared__ uint32_t s_nnz[TINY_TILE];   // nnz of every row of the tile
+    __shared__ uint32_t s_off[TINY_TILE];   // exclusive offsets inside the tile
+    __shared__ uint32_t s_light;            // bit rt set <=> row rt was computed here
+    __shared__ unsigned long long s_excl;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (threadIdx.x == 0) s_light = 0u;
+    __syncthreads();
+
+#pragma unroll 1
+    for (int q = 0; q < TINY_RPW; ++q) {
+        const int rt = warp * TINY_RPW + q;
+        const int64_t r = (int64_t)tile * TINY_TILE + rt;
+        int nnz = 0;
+        if (r < m) {
+            const int bn = bin_of(flops[r]);
+            if (bn == 1) {
+                const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+                uint32_t* rc = s_col[rt];
+                double* rv = s_val[rt];
+                int p = 0;
+                for (int64_t pb = a_begin; pb < a_end; pb += 32) {
+                    int bt;
+                    expand_batch<true, false>(a, b, pb + lane, a_end, lane, p, bt,
+                                              [&](int sq, uint32_t c, double av, double bv) {
+                                                  rc[sq] = c;
+                                                  rv[sq] = __dmul_rn(av, bv);
+                                              });
+                    p += bt;
+                }
+                __syncwarp();
+                const bool have = lane < p;
+                K x[1];
+                x[0] = have ? (((K)rc[lane] << 5) | (K)lane) : KeyTraits<K>::sentinel;
+                const double prod = have ? rv[lane] : 0.0;
+                __syncwarp();
+                warp_sort<K, 1>(x, lane, false);
+                const uint32_t col = (uint32_t)(x[0] >> 5);
+                const double v = shfl_f64(prod, (int)(x[0] & (K)31));
+                const uint32_t col_prev = __shfl_up_sync(FULL, col, 1);
+                const bool head = have && (lane == 0 || col_prev != col);
+                const unsigned hm = __ballot_sync(FULL, head);
+                const unsigned mem = __ballot_sync(FULL, have && !head);   // run members after their head
+                double sum = v;
+                for (int d = 1; d < 32; ++d) {
+                    const unsigned need = (1u << d) - 1u;
+                    const unsigned after = lane < 31 ? (mem >> (lane + 1)) : 0u;
+                    const bool cont = head && (lane + d < 32) && ((after & need) == need);
+                    if (!__any_sync(FULL, cont)) break;
+                    const double nv = shfl_f64(v, (lane + d) & 31);
+                    if (cont) sum = __dadd_rn(sum, nv);
+                }
+                if (head) {
+                    const int pos = __popc(hm & ((1u << lane) - 1u));
+                    rc[pos] = col;
+                    rv[pos] = sum;
+                }
+                nnz = __popc(hm);
+                if (lane == 0) atomicOr(&s_light, 1u << rt);
+            } else if (bn >= 2) {
+                nnz = (int)pre_nnz[r];   // counted by its own symbolic kernel
+            }
+        }
+        if (lane == 0) s_nnz[rt] = (uint32_t)nnz;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the 32 row counts, then the look-back for the tile's base
+        const uint32_t n = s_nnz[lane];
+        uint32_t x = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        s_off[lane] = x - n;
+        const unsigned long long tile_total = __shfl_sync(FULL, x, 31);
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(&tile_state[0], FST_PREFIX | tile_total);
+        } else {
+            if (lane == 0) atomicExch(&tile_state[tile], FST_AGG | tile_total);
+            int64_t pidx = (int64_t)tile - 1;
+            while (true) {
+                int64_t idx = pidx - lane;
+                unsigned long long s;
+                do {
+                    s = (idx >= 0) ? *((volatile unsigned long long*)&tile_state[idx]) : FST_PREFIX;
+                } while (__any_sync(FULL, (s & FST_MASK) == 0));
+                unsigned has_prefix = __ballot_sync(FULL, (s & FST_MASK) == FST_PREFIX);
+                unsigned long long val = s & ~FST_MASK;
+                if (has_prefix) {
+                    int first = __ffs(has_prefix) - 1;
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
+                excl += val;
+                if (has_prefix) break;
+                pidx -= 32;
+            }
+            if (lane == 0) atomicExch(&tile_state[tile], FST_PREFIX | (excl + tile_total));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    // row_ptr: one thread per row of the tile
+    if (threadIdx.x < TINY_TILE) {
+        const int64_t r = (int64_t)tile * TINY_TILE + threadIdx.x;
+        if (r < m) {
+            const int64_t base = (int64_t)(s_excl + s_off[threadIdx.x]);
+            c_ptr[r] = base;
+            if (r == m - 1) c_ptr[m] = base + s_nnz[threadIdx.x];
+        }
+    }
+    // entries: a warp stores its four rows as one contiguous stream
+    const int rt0 = warp * TINY_RPW;
+    const uint32_t n0 = s_nnz[rt0], n1 = s_nnz[rt0 + 1], n2 = s_nnz[rt0 + 2], n3 = s_nnz[rt0 + 3];
+    const uint32_t c1 = n0, c2 = n0 + n1, c3 = n0 + n1 + n2, tot = c3 + n3;
+    const int64_t wbase = (int64_t)(s_excl + s_off[rt0]);
+    const uint32_t lightmask = (s_light >> rt0) & 0xfu;
+    for (uint32_t e = lane; e < tot; e += 32) {
+        const int q = (e >= c1) + (e >= c2) + (e >= c3);
+        if ((lightmask >> q) & 1u) {
+            const uint32_t idx = e - (q == 0 ? 0u : (q == 1 ? c1 : (q == 2 ? c2 : c3)));
+            c_col[wbase + e] = (int32_t)s_col[rt0 + q][idx];
+            c_val[wbase + e] = s_val[rt0 + q][idx];
+        }
+    }
+}
+
 constexpr int fused_rpw(int nmax) { return nmax <= 32 ? 4 : (nmax <= 64 ? 2 : 1); }
 
 template <typename K, int NMAX>
@@ -243,6 +390,17 @@ void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t r
     if (max_bin < 1) max_bin = 1;
     if (max_bin > 5) max_bin = 5;
     (void)ctr;
+    if (max_bin == 1) {
+        size_t tiles = (size_t)((m + TINY_TILE - 1) / TINY_TILE);
+        cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
+        if ((uint64_t)b.cols <= (1ull << 27))
+            k_fused_tiny<uint32_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
+                a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+        else
+            k_fused_tiny<uint64_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
+                a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+        return;
+    }
     int sbk = 4 + max_bin;
     bool narrow = (uint64_t)b.cols <= (1ull << (32 - sbk));
     if (narrow)
