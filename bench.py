@@ -203,7 +203,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="<1 shrinks the workload (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--two-phase", action="store_true", help="separate symbolic/numeric passes (exact-size C)")
+    ap.add_argument("--two-phase", action="store_true", help="force separate symbolic/numeric passes (exact-size C)")
+    ap.add_argument("--single-pass", action="store_true", help="force the fused single pass for rows <= 512 products")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -226,7 +227,8 @@ def main():
     D = importlib.import_module("spada-sim_b200.distributed")
 
     stream = torch.cuda.current_stream()
-    eng = pkg.Engine(device=local_rank, validate=True, stream=stream.cuda_stream, two_phase=args.two_phase)
+    eng = pkg.Engine(device=local_rank, validate=True, stream=stream.cuda_stream, two_phase=args.two_phase,
+                     single_pass=args.single_pass)
 
     # ---- operands resident in HBM (not timed) ---------------------------------------------------
     a = b = None

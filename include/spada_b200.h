@@ -98,9 +98,10 @@ typedef struct spada_b200_opts {
 } spada_b200_opts;
 
 #define SPADA_B200_FLAG_VALIDATE 1u  /* check canonical CSR on upload (UNSORTED_INPUT) */
-#define SPADA_B200_FLAG_TWO_PHASE 2u /* always run the separate symbolic + numeric passes (exact-size C);
-                                        default: rows with <= 512 products are done in one fused pass and C is
-                                        allocated with capacity = intermediate-product count */
+#define SPADA_B200_FLAG_TWO_PHASE 2u /* always run the separate symbolic + numeric passes (exact-size C) */
+#define SPADA_B200_FLAG_SINGLE_PASS 4u /* always do rows with <= 512 products in one fused pass (C is then
+                                          allocated with capacity = intermediate-product count).  With neither
+                                          flag the engine picks: single pass when one bin holds >= 80 % of the rows */
 
 typedef struct spada_b200 spada_b200_t;               /* engine handle (streams, workspace pool) */
 typedef struct spada_b200_csr spada_b200_csr_t;       /* device-resident operand */

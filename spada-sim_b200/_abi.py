@@ -19,6 +19,7 @@ STATUS = {0: "OK", 1: "INVALID_ARG", 2: "UNSORTED_INPUT", 3: "DIM_MISMATCH", 4: 
 ACCELERATORS = {"ip": 0, "op": 1, "multirow": 2, "spada": 3}
 FLAG_VALIDATE = 1
 FLAG_TWO_PHASE = 2
+FLAG_SINGLE_PASS = 4
 
 
 class CsrView(C.Structure):

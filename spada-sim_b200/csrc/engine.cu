@@ -683,8 +683,17 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             max_light_bin = bnum;
             light_rows += pc.bin_rows[bnum];
         }
-    const bool fused = !(h->opts.flags & SPADA_B200_FLAG_TWO_PHASE) && light_rows > 0 &&
-                       (double)pc.total_products * 12.0 <= 0.45 * (double)h->dev_total_mem;
+    // The look-back places rows in row order, so a tile finishes with its slowest row: the single pass
+    // pays off when the rows look alike (one bin holds >= 80 % of the non-empty rows, e.g. stencils and
+    // uniform random graphs: measured 1.3x-1.6x), not on heavy-tailed row lengths (0.9x) -- see DESIGN.md.
+    uint64_t dominant = 0, non_empty = 0;
+    for (int bnum = 1; bnum < NUM_BINS; ++bnum) {
+        non_empty += pc.bin_rows[bnum];
+        if (bnum <= 5) dominant = std::max<uint64_t>(dominant, pc.bin_rows[bnum]);
+    }
+    bool fused = !(h->opts.flags & SPADA_B200_FLAG_TWO_PHASE) && light_rows > 0 &&
+                 (double)pc.total_products * 12.0 <= 0.45 * (double)h->dev_total_mem;
+    if (fused && !(h->opts.flags & SPADA_B200_FLAG_SINGLE_PASS) && dominant * 10 < non_empty * 8) fused = false;
     const int first_sym_bin = fused ? 6 : 1;
 
     // heavy rows: cut into items, bitmaps for one wave of rows at a time

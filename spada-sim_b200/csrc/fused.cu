@@ -23,72 +23,77 @@
 
 namespace spada {
 
-constexpr int FUSED_WARPS = 8;  // warps per tile; each warp owns RPW consecutive rows of the tile
+constexpr int FUSED_WARPS = 8;  // warps per tile of the tiny-row kernel
+constexpr int LIGHT_WARPS = 4;  // warps per tile of the general kernel; each warp owns RPW consecutive rows
 
 #define FST_AGG (1ull << 62)
 #define FST_PREFIX (2ull << 62)
 #define FST_MASK (3ull << 62)
 
-// sort the warp's N = 32*E packed keys, bring the products into sorted order, then sum equal
-// columns left to right and compact in place: on return ocol[0..nnz) / vals[0..nnz) hold the row.
+// sort the warp's N = 32*E packed keys in registers, leave them sorted in shared memory (blocked
+// layout = sorted order) and return the number of distinct columns among the first p keys
 template <typename K, int E, int SBK>
-__device__ __forceinline__ int sort_reduce_in_place(K* keys, double* vals, int p, int lane) {
+__device__ __forceinline__ int sort_count(K* keys, int p, int lane) {
     constexpr int N = 32 * E;
     for (int t = p + lane; t < N; t += 32) keys[t] = KeyTraits<K>::sentinel;
     __syncwarp();
     K x[E];
     load_blocked<K, E>(x, keys, lane);
     warp_sort<K, E>(x, lane, false);
-    double v[E];
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-        int sq = (int)(x[r] & (K)((1u << SBK) - 1u));
-        v[r] = (lane * E + r < p) ? vals[sq] : 0.0;
-    }
     __syncwarp();
     store_blocked<K, E>(x, keys, lane);
+    const K prev = shfl_up_key(x[E - 1]);
+    int cnt = 0;
 #pragma unroll
-    for (int r = 0; r < E; ++r) vals[lane * E + r] = v[r];
+    for (int i = 0; i < E; ++i) {
+        const bool first = (lane == 0 && i == 0);
+        const K pv = (i == 0) ? prev : x[i - 1];
+        if (x[i] != KeyTraits<K>::sentinel && (first || (uint32_t)(x[i] >> SBK) != (uint32_t)(pv >> SBK))) ++cnt;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
     __syncwarp();
-    uint32_t* ocol = reinterpret_cast<uint32_t*>(keys);
-    int out = 0;
+    return cnt;
+}
+
+// sums equal columns of the sorted row left to right and stores the row at c_col/c_val + base
+template <typename K, int SBK>
+__device__ __forceinline__ void reduce_store(const K* keys, const double* vals, int p, int lane, int64_t base,
+                                             int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+    int out_base = 0;
     uint32_t prev_last = 0;
-    for (int base = 0; base < p; base += 32) {
-        const int i = base + lane;
+    for (int cb = 0; cb < p; cb += 32) {
+        const int i = cb + lane;
         const bool valid = i < p;
-        const uint32_t col = valid ? (uint32_t)(keys[i] >> SBK) : 0xffffffffu;
+        const K ki = valid ? keys[i] : KeyTraits<K>::sentinel;
+        const uint32_t col = (uint32_t)(ki >> SBK);
         uint32_t col_prev = __shfl_up_sync(FULL, col, 1);
         if (lane == 0) col_prev = prev_last;
         const bool head = valid && (i == 0 || col_prev != col);
         const unsigned hm = __ballot_sync(FULL, head);
-        double sum = 0.0;
-        if (head) {
-            sum = vals[i];
-            for (int j = i + 1; j < p; ++j) {
-                if ((uint32_t)(keys[j] >> SBK) != col) break;
-                sum = __dadd_rn(sum, vals[j]);
-            }
-        }
         prev_last = __shfl_sync(FULL, col, 31);
-        __syncwarp();  // every read of this chunk (and its forward runs) is done before the compaction writes
         if (head) {
-            int o = out + __popc(hm & ((1u << lane) - 1u));
-            ocol[o] = col;
-            vals[o] = sum;
+            double sum = vals[(int)(ki & (K)((1u << SBK) - 1u))];
+            for (int j = i + 1; j < p; ++j) {
+                const K kj = keys[j];
+                if ((uint32_t)(kj >> SBK) != col) break;
+                sum = __dadd_rn(sum, vals[(int)(kj & (K)((1u << SBK) - 1u))]);
+            }
+            const int o = out_base + __popc(hm & ((1u << lane) - 1u));
+            c_col[base + o] = (int32_t)col;
+            c_val[base + o] = sum;
         }
-        out += __popc(hm);
-        __syncwarp();
+        out_base += __popc(hm);
     }
-    return out;
 }
 
 template <typename K, int NMAX, int RPW>
-__global__ void __launch_bounds__(FUSED_WARPS * 32)
+__global__ void __launch_bounds__(LIGHT_WARPS * 32)
 k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
               const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
               double* __restrict__ c_val, unsigned long long* tile_state) {
     constexpr int SBK = Log2<NMAX>::v;
-    constexpr int TILE_ROWS = FUSED_WARPS * RPW;
+    constexpr int TILE_ROWS = LIGHT_WARPS * RPW;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ uint32_t s_nnz[TILE_ROWS];
     __shared__ unsigned long long s_excl;
@@ -102,11 +107,11 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
     const int64_t r0 = (int64_t)tile * TILE_ROWS + warp * RPW;
 
     int nnz[RPW];
-    bool light[RPW];
+    int prod[RPW];   // products of a row computed here, -1 otherwise
 #pragma unroll
     for (int q = 0; q < RPW; ++q) {
         nnz[q] = 0;
-        light[q] = false;
+        prod[q] = -1;
         const int64_t r = r0 + q;
         K* keys = keys_w + q * NMAX;
         double* vals = vals_w + q * NMAX;
@@ -114,7 +119,6 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
             const uint32_t pf = flops[r];
             const int bn = bin_of(pf);
             if (bn >= 1 && bn <= 5) {
-                light[q] = true;
                 const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
                 int seq = 0;
                 for (int64_t pb = a_begin; pb < a_end; pb += 32) {
@@ -126,13 +130,14 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
                                               });
                     seq += bt;
                 }
+                prod[q] = seq;
                 // the window shape of this row: 32 lanes x E keys per lane, E picked by its product count
                 switch (bn) {
-                    case 1: nnz[q] = sort_reduce_in_place<K, 1, SBK>(keys, vals, seq, lane); break;
-                    case 2: if constexpr (NMAX >= 64) nnz[q] = sort_reduce_in_place<K, 2, SBK>(keys, vals, seq, lane); break;
-                    case 3: if constexpr (NMAX >= 128) nnz[q] = sort_reduce_in_place<K, 4, SBK>(keys, vals, seq, lane); break;
-                    case 4: if constexpr (NMAX >= 256) nnz[q] = sort_reduce_in_place<K, 8, SBK>(keys, vals, seq, lane); break;
-                    default: if constexpr (NMAX >= 512) nnz[q] = sort_reduce_in_place<K, 16, SBK>(keys, vals, seq, lane); break;
+                    case 1: nnz[q] = sort_count<K, 1, SBK>(keys, seq, lane); break;
+                    case 2: if constexpr (NMAX >= 64) nnz[q] = sort_count<K, 2, SBK>(keys, seq, lane); break;
+                    case 3: if constexpr (NMAX >= 128) nnz[q] = sort_count<K, 4, SBK>(keys, seq, lane); break;
+                    case 4: if constexpr (NMAX >= 256) nnz[q] = sort_count<K, 8, SBK>(keys, seq, lane); break;
+                    default: if constexpr (NMAX >= 512) nnz[q] = sort_count<K, 16, SBK>(keys, seq, lane); break;
                 }
             } else if (bn >= 6) {
                 nnz[q] = (int)pre_nnz[r];
@@ -187,14 +192,8 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
                 c_ptr[r] = base;
                 if (r == m - 1) c_ptr[m] = base + nnz[q];
             }
-            if (light[q]) {
-                const uint32_t* ocol = reinterpret_cast<const uint32_t*>(keys_w + q * NMAX);
-                const double* vals = vals_w + q * NMAX;
-                for (int j = lane; j < nnz[q]; j += 32) {
-                    c_col[base + j] = (int32_t)ocol[j];
-                    c_val[base + j] = vals[j];
-                }
-            }
+            if (prod[q] >= 0)
+                reduce_store<K, SBK>(keys_w + q * NMAX, vals_w + q * NMAX, prod[q], lane, base, c_col, c_val);
         }
         base += nnz[q];
     }
@@ -231,42 +230,74 @@ k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* _
         const int64_t r = (int64_t)tile * TINY_TILE + rt;
         int nnz = 0;
         if (r < m) {
-            const int bn = bin_of(flops[r]);
+            const uint32_t pf = flops[r];
+            const int bn = (pf >= 1u && pf <= 32u) ? 1 : (pf == 0u ? 0 : 2);
             if (bn == 1) {
                 const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
                 uint32_t* rc = s_col[rt];
                 double* rv = s_val[rt];
-                int p = 0;
-                for (int64_t pb = a_begin; pb < a_end; pb += 32) {
-                    int bt;
-                    expand_batch<true, false>(a, b, pb + lane, a_end, lane, p, bt,
-                                              [&](int sq, uint32_t c, double av, double bv) {
-                                                  rc[sq] = c;
-                                                  rv[sq] = __dmul_rn(av, bv);
-                                              });
-                    p += bt;
-                }
-                __syncwarp();
-                const bool have = lane < p;
                 K x[1];
-                x[0] = have ? (((K)rc[lane] << 5) | (K)lane) : KeyTraits<K>::sentinel;
-                const double prod = have ? rv[lane] : 0.0;
-                __syncwarp();
+                double prod = 0.0;
+                int p;
+                if (a_end - a_begin <= 32) {
+                    // the whole A row is one batch: one product per lane, nothing staged
+                    int64_t bs = 0;
+                    int len = 0;
+                    double av = 0.0;
+                    if (lane < (int)(a_end - a_begin)) {
+                        const int32_t k = ldg_i32(a.col + a_begin + lane);
+                        av = ldg_f64(a.val + a_begin + lane);
+                        bs = ldg_i64(b.ptr + k);
+                        len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+                    }
+                    const int off = warp_excl_scan(len, lane, p);
+                    int j = 0;
+#pragma unroll
+                    for (int st = 16; st > 0; st >>= 1) {
+                        const int o = __shfl_sync(FULL, off, j + st);
+                        if (o <= lane) j += st;
+                    }
+                    const int oj = __shfl_sync(FULL, off, j);
+                    const int64_t bsj = shfl_i64(bs, j);
+                    const double aj = shfl_f64(av, j);
+                    x[0] = KeyTraits<K>::sentinel;
+                    if (lane < p) {
+                        const int64_t qq = bsj + (lane - oj);
+                        x[0] = ((K)(uint32_t)ldg_i32(b.col + qq) << 5) | (K)lane;
+                        prod = __dmul_rn(aj, ldg_f64(b.val + qq));
+                    }
+                } else {
+                    // more than 32 A entries (most of them meeting empty B rows): stage through shared memory
+                    p = 0;
+                    for (int64_t pb = a_begin; pb < a_end; pb += 32) {
+                        int bt;
+                        expand_batch<true, false>(a, b, pb + lane, a_end, lane, p, bt,
+                                                  [&](int sq, uint32_t c, double av, double bv) {
+                                                      rc[sq] = c;
+                                                      rv[sq] = __dmul_rn(av, bv);
+                                                  });
+                        p += bt;
+                    }
+                    __syncwarp();
+                    x[0] = lane < p ? (((K)rc[lane] << 5) | (K)lane) : KeyTraits<K>::sentinel;
+                    prod = lane < p ? rv[lane] : 0.0;
+                    __syncwarp();
+                }
+                const bool have = lane < p;
                 warp_sort<K, 1>(x, lane, false);
                 const uint32_t col = (uint32_t)(x[0] >> 5);
                 const double v = shfl_f64(prod, (int)(x[0] & (K)31));
                 const uint32_t col_prev = __shfl_up_sync(FULL, col, 1);
                 const bool head = have && (lane == 0 || col_prev != col);
                 const unsigned hm = __ballot_sync(FULL, head);
-                const unsigned mem = __ballot_sync(FULL, have && !head);   // run members after their head
+                // run length of a head = distance to the next head (or to the end of the row)
+                const unsigned later = lane < 31 ? (hm >> (lane + 1)) : 0u;
+                const int run = head ? (later ? __ffs(later) : (p - lane)) : 0;
+                const int max_run = __reduce_max_sync(FULL, run);
                 double sum = v;
-                for (int d = 1; d < 32; ++d) {
-                    const unsigned need = (1u << d) - 1u;
-                    const unsigned after = lane < 31 ? (mem >> (lane + 1)) : 0u;
-                    const bool cont = head && (lane + d < 32) && ((after & need) == need);
-                    if (!__any_sync(FULL, cont)) break;
+                for (int d = 1; d < max_run; ++d) {
                     const double nv = shfl_f64(v, (lane + d) & 31);
-                    if (cont) sum = __dadd_rn(sum, nv);
+                    if (d < run) sum = __dadd_rn(sum, nv);
                 }
                 if (head) {
                     const int pos = __popc(hm & ((1u << lane) - 1u));
@@ -354,7 +385,7 @@ static void fused_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, in
                          const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val, uint64_t* tile_state,
                          cudaStream_t s) {
     constexpr int RPW = fused_rpw(NMAX);
-    constexpr int TILE_ROWS = FUSED_WARPS * RPW;
+    constexpr int TILE_ROWS = LIGHT_WARPS * RPW;
     size_t smem = (sizeof(K) + sizeof(double)) * NMAX * TILE_ROWS;
     static bool attr = false;
     if (!attr) {
@@ -363,11 +394,11 @@ static void fused_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, in
     }
     size_t tiles = (size_t)((m + TILE_ROWS - 1) / TILE_ROWS);
     cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
-    k_fused_light<K, NMAX, RPW><<<(unsigned)tiles, FUSED_WARPS * 32, smem, s>>>(
+    k_fused_light<K, NMAX, RPW><<<(unsigned)tiles, LIGHT_WARPS * 32, smem, s>>>(
         a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
 }
 
-size_t fused_tile_state_words(int64_t m) { return (size_t)((m + FUSED_WARPS - 1) / FUSED_WARPS) + 1; }
+size_t fused_tile_state_words(int64_t m) { return (size_t)((m + LIGHT_WARPS - 1) / LIGHT_WARPS) + 1; }
 
 template <typename K>
 static void fused_dispatch(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
@@ -393,7 +424,7 @@ void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t r
     if (max_bin == 1) {
         size_t tiles = (size_t)((m + TINY_TILE - 1) / TINY_TILE);
         cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
-        if ((uint64_t)b.cols <= (1ull << 27))
+        if ((uint64_t)b.cols < (1ull << 27))
             k_fused_tiny<uint32_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
                 a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
         else
@@ -402,7 +433,7 @@ void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t r
         return;
     }
     int sbk = 4 + max_bin;
-    bool narrow = (uint64_t)b.cols <= (1ull << (32 - sbk));
+    bool narrow = (uint64_t)b.cols < (1ull << (32 - sbk));  // strict: a valid key is never the all-ones sentinel
     if (narrow)
         fused_dispatch<uint32_t>(max_bin, a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s);
     else

@@ -55,6 +55,13 @@ __device__ __forceinline__ uint64_t shfl_xor_key(uint64_t v, int m) {
     return ((uint64_t)hi << 32) | lo;
 }
 
+__device__ __forceinline__ uint32_t shfl_up_key(uint32_t v) { return __shfl_up_sync(FULL, v, 1); }
+__device__ __forceinline__ uint64_t shfl_up_key(uint64_t v) {
+    uint32_t lo = __shfl_up_sync(FULL, (uint32_t)v, 1);
+    uint32_t hi = __shfl_up_sync(FULL, (uint32_t)(v >> 32), 1);
+    return ((uint64_t)hi << 32) | lo;
+}
+
 // One phase (all strides KK/2 .. 1) of the bitonic network over the 32*E keys a warp holds in
 // registers, element index e = lane*E + r.  `flip` inverts every comparison (descending).
 template <typename K, int E, int KK>

@@ -14,6 +14,7 @@ pub const SPADA_B200_MAX_BINS: usize = 16;
 pub const SPADA_B200_MAX_LAUNCHES: usize = 48;
 pub const SPADA_B200_FLAG_VALIDATE: u32 = 1;
 pub const SPADA_B200_FLAG_TWO_PHASE: u32 = 2;
+pub const SPADA_B200_FLAG_SINGLE_PASS: u32 = 4;
 
 /// `Vec<usize>` / `Vec<usize>` / `Vec<f64>` exactly as `CsrMatStorage` holds them (storage.rs:150-160).
 #[repr(C)]

@@ -44,7 +44,7 @@ def engine(spada, request):
     """Both engine modes: single-pass (fused light rows + look-back) and separate symbolic/numeric passes."""
     if spada.device_count() == 0:
         pytest.skip("no CUDA device")
-    e = spada.Engine(two_phase=(request.param == "two_phase"))
+    e = spada.Engine(two_phase=(request.param == "two_phase"), single_pass=(request.param == "fused"))
     yield e
     e.close()
 
