@@ -104,7 +104,7 @@ constexpr int EXPAND_UNROLL = 4;  // independent B gathers in flight per lane
 // emit(seq, col, a_val, b_val): the B column id (and value when NUMERIC) are already loaded.  The loads
 // of EXPAND_UNROLL consecutive steps are issued back to back before any of them is consumed, so a
 // warp keeps several HBM/L2 round trips in flight instead of one.
-template <bool NUMERIC, bool BIG, typename F>
+template <bool NUMERIC, bool BIG, bool LOAD_COL = true, typename F>
 __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, int64_t p, int64_t a_end,
                                              int lane, int seq_base, int& batch_total, F&& emit) {
     int64_t bs = 0;
@@ -142,7 +142,7 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
         if (NUMERIC) aj = shfl_f64(av, j);
         if (lane < total) {
             int64_t q = bsj + (lane - oj);
-            emit(seq_base + lane, (uint32_t)ldg_i32(b.col + q), aj, NUMERIC ? ldg_f64(b.val + q) : 0.0);
+            emit(seq_base + lane, LOAD_COL ? (uint32_t)ldg_i32(b.col + q) : 0u, aj, NUMERIC ? ldg_f64(b.val + q) : 0.0);
         }
     } else
     for (int base = 0; base < total; base += 32 * EXPAND_UNROLL) {
@@ -173,7 +173,7 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
             c[u] = 0;
             bv[u] = 0.0;
             if (base + u * 32 + lane < total) {
-                c[u] = (uint32_t)ldg_i32(b.col + q[u]);
+                if (LOAD_COL) c[u] = (uint32_t)ldg_i32(b.col + q[u]);
                 if (NUMERIC) bv[u] = ldg_f64(b.val + q[u]);
             }
         }
@@ -192,7 +192,7 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
             double aj = 0.0;
             if (NUMERIC) aj = shfl_f64(av, j);
             for (int t = lane; t < lj; t += 32)
-                emit(-1, (uint32_t)ldg_i32(b.col + bsj + t), aj, NUMERIC ? ldg_f64(b.val + bsj + t) : 0.0);
+                emit(-1, LOAD_COL ? (uint32_t)ldg_i32(b.col + bsj + t) : 0u, aj, NUMERIC ? ldg_f64(b.val + bsj + t) : 0.0);
         }
     }
 }
@@ -221,6 +221,21 @@ void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_
                          uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
 void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                         uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+// two-phase mode with kept keys: symbolic stores each row's sorted (column, arrival) keys at
+// kstore + prod_ptr[row]; numeric reloads them instead of sorting again (bins 1..8)
+void launch_esc_symbolic_keep(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                              const uint32_t* perm, uint32_t rows, uint32_t* row_nnz, const int64_t* prod_ptr,
+                              void* kstore, cudaStream_t s);
+void launch_esc_numeric_presorted(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                                  const uint32_t* perm, uint32_t rows, const int64_t* c_ptr, int32_t* c_col,
+                                  double* c_val, const int64_t* prod_ptr, const void* kstore, cudaStream_t s);
+void launch_cta_symbolic_keep(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                              const uint32_t* perm, uint32_t rows, uint32_t* row_nnz, const int64_t* prod_ptr,
+                              void* kstore, cudaStream_t s);
+void launch_cta_numeric_presorted(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                                  const uint32_t* perm, uint32_t rows, const int64_t* c_ptr, int32_t* c_col,
+                                  double* c_val, const int64_t* prod_ptr, const void* kstore, cudaStream_t s);
+bool esc_needs_wide_keys(int bin, int64_t b_cols);
 // stage 2 / 3, heavy bin (9): rows are cut into items (~8192 products) spread over the grid
 struct HeavyPlan {
     uint32_t words;      // bitmap words per row = ceil(B.cols / 32)

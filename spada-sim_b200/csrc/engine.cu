@@ -66,6 +66,7 @@ struct spada_b200 {
     std::unordered_map<void*, size_t> pool_live;
     size_t pool_bytes = 0;
     size_t dev_total_mem = 0;
+    bool keep_keys = true;    // two-phase mode: numeric reloads the keys symbolic sorted (SPADA_B200_KEEP_KEYS=0 off)
     bool cta_bitonic = true;  // sort of the CTA-per-row bins 1024..4096: bitonic (default) or radix
     size_t heavy_ws_budget = (size_t)2 << 30;  // bitmap workspace for the heavy bin (SPADA_B200_HEAVY_WS_MB)
 };
@@ -301,6 +302,7 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
     CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_scalar, 64));
     setup_kernel_attributes();
+    if (const char* e = getenv("SPADA_B200_KEEP_KEYS")) h->keep_keys = atoi(e) != 0;
     if (const char* e = getenv("SPADA_B200_CTA_SORT")) h->cta_bitonic = strcmp(e, "radix") != 0;
     if (const char* e = getenv("SPADA_B200_HEAVY_WS_MB")) {
         long mb = atol(e);
@@ -592,7 +594,8 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     uint64_t* d_tiles = nullptr;
     uint2* d_heavy_ws = nullptr;
     uint32_t *d_items_per_row = nullptr, *d_item_row = nullptr;
-    int64_t* d_item_off = nullptr;
+    int64_t *d_item_off = nullptr, *d_prod_ptr = nullptr;
+    void* d_kstore = nullptr;
     uint32_t kernels = 0;
     auto cleanup = [&]() {
         dfree(h, d_flops);
@@ -604,6 +607,8 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         dfree(h, d_items_per_row);
         dfree(h, d_item_row);
         dfree(h, d_item_off);
+        dfree(h, d_prod_ptr);
+        dfree(h, (char*)d_kstore);
     };
 #define TRY(x)                    \
     do {                          \
@@ -696,6 +701,30 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     if (fused && !(h->opts.flags & SPADA_B200_FLAG_SINGLE_PASS) && dominant * 10 < non_empty * 8) fused = false;
     const int first_sym_bin = fused ? 6 : 1;
 
+    // Two-phase mode: the symbolic kernels of the sort bins (1..8) leave each row's sorted keys in HBM
+    // at kstore + prod_ptr[row]; the numeric kernels reload them instead of sorting the row again.
+    bool keep_keys = false, wide_keys = false;
+    if (!fused && h->keep_keys) {
+        uint64_t sorted_rows = 0;
+        for (int bnum = 1; bnum <= 8; ++bnum) {
+            sorted_rows += pc.bin_rows[bnum];
+            if (pc.bin_rows[bnum] && esc_needs_wide_keys(bnum, B.cols)) wide_keys = true;
+        }
+        const double kbytes = (double)pc.total_products * (wide_keys ? 8.0 : 4.0);
+        keep_keys = sorted_rows > 0 && kbytes <= 0.15 * (double)h->dev_total_mem;
+    }
+    if (keep_keys) {
+        TRY(dalloc(h, &d_prod_ptr, (size_t)m + 1));
+        char* ks = nullptr;
+        TRY(dalloc(h, &ks, (size_t)pc.total_products * (wide_keys ? 8 : 4)));
+        d_kstore = ks;
+        begin_rec("product_scan", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
+        launch_scan_u32_i64(d_flops, m, d_prod_ptr, d_tiles, h->d_ctr, s);
+        CUT(cudaGetLastError());
+        kernels += 1;
+        end_rec();
+    }
+
     // heavy rows: cut into items, bitmaps for one wave of rows at a time
     HeavyPlan HP{};
     const uint32_t n_heavy = pc.bin_rows[BIN_HEAVY];
@@ -737,7 +766,13 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             }
         } else {
             begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
-            if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
+            if (keep_keys && bnum <= 5)
+                launch_esc_symbolic_keep(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz,
+                                         d_prod_ptr, d_kstore, s);
+            else if (keep_keys && bnum <= 8)
+                launch_cta_symbolic_keep(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz,
+                                         d_prod_ptr, d_kstore, s);
+            else if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
                 launch_bitonic_cta_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
             else
                 launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
@@ -808,7 +843,13 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             }
         } else {
             begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
-            if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
+            if (keep_keys && bnum <= 5)
+                launch_esc_numeric_presorted(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr,
+                                             R->col, R->val, d_prod_ptr, d_kstore, s);
+            else if (keep_keys && bnum <= 8)
+                launch_cta_numeric_presorted(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr,
+                                             R->col, R->val, d_prod_ptr, d_kstore, s);
+            else if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
                 launch_bitonic_cta_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col,
                                            R->val, s);
             else

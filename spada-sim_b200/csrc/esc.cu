@@ -120,6 +120,105 @@ k_esc_numeric_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __rest
     }
 }
 
+// ---- kept-keys variants (two-phase mode) ----------------------------------------------------------
+// Symbolic sorts the same (column << log2 N | arrival) keys numeric needs, counts the distinct
+// columns and leaves the sorted keys in HBM (4 or 8 B per product); numeric then only expands the
+// products' values, reloads the keys with coalesced loads and reduces -- the row is sorted once.
+template <typename K, int N>
+__global__ void __launch_bounds__(ESC_WARPS * 32)
+k_esc_symbolic_keep_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
+                         uint32_t* __restrict__ row_nnz, const int64_t* __restrict__ prod_ptr, K* __restrict__ kstore) {
+    constexpr int E = N / 32;
+    constexpr int SB = Log2<N>::v;
+    __shared__ __align__(16) K s_keys[ESC_WARPS][N];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * ESC_WARPS + warp;
+    if (w >= rows) return;
+    const uint32_t r = perm ? perm[w] : w;
+    K* keys = s_keys[warp];
+    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+    int seq = 0;
+    for (int64_t pb = a_begin; pb < a_end; pb += 32) {
+        int bt;
+        expand_batch<false, false>(a, b, pb + lane, a_end, lane, seq, bt,
+                                   [&](int sq, uint32_t c, double, double) { keys[sq] = ((K)c << SB) | (K)sq; });
+        seq += bt;
+    }
+    const int p = seq;
+    for (int t = p + lane; t < N; t += 32) keys[t] = KeyTraits<K>::sentinel;
+    __syncwarp();
+    K x[E];
+    load_blocked<K, E>(x, keys, lane);
+    warp_sort<K, E>(x, lane, false);
+    __syncwarp();
+    store_blocked<K, E>(x, keys, lane);
+    const K prev = shfl_up_key(x[E - 1]);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const bool first = (lane == 0 && i == 0);
+        const K pv = (i == 0) ? prev : x[i - 1];
+        if (lane * E + i < p && (first || (uint32_t)(x[i] >> SB) != (uint32_t)(pv >> SB))) ++cnt;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+    if (lane == 0) row_nnz[r] = (uint32_t)cnt;
+    __syncwarp();
+    K* dst = kstore + prod_ptr[r];
+    for (int t = lane; t < p; t += 32) dst[t] = keys[t];
+}
+
+template <typename K, int N>
+__global__ void __launch_bounds__(ESC_WARPS * 32)
+k_esc_numeric_presorted_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
+                             const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val,
+                             const int64_t* __restrict__ prod_ptr, const K* __restrict__ kstore) {
+    constexpr int SB = Log2<N>::v;
+    __shared__ __align__(16) double s_vals[ESC_WARPS][N];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * ESC_WARPS + warp;
+    if (w >= rows) return;
+    const uint32_t r = perm ? perm[w] : w;
+    double* vals = s_vals[warp];
+    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+    int seq = 0;
+    for (int64_t pb = a_begin; pb < a_end; pb += 32) {
+        int bt;
+        expand_batch<true, false, false>(a, b, pb + lane, a_end, lane, seq, bt,
+                                         [&](int sq, uint32_t, double av, double bv) { vals[sq] = __dmul_rn(av, bv); });
+        seq += bt;
+    }
+    const int p = seq;
+    __syncwarp();
+    const K* keys = kstore + prod_ptr[r];
+    const int64_t cbase = c_ptr[r];
+    int out_base = 0;
+    uint32_t prev_last = 0;
+    for (int base = 0; base < p; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < p;
+        const K ki = valid ? keys[i] : KeyTraits<K>::sentinel;
+        const uint32_t col = (uint32_t)(ki >> SB);
+        uint32_t col_prev = __shfl_up_sync(FULL, col, 1);
+        if (lane == 0) col_prev = prev_last;
+        const bool head = valid && (i == 0 || col_prev != col);
+        const unsigned hm = __ballot_sync(FULL, head);
+        prev_last = __shfl_sync(FULL, col, 31);
+        if (head) {
+            double sum = vals[(int)(ki & (K)(N - 1))];
+            for (int j = i + 1; j < p; ++j) {
+                const K kj = keys[j];
+                if ((uint32_t)(kj >> SB) != col) break;
+                sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
+            }
+            const int o = out_base + __popc(hm & ((1u << lane) - 1u));
+            c_col[cbase + o] = (int32_t)col;
+            c_val[cbase + o] = sum;
+        }
+        out_base += __popc(hm);
+    }
+}
+
 // =============================================================================================
 // CTA-per-row kernels, N = 1024 / 2048 / 4096 / 8192 products at most.
 //
@@ -431,6 +530,54 @@ void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_b
         case 9: num_cta_launch<8192, 512>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;
         default: break;
     }
+}
+
+bool esc_needs_wide_keys(int bin, int64_t b_cols) {
+    int sb = 4 + bin;  // log2 of the bin capacity
+    return !((uint64_t)b_cols <= (1ull << (32 - sb)));
+}
+
+template <typename K>
+static void sym_keep_dispatch(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                              uint32_t rows, uint32_t* row_nnz, const int64_t* prod_ptr, void* kstore, cudaStream_t s) {
+    unsigned g = (unsigned)esc_grid(bin, rows);
+    K* ks = reinterpret_cast<K*>(kstore);
+    switch (bin) {
+        case 1: k_esc_symbolic_keep_warp<K, 32><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, ks); break;
+        case 2: k_esc_symbolic_keep_warp<K, 64><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, ks); break;
+        case 3: k_esc_symbolic_keep_warp<K, 128><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, ks); break;
+        case 4: k_esc_symbolic_keep_warp<K, 256><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, ks); break;
+        default: k_esc_symbolic_keep_warp<K, 512><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, ks); break;
+    }
+}
+template <typename K>
+static void num_presorted_dispatch(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
+                                   uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val,
+                                   const int64_t* prod_ptr, const void* kstore, cudaStream_t s) {
+    unsigned g = (unsigned)esc_grid(bin, rows);
+    const K* ks = reinterpret_cast<const K*>(kstore);
+    switch (bin) {
+        case 1: k_esc_numeric_presorted_warp<K, 32><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, ks); break;
+        case 2: k_esc_numeric_presorted_warp<K, 64><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, ks); break;
+        case 3: k_esc_numeric_presorted_warp<K, 128><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, ks); break;
+        case 4: k_esc_numeric_presorted_warp<K, 256><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, ks); break;
+        default: k_esc_numeric_presorted_warp<K, 512><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, ks); break;
+    }
+}
+
+void launch_esc_symbolic_keep(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                              const uint32_t* perm, uint32_t rows, uint32_t* row_nnz, const int64_t* prod_ptr,
+                              void* kstore, cudaStream_t s) {
+    if (rows == 0) return;
+    if (wide) sym_keep_dispatch<uint64_t>(bin, a, b, row_begin, perm, rows, row_nnz, prod_ptr, kstore, s);
+    else sym_keep_dispatch<uint32_t>(bin, a, b, row_begin, perm, rows, row_nnz, prod_ptr, kstore, s);
+}
+void launch_esc_numeric_presorted(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                                  const uint32_t* perm, uint32_t rows, const int64_t* c_ptr, int32_t* c_col,
+                                  double* c_val, const int64_t* prod_ptr, const void* kstore, cudaStream_t s) {
+    if (rows == 0) return;
+    if (wide) num_presorted_dispatch<uint64_t>(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, kstore, s);
+    else num_presorted_dispatch<uint32_t>(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, kstore, s);
 }
 
 }  // namespace spada

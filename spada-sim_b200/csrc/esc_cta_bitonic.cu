@@ -23,7 +23,8 @@ struct CtaStage {
     int wtot[ESC_CTA_THREADS / 32];
 };
 
-template <typename K, int N, bool NUMERIC>
+// PACKED: keys carry the arrival index (column << log2 N | seq); LOAD_COL = false: values only
+template <typename K, int N, bool NUMERIC, bool PACKED = NUMERIC, bool LOAD_COL = true>
 __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr& b, int64_t a_begin, int64_t a_end,
                                                   K* keys, double* vals, CtaStage& st) {
     constexpr int SB = Log2<N>::v;
@@ -81,7 +82,7 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
                 c[u] = 0;
                 bv[u] = 0.0;
                 if (t[u] < all) {
-                    c[u] = (uint32_t)ldg_i32(b.col + q[u]);
+                    if (LOAD_COL) c[u] = (uint32_t)ldg_i32(b.col + q[u]);
                     if (NUMERIC) bv[u] = ldg_f64(b.val + q[u]);
                 }
             }
@@ -89,12 +90,8 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
             for (int u = 0; u < 2; ++u) {
                 if (t[u] < all) {
                     int sq = seq_base + t[u];
-                    if (NUMERIC) {
-                        keys[sq] = ((K)c[u] << SB) | (K)sq;
-                        vals[sq] = __dmul_rn(st.av[j[u]], bv[u]);
-                    } else {
-                        keys[sq] = (K)c[u];
-                    }
+                    if (LOAD_COL) keys[sq] = PACKED ? (((K)c[u] << SB) | (K)sq) : (K)c[u];
+                    if (NUMERIC) vals[sq] = __dmul_rn(st.av[j[u]], bv[u]);
                 }
             }
         }
@@ -223,6 +220,153 @@ k_bitonic_numeric_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __r
             ++o;
         }
     }
+}
+
+// ---- kept-keys variants: symbolic leaves the sorted packed keys in HBM, numeric reloads them ----------
+template <typename K, int N>
+__global__ void __launch_bounds__(ESC_CTA_THREADS)
+k_bitonic_symbolic_keep_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
+                            uint32_t* __restrict__ row_nnz, const int64_t* __restrict__ prod_ptr, K* __restrict__ kstore) {
+    constexpr int SB = Log2<N>::v;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    K* keys = reinterpret_cast<K*>(s_raw);
+    __shared__ CtaStage st;
+    const uint32_t r = perm ? perm[blockIdx.x] : blockIdx.x;
+    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+    const int p = bitonic_cta_expand<K, N, false, true>(a, b, a_begin, a_end, keys, nullptr, st);
+    for (int t = p + threadIdx.x; t < N; t += ESC_CTA_THREADS) keys[t] = KeyTraits<K>::sentinel;
+    __syncthreads();
+    bitonic_cta_sort<K, N>(keys);
+    int cnt = 0;
+    K* dst = kstore + prod_ptr[r];
+    for (int i = threadIdx.x; i < p; i += ESC_CTA_THREADS) {
+        const K ki = keys[i];
+        dst[i] = ki;
+        if (i == 0 || (uint32_t)(keys[i - 1] >> SB) != (uint32_t)(ki >> SB)) ++cnt;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+    __syncthreads();
+    if (lane_id() == 0) st.wtot[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < ESC_CTA_THREADS / 32; ++w) t += st.wtot[w];
+        row_nnz[r] = (uint32_t)t;
+    }
+}
+
+template <typename K, int N>
+__global__ void __launch_bounds__(ESC_CTA_THREADS)
+k_bitonic_numeric_presorted_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
+                                const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
+                                double* __restrict__ c_val, const int64_t* __restrict__ prod_ptr,
+                                const K* __restrict__ kstore) {
+    constexpr int SB = Log2<N>::v;
+    constexpr int ITEMS = N / ESC_CTA_THREADS;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    double* vals = reinterpret_cast<double*>(s_raw);
+    K* keys = reinterpret_cast<K*>(s_raw + sizeof(double) * N);
+    __shared__ CtaStage st;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t r = perm ? perm[blockIdx.x] : blockIdx.x;
+    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+    const int p = bitonic_cta_expand<K, N, true, true, false>(a, b, a_begin, a_end, keys, vals, st);
+    const K* src = kstore + prod_ptr[r];
+    for (int t = threadIdx.x; t < p; t += ESC_CTA_THREADS) keys[t] = src[t];
+    __syncthreads();
+    const int i0 = threadIdx.x * ITEMS;
+    uint32_t col[ITEMS];
+    bool head[ITEMS];
+    int cnt = 0;
+    uint32_t prev = (i0 > 0 && i0 <= p) ? (uint32_t)(keys[i0 - 1] >> SB) : 0xffffffffu;
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        const int i = i0 + e;
+        col[e] = (i < p) ? (uint32_t)(keys[i] >> SB) : 0xffffffffu;
+        head[e] = (i < p) && (i == 0 || col[e] != prev);
+        prev = col[e];
+        cnt += head[e] ? 1 : 0;
+    }
+    int wtotal;
+    int woff = warp_excl_scan(cnt, lane, wtotal);
+    __syncthreads();
+    if (lane == 0) st.wtot[warp] = wtotal;
+    __syncthreads();
+    int o = woff;
+#pragma unroll
+    for (int w = 0; w < ESC_CTA_THREADS / 32; ++w)
+        if (w < warp) o += st.wtot[w];
+    const int64_t cbase = c_ptr[r];
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        if (head[e]) {
+            const int i = i0 + e;
+            double sum = vals[(int)(keys[i] & (K)(N - 1))];
+            for (int j = i + 1; j < p; ++j) {
+                K kj = keys[j];
+                if ((uint32_t)(kj >> SB) != col[e]) break;
+                sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
+            }
+            c_col[cbase + o] = (int32_t)col[e];
+            c_val[cbase + o] = sum;
+            ++o;
+        }
+    }
+}
+
+template <typename K, int N>
+static void keep_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm, uint32_t rows,
+                        uint32_t* row_nnz, const int64_t* prod_ptr, void* kstore, cudaStream_t s) {
+    size_t smem = sizeof(K) * N;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_bitonic_symbolic_keep_cta<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    k_bitonic_symbolic_keep_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(a, b, row_begin, perm, rows, row_nnz, prod_ptr,
+                                                                      reinterpret_cast<K*>(kstore));
+}
+template <typename K, int N>
+static void presorted_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm, uint32_t rows,
+                             const int64_t* c_ptr, int32_t* c_col, double* c_val, const int64_t* prod_ptr,
+                             const void* kstore, cudaStream_t s) {
+    size_t smem = (sizeof(K) + sizeof(double)) * N;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_bitonic_numeric_presorted_cta<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        attr = true;
+    }
+    k_bitonic_numeric_presorted_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(
+        a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, reinterpret_cast<const K*>(kstore));
+}
+
+void launch_cta_symbolic_keep(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                              const uint32_t* perm, uint32_t rows, uint32_t* row_nnz, const int64_t* prod_ptr,
+                              void* kstore, cudaStream_t s) {
+    if (rows == 0) return;
+#define KEEP_CASE(K)                                                                                       \
+    switch (bin) {                                                                                          \
+        case 6: keep_launch<K, 1024>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, kstore, s); break;     \
+        case 7: keep_launch<K, 2048>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, kstore, s); break;     \
+        default: keep_launch<K, 4096>(a, b, row_begin, perm, rows, row_nnz, prod_ptr, kstore, s); break;    \
+    }
+    if (wide) { KEEP_CASE(uint64_t) } else { KEEP_CASE(uint32_t) }
+#undef KEEP_CASE
+}
+void launch_cta_numeric_presorted(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
+                                  const uint32_t* perm, uint32_t rows, const int64_t* c_ptr, int32_t* c_col,
+                                  double* c_val, const int64_t* prod_ptr, const void* kstore, cudaStream_t s) {
+    if (rows == 0) return;
+#define PRE_CASE(K)                                                                                                   \
+    switch (bin) {                                                                                                     \
+        case 6: presorted_launch<K, 1024>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, kstore, s); break;  \
+        case 7: presorted_launch<K, 2048>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, kstore, s); break;  \
+        default: presorted_launch<K, 4096>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, kstore, s); break; \
+    }
+    if (wide) { PRE_CASE(uint64_t) } else { PRE_CASE(uint32_t) }
+#undef PRE_CASE
 }
 
 template <typename K, int N>
