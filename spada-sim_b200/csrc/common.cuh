@@ -15,12 +15,12 @@ constexpr unsigned FULL = 0xffffffffu;
 //   bin 0          p == 0                 nothing to do, nnz = 0
 //   bin 1          p <= 32                one warp per row, products sorted in registers
 //   bin 2..5       p <= 64,128,256,512    one warp per row, E = N/32 keys per lane
-//   bin 6..9       p <= 1024 .. 8192      one CTA per row, shared-memory radix sort
-//   bin 10         p  > 8192              items of ~8192 products over the grid, bitmap + rank
-constexpr int NUM_BINS = 11;
+//   bin 6..8       p <= 1024,2048,4096    one CTA per row, register chunk sorts merged in shared memory
+//   bin 9          p  > 4096              items of ~8192 products over the grid, bitmap + rank
+constexpr int NUM_BINS = 10;
 constexpr int BIN_EMPTY = 0;
-constexpr int BIN_HEAVY = 10;
-constexpr uint32_t ESC_MAX_PRODUCTS = 8192;
+constexpr int BIN_HEAVY = 9;
+constexpr uint32_t ESC_MAX_PRODUCTS = 4096;
 
 __host__ __device__ inline int bin_of(uint32_t p) {
     if (p == 0) return 0;
@@ -32,8 +32,7 @@ __host__ __device__ inline int bin_of(uint32_t p) {
     if (p <= 1024) return 6;
     if (p <= 2048) return 7;
     if (p <= 4096) return 8;
-    if (p <= 8192) return 9;
-    return 10;
+    return 9;
 }
 __host__ __device__ inline uint32_t bin_capacity(int b) { return b == 0 ? 0u : (b >= BIN_HEAVY ? 0u : (32u << (b - 1))); }
 

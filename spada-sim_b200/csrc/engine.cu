@@ -67,7 +67,6 @@ struct spada_b200 {
     size_t pool_bytes = 0;
     size_t dev_total_mem = 0;
     bool keep_keys = true;    // two-phase mode: numeric reloads the keys symbolic sorted (SPADA_B200_KEEP_KEYS=0 off)
-    bool cta_bitonic = true;  // sort of the CTA-per-row bins 1024..4096: bitonic (default) or radix
     size_t heavy_ws_budget = (size_t)2 << 30;  // bitmap workspace for the heavy bin (SPADA_B200_HEAVY_WS_MB)
 };
 
@@ -177,7 +176,7 @@ struct LaunchRec {
 };
 
 const char* bin_name(int b) {
-    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "8192", "heavy"};
+    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy"};
     return names[b];
 }
 
@@ -303,7 +302,6 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
     CU(cudaMallocHost((void**)&h->h_scalar, 64));
     setup_kernel_attributes();
     if (const char* e = getenv("SPADA_B200_KEEP_KEYS")) h->keep_keys = atoi(e) != 0;
-    if (const char* e = getenv("SPADA_B200_CTA_SORT")) h->cta_bitonic = strcmp(e, "radix") != 0;
     if (const char* e = getenv("SPADA_B200_HEAVY_WS_MB")) {
         long mb = atol(e);
         if (mb > 0) h->heavy_ws_budget = (size_t)mb << 20;
@@ -662,7 +660,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         st.bin_rows[bnum] = pc.bin_rows[bnum];
         st.bin_products[bnum] = pc.bin_products[bnum];
         st.bin_window_rows[bnum] = (bnum >= 1 && bnum <= 5) ? 4u : (bnum == 0 ? 0u : 1u);
-        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : (bnum == BIN_HEAVY ? 256u : (bnum == 9 ? 512u : 256u)));
+        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : 256u);
     }
     tbl.offset[NUM_BINS] = off;
     // a single non-empty bin holding every row needs no permutation
@@ -750,19 +748,20 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
         if (bnum == BIN_HEAVY) {
             const uint32_t* hl = perm_of_bin[bnum];
+            const bool detail = HP.n_waves == 1;  // per-kernel records for a single wave, one record otherwise
+            if (!detail) begin_rec(name, 2, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum]);
             for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
                 uint32_t hi = std::min(rows, lo + HP.wave_rows);
-                begin_rec("sym_heavy_clear", 2, 0, hi - lo, 0);
+                if (detail) begin_rec("sym_heavy_clear", 2, 0, hi - lo, 0);
                 CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), s));
-                end_rec();
-                begin_rec("sym_heavy_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                if (detail) end_rec();
+                if (detail) begin_rec("sym_heavy_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
                                   h->sm_count, s);
-                end_rec();
-                begin_rec("sym_heavy_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum]);
+                if (detail) end_rec();
+                if (detail) begin_rec("sym_heavy_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, s);
                 kernels += 2;
-                if (hi < rows) end_rec();
             }
         } else {
             begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
@@ -772,8 +771,6 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             else if (keep_keys && bnum <= 8)
                 launch_cta_symbolic_keep(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz,
                                          d_prod_ptr, d_kstore, s);
-            else if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
-                launch_bitonic_cta_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
             else
                 launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
             kernels += 1;
@@ -821,25 +818,23 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         if (bnum == BIN_HEAVY) {
             const uint32_t* hl = perm_of_bin[bnum];
             const bool ws_valid = HP.n_waves == 1;  // bitmaps + ranks of the symbolic stage are still resident
+            if (!ws_valid) begin_rec(name, 3, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum]);
             for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
                 uint32_t hi = std::min(rows, lo + HP.wave_rows);
                 if (!ws_valid) {
-                    begin_rec("num_heavy_bits", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
                     CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), s));
                     launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws,
                                       HP, h->sm_count, s);
                     launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, nullptr, s);
                     kernels += 2;
-                    end_rec();
                 }
-                begin_rec("num_heavy_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum]);
+                if (ws_valid) begin_rec("num_heavy_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, R->ptr, R->col, R->val, s);
-                end_rec();
-                begin_rec("num_heavy_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                if (ws_valid) end_rec();
+                if (ws_valid) begin_rec("num_heavy_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_accum(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
                                    R->ptr, R->val, h->sm_count, s);
                 kernels += 2;
-                if (hi < rows) end_rec();
             }
         } else {
             begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
@@ -849,9 +844,6 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             else if (keep_keys && bnum <= 8)
                 launch_cta_numeric_presorted(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr,
                                              R->col, R->val, d_prod_ptr, d_kstore, s);
-            else if (h->cta_bitonic && bnum >= 6 && bnum <= 8)
-                launch_bitonic_cta_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col,
-                                           R->val, s);
             else
                 launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
             kernels += 1;

@@ -13,8 +13,8 @@
 // 1e-12.  Products use __dmul_rn / __dadd_rn: never contracted into an FMA.
 //
 // Window shape (scheduler.rs:729-753): bins 1..5 give each A row one warp (32 lanes x E keys
-// per lane, E = N/32, bitonic network in registers), four rows share a CTA; bins 6..9 give each
-// A row a whole CTA (stable radix sort in shared memory).
+// per lane, E = N/32, bitonic network in registers), four rows share a CTA; bins 6..8 give each
+// A row a whole CTA (esc_cta_bitonic.cu).
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -219,265 +219,14 @@ k_esc_numeric_presorted_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32
     }
 }
 
-// =============================================================================================
-// CTA-per-row kernels, N = 1024 / 2048 / 4096 / 8192 products at most.
-//
-// Sorting here is a stable least-significant-digit radix sort over the column bits only (4 bits
-// per pass): because it is stable, products that land on the same column stay in arrival order,
-// so the key needs no arrival index and the summation order is still the oracle's ascending-k
-// order.  Work is linear in N (a bitonic network costs N log^2 N: at N = 4096 about 4x more).
-//
-// One pass (CUB-style ranking without atomics or votes): thread t owns ITEMS consecutive keys;
-// it counts its keys per digit in a private column of 16-bit counters cnt[digit][t], the block
-// scans the counters in (digit-major, thread-minor) order, and key i goes to
-// scanned[digit][t] + (its rank among the thread's own keys with that digit).
-// =============================================================================================
-constexpr int RADIX_BITS = 4;
-constexpr int RADIX_DIGITS = 1 << RADIX_BITS;
-
-template <int THREADS>
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp /* THREADS/32 */, uint32_t& total) {
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(FULL, x, d);
-        if (lane >= d) x += y;
-    }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    uint32_t base = 0, all = 0;
-#pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) {
-        uint32_t t = s_warp[w];
-        if (w < warp) base += t;
-        all += t;
-    }
-    total = all;
-    __syncthreads();
-    return base + x - v;
-}
-
-// keys[0..N) (and pay[0..N) if PAYLOAD) in shared memory are sorted by the low `bits` bits of the key.
-template <int THREADS, int ITEMS, bool PAYLOAD>
-__device__ __forceinline__ void block_radix_sort(uint32_t* keys, uint32_t* pay, uint16_t* cnt, uint32_t* s_warp,
-                                                 int bits) {
-    const int t = threadIdx.x;
-    uint32_t k[ITEMS], v[ITEMS];
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        k[i] = keys[t * ITEMS + i];
-        v[i] = (uint32_t)(t * ITEMS + i);  // payload = arrival index of the product
-    }
-    __syncthreads();
-    for (int shift = 0; shift < bits; shift += RADIX_BITS) {
-        uint32_t* cnt32 = reinterpret_cast<uint32_t*>(cnt);
-#pragma unroll
-        for (int i = 0; i < RADIX_DIGITS / 2; ++i) cnt32[i * THREADS + t] = 0u;
-        __syncthreads();
-        uint16_t r[ITEMS];
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            uint32_t d = (k[i] >> shift) & (RADIX_DIGITS - 1);
-            uint16_t c = cnt[d * THREADS + t];
-            r[i] = c;
-            cnt[d * THREADS + t] = (uint16_t)(c + 1);
-        }
-        __syncthreads();
-        // thread t scans counters [t*DIGITS, (t+1)*DIGITS) of the linear (digit-major) order
-        uint16_t c[RADIX_DIGITS];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int j = 0; j < RADIX_DIGITS; ++j) {
-            c[j] = cnt[t * RADIX_DIGITS + j];
-            sum += c[j];
-        }
-        uint32_t total;
-        uint32_t run = block_excl_scan<THREADS>(sum, s_warp, total);
-#pragma unroll
-        for (int j = 0; j < RADIX_DIGITS; ++j) {
-            cnt[t * RADIX_DIGITS + j] = (uint16_t)run;
-            run += c[j];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            uint32_t d = (k[i] >> shift) & (RADIX_DIGITS - 1);
-            uint32_t pos = (uint32_t)cnt[d * THREADS + t] + r[i];
-            keys[pos] = k[i];
-            if (PAYLOAD) pay[pos] = v[i];
-        }
-        __syncthreads();
-        if (shift + RADIX_BITS < bits) {
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                k[i] = keys[t * ITEMS + i];
-                if (PAYLOAD) v[i] = pay[t * ITEMS + i];
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// expansion of one A row by a whole CTA: keys[seq] = column, vals[seq] = product (numeric only)
-template <int THREADS, bool NUMERIC>
-__device__ __forceinline__ int cta_expand(const DevCsr& a, const DevCsr& b, int64_t a_begin, int64_t a_end,
-                                          uint32_t* keys, double* vals, int* s_wtot) {
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    int seq_base = 0;
-    for (int64_t pb = a_begin; pb < a_end; pb += THREADS) {
-        // pre-pass: per-warp product totals of this batch so every warp knows its arrival offset
-        int64_t p = pb + threadIdx.x;
-        int len = 0;
-        if (p < a_end) {
-            int32_t k = ldg_i32(a.col + p);
-            len = (int)(ldg_i64(b.ptr + k + 1) - ldg_i64(b.ptr + k));
-        }
-        int wt = len;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) wt += __shfl_xor_sync(FULL, wt, d);
-        if (lane == 0) s_wtot[warp] = wt;
-        __syncthreads();
-        int my_base = seq_base, all = 0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) {
-            int t = s_wtot[w];
-            if (w < warp) my_base += t;
-            all += t;
-        }
-        int bt;
-        expand_batch<NUMERIC, false>(a, b, p, a_end, lane, my_base, bt, [&](int sq, uint32_t c, double av, double bv) {
-            keys[sq] = c;
-            if (NUMERIC) vals[sq] = __dmul_rn(av, bv);
-        });
-        seq_base += all;
-        __syncthreads();
-    }
-    return seq_base;
-}
-
-template <int N, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_esc_symbolic_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
-                   uint32_t* __restrict__ row_nnz, int col_bits) {
-    constexpr int ITEMS = N / THREADS;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    uint32_t* keys = reinterpret_cast<uint32_t*>(s_raw);
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(s_raw + sizeof(uint32_t) * N);
-    __shared__ int s_wtot[THREADS / 32];
-    const uint32_t r = perm ? perm[blockIdx.x] : blockIdx.x;
-    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
-    const int p = cta_expand<THREADS, false>(a, b, a_begin, a_end, keys, nullptr, s_wtot);
-    for (int t = p + threadIdx.x; t < N; t += THREADS) keys[t] = 0xffffffffu;
-    __syncthreads();
-    block_radix_sort<THREADS, ITEMS, false>(keys, nullptr, cnt, reinterpret_cast<uint32_t*>(s_wtot), col_bits);
-    int c = 0;
-    for (int i = threadIdx.x; i < p; i += THREADS)
-        if (i == 0 || keys[i] != keys[i - 1]) ++c;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
-    __syncthreads();
-    if (lane_id() == 0) s_wtot[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < THREADS / 32; ++w) t += s_wtot[w];
-        row_nnz[r] = (uint32_t)t;
-    }
-}
-
-template <int N, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_esc_numeric_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
-                  const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val,
-                  int col_bits) {
-    constexpr int ITEMS = N / THREADS;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    double* vals = reinterpret_cast<double*>(s_raw);
-    uint32_t* keys = reinterpret_cast<uint32_t*>(s_raw + sizeof(double) * N);
-    uint32_t* pay = keys + N;
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(pay + N);
-    __shared__ int s_wtot[THREADS / 32];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t r = perm ? perm[blockIdx.x] : blockIdx.x;
-    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
-    const int p = cta_expand<THREADS, true>(a, b, a_begin, a_end, keys, vals, s_wtot);
-    for (int t = p + threadIdx.x; t < N; t += THREADS) keys[t] = 0xffffffffu;
-    __syncthreads();
-    block_radix_sort<THREADS, ITEMS, true>(keys, pay, cnt, reinterpret_cast<uint32_t*>(s_wtot), col_bits);
-    const int64_t cbase = c_ptr[r];
-    int out_base = 0;
-    for (int base = 0; base < p; base += THREADS) {
-        int i = base + threadIdx.x;
-        bool valid = i < p;
-        uint32_t col = valid ? keys[i] : 0xffffffffu;
-        bool head = valid && (i == 0 || keys[i - 1] != col);
-        unsigned hm = __ballot_sync(FULL, head);
-        if (lane == 0) s_wtot[warp] = __popc(hm);
-        __syncthreads();
-        int wbase = out_base, all = 0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) {
-            int t = s_wtot[w];
-            if (w < warp) wbase += t;
-            all += t;
-        }
-        if (head) {
-            double sum = vals[pay[i]];
-            for (int j = i + 1; j < p; ++j) {
-                if (keys[j] != col) break;
-                sum = __dadd_rn(sum, vals[pay[j]]);
-            }
-            int o = wbase + __popc(hm & ((1u << lane) - 1u));
-            c_col[cbase + o] = (int32_t)col;
-            c_val[cbase + o] = sum;
-        }
-        out_base += all;
-        __syncthreads();
-    }
-}
-
 // ---- launchers --------------------------------------------------------------------------------
-// bins 1..5: warp per row (ESC_WARPS rows per CTA); bins 6..9: CTA per row
+// bins 1..5: warp per row (ESC_WARPS rows per CTA); bins 6..8: CTA per row (esc_cta_bitonic.cu)
 int esc_grid(int bin, uint32_t rows) {
     if (bin <= 5) return (int)((rows + ESC_WARPS - 1) / ESC_WARPS);
     return (int)rows;
 }
 
-static int col_bits_of(int64_t cols) {
-    int bits = 1;
-    while (bits < 32 && ((int64_t)1 << bits) < cols) ++bits;
-    return bits;
-}
-
-template <int N, int THREADS>
-static size_t sym_cta_smem() { return sizeof(uint32_t) * N + sizeof(uint16_t) * RADIX_DIGITS * THREADS; }
-template <int N, int THREADS>
-static size_t num_cta_smem() { return (sizeof(double) + 2 * sizeof(uint32_t)) * N + sizeof(uint16_t) * RADIX_DIGITS * THREADS; }
-
-template <int N, int THREADS>
-static void sym_cta_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm, uint32_t rows,
-                           uint32_t* row_nnz, cudaStream_t s) {
-    k_esc_symbolic_cta<N, THREADS><<<rows, THREADS, sym_cta_smem<N, THREADS>(), s>>>(a, b, row_begin, perm, rows, row_nnz,
-                                                                                  col_bits_of(b.cols));
-}
-template <int N, int THREADS>
-static void num_cta_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm, uint32_t rows,
-                           const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
-    k_esc_numeric_cta<N, THREADS><<<rows, THREADS, num_cta_smem<N, THREADS>(), s>>>(a, b, row_begin, perm, rows, c_ptr,
-                                                                                 c_col, c_val, col_bits_of(b.cols));
-}
-
-void setup_kernel_attributes() {
-    cudaFuncSetAttribute(k_esc_symbolic_cta<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sym_cta_smem<8192, 512>());
-    cudaFuncSetAttribute(k_esc_numeric_cta<2048, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)num_cta_smem<2048, 256>());
-    cudaFuncSetAttribute(k_esc_numeric_cta<4096, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)num_cta_smem<4096, 256>());
-    cudaFuncSetAttribute(k_esc_numeric_cta<8192, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)num_cta_smem<8192, 512>());
-}
+void setup_kernel_attributes() {}
 
 void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                          uint32_t rows, uint32_t* row_nnz, cudaStream_t s) {
@@ -489,11 +238,7 @@ void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_
         case 3: k_esc_symbolic_warp<128><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz); break;
         case 4: k_esc_symbolic_warp<256><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz); break;
         case 5: k_esc_symbolic_warp<512><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, row_nnz); break;
-        case 6: sym_cta_launch<1024, 256>(a, b, row_begin, perm, rows, row_nnz, s); break;
-        case 7: sym_cta_launch<2048, 256>(a, b, row_begin, perm, rows, row_nnz, s); break;
-        case 8: sym_cta_launch<4096, 256>(a, b, row_begin, perm, rows, row_nnz, s); break;
-        case 9: sym_cta_launch<8192, 512>(a, b, row_begin, perm, rows, row_nnz, s); break;
-        default: break;
+        default: launch_bitonic_cta_symbolic(bin, a, b, row_begin, perm, rows, row_nnz, s); break;
     }
 }
 
@@ -523,13 +268,7 @@ void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_b
             numeric_warp_dispatch<uint64_t>(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s);
         return;
     }
-    switch (bin) {
-        case 6: num_cta_launch<1024, 256>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;
-        case 7: num_cta_launch<2048, 256>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;
-        case 8: num_cta_launch<4096, 256>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;
-        case 9: num_cta_launch<8192, 512>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;
-        default: break;
-    }
+    launch_bitonic_cta_numeric(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s);
 }
 
 bool esc_needs_wide_keys(int bin, int64_t b_cols) {

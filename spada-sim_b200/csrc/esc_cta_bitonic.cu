@@ -1,6 +1,7 @@
-// esc_cta_bitonic.cu -- CTA-per-row ESC kernels (1024 / 2048 / 4096 products) with the hybrid
-// bitonic sort: every warp sorts its chunk in registers, chunks are merged through shared memory.
-// Kept beside the radix-sort variant of esc.cu; SPADA_B200_CTA_SORT picks one (see engine.cu).
+// esc_cta_bitonic.cu -- CTA-per-row ESC kernels (bins 6..8: 1024 / 2048 / 4096 products) with the
+// hybrid bitonic sort: every warp sorts its chunk in registers, chunks are merged through shared
+// memory.  (A stable 4-bit LSD radix sort in shared memory was tried for these bins and for an
+// 8192 bin: 30+ barriers per row made it 1.3-1.5x slower than this network at these sizes.)
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -135,6 +136,57 @@ __device__ __forceinline__ void bitonic_cta_sort(K* keys) {
     }
 }
 
+// Segmented sums + store of a sorted row held in shared memory.  Warp w owns the positions
+// [w*32*ITEMS, (w+1)*32*ITEMS), lanes interleaved (position = base + e*32 + lane: conflict-free
+// shared-memory reads, coalesced stores); run heads are found with ballots, one scan over the eight
+// warp totals places them, then every head sums its run left to right.
+template <typename K, int N>
+__device__ __forceinline__ void cta_reduce_store(const K* keys, const double* vals, int p, int64_t cbase,
+                                                 int32_t* __restrict__ c_col, double* __restrict__ c_val, CtaStage& st) {
+    constexpr int SB = Log2<N>::v;
+    constexpr int ITEMS = N / ESC_CTA_THREADS;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int w0 = warp * 32 * ITEMS;
+    unsigned hm[ITEMS];
+    uint32_t col[ITEMS];
+    uint32_t carry = (w0 > 0 && w0 <= p) ? (uint32_t)(keys[w0 - 1] >> SB) : 0xffffffffu;
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        const int i = w0 + e * 32 + lane;
+        col[e] = (i < p) ? (uint32_t)(keys[i] >> SB) : 0xffffffffu;
+        uint32_t cp = __shfl_up_sync(FULL, col[e], 1);
+        if (lane == 0) cp = carry;
+        const bool head = (i < p) && (i == 0 || cp != col[e]);
+        hm[e] = __ballot_sync(FULL, head);
+        carry = __shfl_sync(FULL, col[e], 31);
+        cnt += __popc(hm[e]);
+    }
+    __syncthreads();
+    if (lane == 0) st.wtot[warp] = cnt;
+    __syncthreads();
+    int o = 0;
+#pragma unroll
+    for (int w = 0; w < ESC_CTA_THREADS / 32; ++w)
+        if (w < warp) o += st.wtot[w];
+#pragma unroll
+    for (int e = 0; e < ITEMS; ++e) {
+        if ((hm[e] >> lane) & 1u) {
+            const int i = w0 + e * 32 + lane;
+            double sum = vals[(int)(keys[i] & (K)(N - 1))];
+            for (int j = i + 1; j < p; ++j) {
+                const K kj = keys[j];
+                if ((uint32_t)(kj >> SB) != col[e]) break;
+                sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
+            }
+            const int oo = o + __popc(hm[e] & ((1u << lane) - 1u));
+            c_col[cbase + oo] = (int32_t)col[e];
+            c_val[cbase + oo] = sum;
+        }
+        o += __popc(hm[e]);
+    }
+}
+
 template <int N>
 __global__ void __launch_bounds__(ESC_CTA_THREADS)
 k_bitonic_symbolic_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
@@ -179,47 +231,7 @@ k_bitonic_numeric_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __r
     for (int t = p + threadIdx.x; t < N; t += ESC_CTA_THREADS) keys[t] = KeyTraits<K>::sentinel;
     __syncthreads();
     bitonic_cta_sort<K, N>(keys);
-    // thread t owns the sorted positions [t*ITEMS, (t+1)*ITEMS): count the run heads among them, one
-    // block scan places them, then every head sums its run left to right (runs may reach into the
-    // next thread's positions; a thread skips the tail of a run that started before its range)
-    const int i0 = threadIdx.x * ITEMS;
-    uint32_t col[ITEMS];
-    bool head[ITEMS];
-    int cnt = 0;
-    uint32_t prev = (i0 > 0 && i0 <= p) ? (uint32_t)(keys[i0 - 1] >> SB) : 0xffffffffu;
-#pragma unroll
-    for (int e = 0; e < ITEMS; ++e) {
-        const int i = i0 + e;
-        col[e] = (i < p) ? (uint32_t)(keys[i] >> SB) : 0xffffffffu;
-        head[e] = (i < p) && (i == 0 || col[e] != prev);
-        prev = col[e];
-        cnt += head[e] ? 1 : 0;
-    }
-    int wtotal;
-    int woff = warp_excl_scan(cnt, lane, wtotal);
-    __syncthreads();
-    if (lane == 0) st.wtot[warp] = wtotal;
-    __syncthreads();
-    int o = woff;
-#pragma unroll
-    for (int w = 0; w < ESC_CTA_THREADS / 32; ++w)
-        if (w < warp) o += st.wtot[w];
-    const int64_t cbase = c_ptr[r];
-#pragma unroll
-    for (int e = 0; e < ITEMS; ++e) {
-        if (head[e]) {
-            const int i = i0 + e;
-            double sum = vals[(int)(keys[i] & (K)(N - 1))];
-            for (int j = i + 1; j < p; ++j) {
-                K kj = keys[j];
-                if ((uint32_t)(kj >> SB) != col[e]) break;
-                sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
-            }
-            c_col[cbase + o] = (int32_t)col[e];
-            c_val[cbase + o] = sum;
-            ++o;
-        }
-    }
+    cta_reduce_store<K, N>(keys, vals, p, c_ptr[r], c_col, c_val, st);
 }
 
 // ---- kept-keys variants: symbolic leaves the sorted packed keys in HBM, numeric reloads them ----------
@@ -275,44 +287,7 @@ k_bitonic_numeric_presorted_cta(DevCsr a, DevCsr b, int64_t row_begin, const uin
     const K* src = kstore + prod_ptr[r];
     for (int t = threadIdx.x; t < p; t += ESC_CTA_THREADS) keys[t] = src[t];
     __syncthreads();
-    const int i0 = threadIdx.x * ITEMS;
-    uint32_t col[ITEMS];
-    bool head[ITEMS];
-    int cnt = 0;
-    uint32_t prev = (i0 > 0 && i0 <= p) ? (uint32_t)(keys[i0 - 1] >> SB) : 0xffffffffu;
-#pragma unroll
-    for (int e = 0; e < ITEMS; ++e) {
-        const int i = i0 + e;
-        col[e] = (i < p) ? (uint32_t)(keys[i] >> SB) : 0xffffffffu;
-        head[e] = (i < p) && (i == 0 || col[e] != prev);
-        prev = col[e];
-        cnt += head[e] ? 1 : 0;
-    }
-    int wtotal;
-    int woff = warp_excl_scan(cnt, lane, wtotal);
-    __syncthreads();
-    if (lane == 0) st.wtot[warp] = wtotal;
-    __syncthreads();
-    int o = woff;
-#pragma unroll
-    for (int w = 0; w < ESC_CTA_THREADS / 32; ++w)
-        if (w < warp) o += st.wtot[w];
-    const int64_t cbase = c_ptr[r];
-#pragma unroll
-    for (int e = 0; e < ITEMS; ++e) {
-        if (head[e]) {
-            const int i = i0 + e;
-            double sum = vals[(int)(keys[i] & (K)(N - 1))];
-            for (int j = i + 1; j < p; ++j) {
-                K kj = keys[j];
-                if ((uint32_t)(kj >> SB) != col[e]) break;
-                sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
-            }
-            c_col[cbase + o] = (int32_t)col[e];
-            c_val[cbase + o] = sum;
-            ++o;
-        }
-    }
+    cta_reduce_store<K, N>(keys, vals, p, c_ptr[r], c_col, c_val, st);
 }
 
 template <typename K, int N>

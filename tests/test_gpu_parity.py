@@ -1,7 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle -- needs a B200.
 
 Bar: row_ptr and col_idx bit-exact; values within relative 1e-12 per
-entry in f64 (TOL below).  The sort-based bins (<= 8192 intermediate products per row) fix the
+entry in f64 (TOL below).  The sort-based bins (<= 4096 intermediate products per row) fix the
 oracle's summation order, so there the values are checked bit-exact as well.
 """
 import hashlib
@@ -49,8 +49,8 @@ def run(engine, oracle, a, b, exact=True, usize=False):
 # ---- every bin, forced individually ---------------------------------------------------------
 @pytest.mark.parametrize("ka,lb,expect_bin", [
     (1, 1, "32"), (4, 8, "32"), (5, 5, "32"), (8, 8, "64"), (10, 12, "128"), (16, 16, "256"),
-    (20, 25, "512"), (32, 32, "1024"), (40, 50, "2048"), (64, 64, "4096"), (70, 100, "8192"), (128, 64, "8192"),
-    (90, 100, "heavy"), (300, 40, "heavy"),
+    (20, 25, "512"), (32, 32, "1024"), (40, 50, "2048"), (64, 64, "4096"), (70, 100, "heavy"), (128, 64, "heavy"),
+    (300, 40, "heavy"),
 ])
 def test_each_bin(engine, oracle, ka, lb, expect_bin):
     m, k, n = 257, 600, 5000
@@ -68,7 +68,7 @@ def test_key_width_paths(engine, oracle, n_cols):
     for ka, lb in [(4, 6), (16, 16), (40, 50), (80, 90)]:
         a = random_csr(130, 300, row_nnz=ka, seed=3)
         b = random_csr(300, n_cols, row_nnz=lb, seed=4)
-        run(engine, oracle, a, b)
+        run(engine, oracle, a, b, exact=(ka * lb <= 4096))   # the heavy bin is checked at TOL
 
 
 def test_mixed_bins_and_permutation(engine, oracle):
@@ -84,7 +84,7 @@ def test_mixed_bins_and_permutation(engine, oracle):
     assert len(st["bins"]) >= 5
     # rows handled by the sort-based bins are bit-exact; the heavy bin is within TOL
     f = oracle.flops(a, b)
-    light = np.repeat(f <= 8192, np.diff(ref[0]))
+    light = np.repeat(f <= 4096, np.diff(ref[0]))
     assert np.array_equal(dx[light].view(np.uint64), ref[2][light].view(np.uint64))
     assert (np.abs(dx[~light] - ref[2][~light]) <= TOL * np.abs(ref[2][~light])).all()
 
