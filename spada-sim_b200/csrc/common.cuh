@@ -16,11 +16,14 @@ constexpr unsigned FULL = 0xffffffffu;
 //   bin 1          p <= 32                one warp per row, products sorted in registers
 //   bin 2..5       p <= 64,128,256,512    one warp per row, E = N/32 keys per lane
 //   bin 6..8       p <= 1024,2048,4096    one CTA per row, register chunk sorts merged in shared memory
-//   bin 9          p  > 4096              items of ~8192 products over the grid, bitmap + rank
-constexpr int NUM_BINS = 10;
+//   bin 9          p <= 65536             one CTA (1024 threads) per row, bitmap + ranks in shared memory
+//   bin 10         p  > 65536             items of ~8192 products over the grid, bitmap + ranks in HBM/L2
+constexpr int NUM_BINS = 11;
 constexpr int BIN_EMPTY = 0;
 constexpr int BIN_HEAVY = 9;
+constexpr int BIN_HUGE = 10;
 constexpr uint32_t ESC_MAX_PRODUCTS = 4096;
+constexpr uint32_t HEAVY_MAX_PRODUCTS = 65536;
 
 __host__ __device__ inline int bin_of(uint32_t p) {
     if (p == 0) return 0;
@@ -32,7 +35,8 @@ __host__ __device__ inline int bin_of(uint32_t p) {
     if (p <= 1024) return 6;
     if (p <= 2048) return 7;
     if (p <= 4096) return 8;
-    return 9;
+    if (p <= 65536) return 9;
+    return 10;
 }
 __host__ __device__ inline uint32_t bin_capacity(int b) { return b == 0 ? 0u : (b >= BIN_HEAVY ? 0u : (32u << (b - 1))); }
 
@@ -235,7 +239,12 @@ void launch_cta_numeric_presorted(int bin, bool wide, const DevCsr& a, const Dev
                                   const uint32_t* perm, uint32_t rows, const int64_t* c_ptr, int32_t* c_col,
                                   double* c_val, const int64_t* prod_ptr, const void* kstore, cudaStream_t s);
 bool esc_needs_wide_keys(int bin, int64_t b_cols);
-// stage 2 / 3, heavy bin (9): rows are cut into items (~8192 products) spread over the grid
+// stage 2 / 3, heavy bin (9): one CTA per row, bitmap in shared memory (heavy_smem.cu)
+void launch_heavy_smem_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
+                                uint32_t n_rows, uint32_t* row_nnz, cudaStream_t s);
+void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
+                               uint32_t n_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+// stage 2 / 3, huge bin (10): rows are cut into items (~8192 products) spread over the grid (heavy.cu)
 struct HeavyPlan {
     uint32_t words;      // bitmap words per row = ceil(B.cols / 32)
     uint32_t wave_rows;  // heavy rows whose bitmaps fit the workspace at once

@@ -176,7 +176,7 @@ struct LaunchRec {
 };
 
 const char* bin_name(int b) {
-    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy"};
+    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy", "huge"};
     return names[b];
 }
 
@@ -660,7 +660,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         st.bin_rows[bnum] = pc.bin_rows[bnum];
         st.bin_products[bnum] = pc.bin_products[bnum];
         st.bin_window_rows[bnum] = (bnum >= 1 && bnum <= 5) ? 4u : (bnum == 0 ? 0u : 1u);
-        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : 256u);
+        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : (bnum == BIN_HEAVY ? 1024u : 256u));
     }
     tbl.offset[NUM_BINS] = off;
     // a single non-empty bin holding every row needs no permutation
@@ -723,17 +723,17 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         end_rec();
     }
 
-    // heavy rows: cut into items, bitmaps for one wave of rows at a time
+    // huge rows: cut into items, bitmaps for one wave of rows at a time
     HeavyPlan HP{};
-    const uint32_t n_heavy = pc.bin_rows[BIN_HEAVY];
+    const uint32_t n_heavy = pc.bin_rows[BIN_HUGE];
     if (n_heavy) {
-        HP = heavy_plan_sizes(n_heavy, pc.bin_products[BIN_HEAVY], B.cols, h->heavy_ws_budget);
+        HP = heavy_plan_sizes(n_heavy, pc.bin_products[BIN_HUGE], B.cols, h->heavy_ws_budget);
         TRY(dalloc(h, &d_items_per_row, (size_t)n_heavy));
         TRY(dalloc(h, &d_item_off, (size_t)n_heavy + 1));
         TRY(dalloc(h, &d_item_row, (size_t)HP.max_items));
         TRY(dalloc(h, &d_heavy_ws, HP.ws_words));
-        begin_rec("heavy_items", 1, (n_heavy + 255) / 256, n_heavy, pc.bin_products[BIN_HEAVY]);
-        launch_heavy_items(A, (int64_t)row_begin, perm_of_bin[BIN_HEAVY], n_heavy, d_flops, d_items_per_row,
+        begin_rec("huge_items", 1, (n_heavy + 255) / 256, n_heavy, pc.bin_products[BIN_HUGE]);
+        launch_heavy_items(A, (int64_t)row_begin, perm_of_bin[BIN_HUGE], n_heavy, d_flops, d_items_per_row,
                            d_item_off, d_item_row, d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
         kernels += 3;
@@ -747,19 +747,23 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         char name[32];
         snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
         if (bnum == BIN_HEAVY) {
+            begin_rec(name, 2, rows, rows, pc.bin_products[bnum]);
+            launch_heavy_smem_symbolic(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
+            kernels += 1;
+        } else if (bnum == BIN_HUGE) {
             const uint32_t* hl = perm_of_bin[bnum];
             const bool detail = HP.n_waves == 1;  // per-kernel records for a single wave, one record otherwise
             if (!detail) begin_rec(name, 2, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum]);
             for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
                 uint32_t hi = std::min(rows, lo + HP.wave_rows);
-                if (detail) begin_rec("sym_heavy_clear", 2, 0, hi - lo, 0);
+                if (detail) begin_rec("sym_huge_clear", 2, 0, hi - lo, 0);
                 CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), s));
                 if (detail) end_rec();
-                if (detail) begin_rec("sym_heavy_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                if (detail) begin_rec("sym_huge_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
                                   h->sm_count, s);
                 if (detail) end_rec();
-                if (detail) begin_rec("sym_heavy_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum]);
+                if (detail) begin_rec("sym_huge_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, s);
                 kernels += 2;
             }
@@ -816,6 +820,10 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         char name[32];
         snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
         if (bnum == BIN_HEAVY) {
+            begin_rec(name, 3, rows, rows, pc.bin_products[bnum]);
+            launch_heavy_smem_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
+            kernels += 1;
+        } else if (bnum == BIN_HUGE) {
             const uint32_t* hl = perm_of_bin[bnum];
             const bool ws_valid = HP.n_waves == 1;  // bitmaps + ranks of the symbolic stage are still resident
             if (!ws_valid) begin_rec(name, 3, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum]);
@@ -828,10 +836,10 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
                     launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, nullptr, s);
                     kernels += 2;
                 }
-                if (ws_valid) begin_rec("num_heavy_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum]);
+                if (ws_valid) begin_rec("num_huge_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, R->ptr, R->col, R->val, s);
                 if (ws_valid) end_rec();
-                if (ws_valid) begin_rec("num_heavy_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                if (ws_valid) begin_rec("num_huge_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
                 launch_heavy_accum(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
                                    R->ptr, R->val, h->sm_count, s);
                 kernels += 2;

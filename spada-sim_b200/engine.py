@@ -15,7 +15,7 @@ from . import _abi
 from ._abi import check, lib
 
 U64_MAX = (1 << 64) - 1
-BIN_NAMES = ["empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy"]
+BIN_NAMES = ["empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy", "huge"]
 
 
 def _ptr(a: np.ndarray, ct):

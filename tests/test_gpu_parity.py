@@ -50,14 +50,14 @@ def run(engine, oracle, a, b, exact=True, usize=False):
 @pytest.mark.parametrize("ka,lb,expect_bin", [
     (1, 1, "32"), (4, 8, "32"), (5, 5, "32"), (8, 8, "64"), (10, 12, "128"), (16, 16, "256"),
     (20, 25, "512"), (32, 32, "1024"), (40, 50, "2048"), (64, 64, "4096"), (70, 100, "heavy"), (128, 64, "heavy"),
-    (300, 40, "heavy"),
+    (300, 40, "heavy"), (300, 230, "huge"),
 ])
 def test_each_bin(engine, oracle, ka, lb, expect_bin):
     m, k, n = 257, 600, 5000
-    vals = "uniform" if expect_bin == "heavy" else "signed"   # heavy bin: order not fixed -> no cancellation
+    vals = "uniform" if expect_bin in ("heavy", "huge") else "signed"   # heavy bin: order not fixed -> no cancellation
     a = random_csr(m, k, row_nnz=ka, seed=ka * 7 + lb, values=vals)
     b = random_csr(k, n, row_nnz=lb, seed=ka * 11 + lb, values=vals)
-    _, st = run(engine, oracle, a, b, exact=(expect_bin != "heavy"))
+    _, st = run(engine, oracle, a, b, exact=(expect_bin not in ("heavy", "huge")))
     assert list(st["bins"].keys()) == [expect_bin], st["bins"]
     assert st["bins"][expect_bin]["rows"] == m
 
