@@ -207,6 +207,9 @@ void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t row_begin, int6
                   uint32_t* flops, uint32_t* long_list, PlanCounters* ctr, cudaStream_t s);
 void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, uint32_t* perm,
                         PlanCounters* ctr, cudaStream_t s);
+void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t* out, cudaStream_t s);
+void launch_copy_rows(const uint32_t* flops, int64_t m, const int64_t* t_ptr, const int32_t* t_col, const double* t_val,
+                      const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
 // stage 4
 void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out /* n+1 */, uint64_t* tile_state,
                          PlanCounters* ctr, cudaStream_t s);
@@ -222,8 +225,10 @@ void launch_validate(const DevCsr& a, PlanCounters* ctr, cudaStream_t s);
 int esc_grid(int bin, uint32_t rows);
 void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                          uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
+// row_nnz_out (nullable): the kernel also records every row's nnz (first pass of the scratch mode)
 void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                        uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+                        uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                        uint32_t* row_nnz_out = nullptr);
 // two-phase mode with kept keys: symbolic stores each row's sorted (column, arrival) keys at
 // kstore + prod_ptr[row]; numeric reloads them instead of sorting again (bins 1..8)
 void launch_esc_symbolic_keep(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
@@ -271,7 +276,8 @@ void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, con
 void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                                  uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
 void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                                uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+                                uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                                uint32_t* row_nnz_out = nullptr);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
 void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,

@@ -66,7 +66,7 @@ struct spada_b200 {
     std::unordered_map<void*, size_t> pool_live;
     size_t pool_bytes = 0;
     size_t dev_total_mem = 0;
-    bool keep_keys = true;    // two-phase mode: numeric reloads the keys symbolic sorted (SPADA_B200_KEEP_KEYS=0 off)
+    int two_phase_mode = 2;   // sort bins in two-phase mode: 0 sort twice, 1 keep the sorted keys, 2 scratch rows + copy
     size_t heavy_ws_budget = (size_t)2 << 30;  // bitmap workspace for the heavy bin (SPADA_B200_HEAVY_WS_MB)
 };
 
@@ -301,7 +301,8 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
     CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_scalar, 64));
     setup_kernel_attributes();
-    if (const char* e = getenv("SPADA_B200_KEEP_KEYS")) h->keep_keys = atoi(e) != 0;
+    if (const char* e = getenv("SPADA_B200_TWO_PHASE_MODE"))
+        h->two_phase_mode = !strcmp(e, "plain") ? 0 : (!strcmp(e, "keys") ? 1 : 2);
     if (const char* e = getenv("SPADA_B200_HEAVY_WS_MB")) {
         long mb = atol(e);
         if (mb > 0) h->heavy_ws_budget = (size_t)mb << 20;
@@ -594,6 +595,9 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     uint32_t *d_items_per_row = nullptr, *d_item_row = nullptr;
     int64_t *d_item_off = nullptr, *d_prod_ptr = nullptr;
     void* d_kstore = nullptr;
+    uint32_t* d_masked = nullptr;
+    int32_t* d_tcol = nullptr;
+    double* d_tval = nullptr;
     uint32_t kernels = 0;
     auto cleanup = [&]() {
         dfree(h, d_flops);
@@ -607,6 +611,9 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         dfree(h, d_item_off);
         dfree(h, d_prod_ptr);
         dfree(h, (char*)d_kstore);
+        dfree(h, d_masked);
+        dfree(h, d_tcol);
+        dfree(h, d_tval);
     };
 #define TRY(x)                    \
     do {                          \
@@ -702,7 +709,13 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     // Two-phase mode: the symbolic kernels of the sort bins (1..8) leave each row's sorted keys in HBM
     // at kstore + prod_ptr[row]; the numeric kernels reload them instead of sorting the row again.
     bool keep_keys = false, wide_keys = false;
-    if (!fused && h->keep_keys) {
+    // Mode 2 (default): the first pass computes the finished rows of the sort bins into a scratch CSR
+    // laid out by product count; after the scan they are copied to their place -- one expansion, one sort.
+    uint64_t sorted_products = 0;
+    for (int bnum = 1; bnum <= 8; ++bnum) sorted_products += pc.bin_products[bnum];
+    const bool scratch = !fused && h->two_phase_mode == 2 && sorted_products > 0 &&
+                         (double)sorted_products * 12.0 <= 0.30 * (double)h->dev_total_mem;
+    if (!fused && !scratch && h->two_phase_mode >= 1) {
         uint64_t sorted_rows = 0;
         for (int bnum = 1; bnum <= 8; ++bnum) {
             sorted_rows += pc.bin_rows[bnum];
@@ -720,6 +733,19 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         launch_scan_u32_i64(d_flops, m, d_prod_ptr, d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
         kernels += 1;
+        end_rec();
+    }
+
+    if (scratch) {
+        TRY(dalloc(h, &d_masked, (size_t)m));
+        TRY(dalloc(h, &d_prod_ptr, (size_t)m + 1));
+        TRY(dalloc(h, &d_tcol, (size_t)sorted_products));
+        TRY(dalloc(h, &d_tval, (size_t)sorted_products));
+        begin_rec("scratch_ptr", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
+        launch_mask_sorted(d_flops, m, d_masked, s);
+        launch_scan_u32_i64(d_masked, m, d_prod_ptr, d_tiles, h->d_ctr, s);
+        CUT(cudaGetLastError());
+        kernels += 2;
         end_rec();
     }
 
@@ -767,6 +793,12 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
                 launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, s);
                 kernels += 2;
             }
+        } else if (scratch) {
+            snprintf(name, sizeof(name), "sort_pass<%s>", bin_name(bnum));
+            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
+            launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_prod_ptr, d_tcol, d_tval, s,
+                               d_nnz);
+            kernels += 1;
         } else {
             begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
             if (keep_keys && bnum <= 5)
@@ -814,9 +846,17 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     }
 
     // ---- stage 3: numeric -------------------------------------------------------------------
+    if (scratch) {
+        begin_rec("copy_rows", 3, (uint32_t)((m + 7) / 8), (uint64_t)m, sorted_products);
+        launch_copy_rows(d_flops, m, d_prod_ptr, d_tcol, d_tval, R->ptr, R->col, R->val, s);
+        CUT(cudaGetLastError());
+        kernels += 1;
+        end_rec();
+    }
     for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
         uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
+        if (scratch && bnum <= 8) continue;
         char name[32];
         snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
         if (bnum == BIN_HEAVY) {

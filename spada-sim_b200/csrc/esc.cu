@@ -65,7 +65,8 @@ k_esc_symbolic_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __res
 template <typename K, int N>
 __global__ void __launch_bounds__(ESC_WARPS * 32)
 k_esc_numeric_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
-                   const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+                   const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val,
+                   uint32_t* __restrict__ row_nnz_out) {
     constexpr int E = N / 32;
     constexpr int SB = Log2<N>::v;
     __shared__ __align__(16) K s_keys[ESC_WARPS][N];
@@ -118,6 +119,7 @@ k_esc_numeric_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __rest
         }
         out_base += __popc(hm);
     }
+    if (row_nnz_out && lane == 0) row_nnz_out[r] = (uint32_t)out_base;
 }
 
 // ---- kept-keys variants (two-phase mode) ----------------------------------------------------------
@@ -244,31 +246,33 @@ void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_
 
 template <typename K>
 static void numeric_warp_dispatch(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                                  uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+                                  uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                                  uint32_t* nnz_out) {
     unsigned g = (unsigned)esc_grid(bin, rows);
     switch (bin) {
-        case 1: k_esc_numeric_warp<K, 32><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val); break;
-        case 2: k_esc_numeric_warp<K, 64><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val); break;
-        case 3: k_esc_numeric_warp<K, 128><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val); break;
-        case 4: k_esc_numeric_warp<K, 256><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val); break;
-        default: k_esc_numeric_warp<K, 512><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val); break;
+        case 1: k_esc_numeric_warp<K, 32><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, nnz_out); break;
+        case 2: k_esc_numeric_warp<K, 64><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, nnz_out); break;
+        case 3: k_esc_numeric_warp<K, 128><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, nnz_out); break;
+        case 4: k_esc_numeric_warp<K, 256><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, nnz_out); break;
+        default: k_esc_numeric_warp<K, 512><<<g, ESC_WARPS * 32, 0, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, nnz_out); break;
     }
 }
 
 void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                        uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+                        uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                        uint32_t* row_nnz_out) {
     if (rows == 0) return;
     if (bin <= 5) {
         // 32-bit keys whenever (column << log2 N | arrival) fits: b.cols <= 2^(32 - log2 N)
         int sb = 4 + bin;  // log2(N): bin 1 -> 32 = 2^5
         bool narrow = (uint64_t)b.cols <= (1ull << (32 - sb));
         if (narrow)
-            numeric_warp_dispatch<uint32_t>(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s);
+            numeric_warp_dispatch<uint32_t>(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s, row_nnz_out);
         else
-            numeric_warp_dispatch<uint64_t>(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s);
+            numeric_warp_dispatch<uint64_t>(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s, row_nnz_out);
         return;
     }
-    launch_bitonic_cta_numeric(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s);
+    launch_bitonic_cta_numeric(bin, a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s, row_nnz_out);
 }
 
 bool esc_needs_wide_keys(int bin, int64_t b_cols) {

@@ -141,8 +141,8 @@ __device__ __forceinline__ void bitonic_cta_sort(K* keys) {
 // shared-memory reads, coalesced stores); run heads are found with ballots, one scan over the eight
 // warp totals places them, then every head sums its run left to right.
 template <typename K, int N>
-__device__ __forceinline__ void cta_reduce_store(const K* keys, const double* vals, int p, int64_t cbase,
-                                                 int32_t* __restrict__ c_col, double* __restrict__ c_val, CtaStage& st) {
+__device__ __forceinline__ int cta_reduce_store(const K* keys, const double* vals, int p, int64_t cbase,
+                                                int32_t* __restrict__ c_col, double* __restrict__ c_val, CtaStage& st) {
     constexpr int SB = Log2<N>::v;
     constexpr int ITEMS = N / ESC_CTA_THREADS;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -165,10 +165,12 @@ __device__ __forceinline__ void cta_reduce_store(const K* keys, const double* va
     __syncthreads();
     if (lane == 0) st.wtot[warp] = cnt;
     __syncthreads();
-    int o = 0;
+    int o = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < ESC_CTA_THREADS / 32; ++w)
+    for (int w = 0; w < ESC_CTA_THREADS / 32; ++w) {
         if (w < warp) o += st.wtot[w];
+        total += st.wtot[w];
+    }
 #pragma unroll
     for (int e = 0; e < ITEMS; ++e) {
         if ((hm[e] >> lane) & 1u) {
@@ -185,6 +187,7 @@ __device__ __forceinline__ void cta_reduce_store(const K* keys, const double* va
         }
         o += __popc(hm[e]);
     }
+    return total;
 }
 
 template <int N>
@@ -217,7 +220,8 @@ k_bitonic_symbolic_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __
 template <typename K, int N>
 __global__ void __launch_bounds__(ESC_CTA_THREADS)
 k_bitonic_numeric_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ perm, uint32_t rows,
-                      const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+                      const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val,
+                      uint32_t* __restrict__ row_nnz_out) {
     constexpr int SB = Log2<N>::v;
     constexpr int ITEMS = N / ESC_CTA_THREADS;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -231,7 +235,8 @@ k_bitonic_numeric_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __r
     for (int t = p + threadIdx.x; t < N; t += ESC_CTA_THREADS) keys[t] = KeyTraits<K>::sentinel;
     __syncthreads();
     bitonic_cta_sort<K, N>(keys);
-    cta_reduce_store<K, N>(keys, vals, p, c_ptr[r], c_col, c_val, st);
+    const int total = cta_reduce_store<K, N>(keys, vals, p, c_ptr[r], c_col, c_val, st);
+    if (row_nnz_out && threadIdx.x == 0) row_nnz_out[r] = (uint32_t)total;
 }
 
 // ---- kept-keys variants: symbolic leaves the sorted packed keys in HBM, numeric reloads them ----------
@@ -346,14 +351,16 @@ void launch_cta_numeric_presorted(int bin, bool wide, const DevCsr& a, const Dev
 
 template <typename K, int N>
 static void bitonic_numeric_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                                   uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+                                   uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                                   uint32_t* nnz_out) {
     size_t smem = (sizeof(K) + sizeof(double)) * N;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_bitonic_numeric_cta<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    k_bitonic_numeric_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val);
+    k_bitonic_numeric_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val,
+                                                                    nnz_out);
 }
 
 void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
@@ -367,15 +374,16 @@ void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int6
 }
 
 void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                                uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+                                uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                                uint32_t* nnz_out) {
     if (rows == 0) return;
     int sb = 4 + bin;
     bool narrow = (uint64_t)b.cols <= (1ull << (32 - sb));
 #define BITONIC_CASE(K)                                                                                      \
     switch (bin) {                                                                                            \
-        case 6: bitonic_numeric_launch<K, 1024>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;  \
-        case 7: bitonic_numeric_launch<K, 2048>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break;  \
-        default: bitonic_numeric_launch<K, 4096>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s); break; \
+        case 6: bitonic_numeric_launch<K, 1024>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s, nnz_out); break;  \
+        case 7: bitonic_numeric_launch<K, 2048>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s, nnz_out); break;  \
+        default: bitonic_numeric_launch<K, 4096>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val, s, nnz_out); break; \
     }
     if (narrow) { BITONIC_CASE(uint32_t) } else { BITONIC_CASE(uint64_t) }
 #undef BITONIC_CASE

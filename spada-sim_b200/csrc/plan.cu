@@ -55,19 +55,28 @@ k_flops(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin, int64_t 
     }
 }
 
-// K1b: long A rows, one CTA per row (persistent over the deferred list).
-__global__ void __launch_bounds__(FLOPS_THREADS)
+// K1b: long A rows, one CTA of 1024 threads per row (persistent over the deferred list); four
+// independent gathers per thread in flight.
+constexpr int FLOPS_LONG_THREADS = 1024;
+__global__ void __launch_bounds__(FLOPS_LONG_THREADS)
 k_flops_long(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin,
              uint32_t* __restrict__ flops, const uint32_t* __restrict__ long_list, PlanCounters* ctr) {
-    __shared__ unsigned long long s_warp[FLOPS_THREADS / 32];
+    __shared__ unsigned long long s_warp[FLOPS_LONG_THREADS / 32];
     uint32_t n_long = ctr->long_rows;
     for (uint32_t idx = blockIdx.x; idx < n_long; idx += gridDim.x) {
         uint32_t i = long_list[idx];
         int64_t s = a.ptr[row_begin + i], e = a.ptr[row_begin + i + 1];
         unsigned long long f = 0;
-        for (int64_t p = s + threadIdx.x; p < e; p += FLOPS_THREADS) {
-            int32_t k = ldg_i32(a.col + p);
-            f += (unsigned long long)(ldg_i64(b_ptr + k + 1) - ldg_i64(b_ptr + k));
+        for (int64_t p0 = s + threadIdx.x; p0 < e; p0 += 4 * FLOPS_LONG_THREADS) {
+            int32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int64_t p = p0 + (int64_t)u * FLOPS_LONG_THREADS;
+                k[u] = p < e ? ldg_i32(a.col + p) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k[u] >= 0) f += (unsigned long long)(ldg_i64(b_ptr + k[u] + 1) - ldg_i64(b_ptr + k[u]));
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
@@ -75,7 +84,7 @@ k_flops_long(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin,
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long t = 0;
-            for (int w = 0; w < FLOPS_THREADS / 32; ++w) t += s_warp[w];
+            for (int w = 0; w < FLOPS_LONG_THREADS / 32; ++w) t += s_warp[w];
             uint32_t f32 = t > 0xffffffffull ? 0xffffffffu : (uint32_t)t;
             flops[i] = f32;
             int b = bin_of(f32);
@@ -92,7 +101,7 @@ void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t row_begin, int6
     if (m <= 0) return;
     unsigned grid = (unsigned)((m + FLOPS_THREADS - 1) / FLOPS_THREADS);
     k_flops<<<grid, FLOPS_THREADS, 0, s>>>(a, b_ptr, row_begin, m, flops, long_list, ctr);
-    k_flops_long<<<148 * 4, FLOPS_THREADS, 0, s>>>(a, b_ptr, row_begin, flops, long_list, ctr);
+    k_flops_long<<<148 * 2, FLOPS_LONG_THREADS, 0, s>>>(a, b_ptr, row_begin, flops, long_list, ctr);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -234,6 +243,45 @@ void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out, uint64_t* 
     cudaMemsetAsync(&ctr->scan_ticket, 0, sizeof(uint32_t), s);
     k_scan_u32_i64<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(in, n, out, (unsigned long long*)tile_state,
                                                             &ctr->scan_ticket);
+}
+
+// ---------------------------------------------------------------------------------------
+// Two-phase mode, sort bins: the first pass writes finished rows to a scratch CSR laid out by
+// product count (an upper bound of every row's nnz); after the row_ptr scan they are copied to
+// their final place.  k_mask_sorted yields the per-row scratch sizes, k_copy_rows moves the rows.
+__global__ void k_mask_sorted(const uint32_t* __restrict__ flops, int64_t m, uint32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) {
+        uint32_t f = flops[i];
+        out[i] = (f <= ESC_MAX_PRODUCTS) ? f : 0u;
+    }
+}
+void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t* out, cudaStream_t s) {
+    if (m > 0) k_mask_sorted<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(flops, m, out);
+}
+
+constexpr int COPY_WARPS = 8;
+__global__ void __launch_bounds__(COPY_WARPS * 32)
+k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, const int64_t* __restrict__ t_ptr,
+            const int32_t* __restrict__ t_col, const double* __restrict__ t_val, const int64_t* __restrict__ c_ptr,
+            int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+    const int lane = lane_id();
+    const int64_t r = (int64_t)blockIdx.x * COPY_WARPS + (threadIdx.x >> 5);
+    if (r >= m) return;
+    const uint32_t f = flops[r];
+    if (f == 0 || f > ESC_MAX_PRODUCTS) return;  // empty rows have nothing; heavy rows are written by their own kernels
+    const int64_t src = t_ptr[r], dst = c_ptr[r];
+    const int n = (int)(c_ptr[r + 1] - dst);
+    for (int j = lane; j < n; j += 32) {
+        c_col[dst + j] = t_col[src + j];
+        c_val[dst + j] = t_val[src + j];
+    }
+}
+void launch_copy_rows(const uint32_t* flops, int64_t m, const int64_t* t_ptr, const int32_t* t_col, const double* t_val,
+                      const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+    if (m > 0)
+        k_copy_rows<<<(unsigned)((m + COPY_WARPS - 1) / COPY_WARPS), COPY_WARPS * 32, 0, s>>>(flops, m, t_ptr, t_col, t_val,
+                                                                                          c_ptr, c_col, c_val);
 }
 
 // ---------------------------------------------------------------------------------------
