@@ -48,7 +48,7 @@ k_esc_symbolic_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __res
     __syncwarp();
     uint32_t x[E];
     load_blocked<uint32_t, E>(x, keys, lane);
-    warp_sort<uint32_t, E>(x, lane, false);
+    warp_sort<uint32_t, E>(x, lane);
     uint32_t prev = __shfl_up_sync(FULL, x[E - 1], 1);
     int cnt = 0;
 #pragma unroll
@@ -92,7 +92,7 @@ k_esc_numeric_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __rest
     __syncwarp();
     K x[E];
     load_blocked<K, E>(x, keys, lane);
-    warp_sort<K, E>(x, lane, false);
+    warp_sort<K, E>(x, lane);
     __syncwarp();
     store_blocked<K, E>(x, keys, lane);
     __syncwarp();
@@ -151,7 +151,7 @@ k_esc_symbolic_keep_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* 
     __syncwarp();
     K x[E];
     load_blocked<K, E>(x, keys, lane);
-    warp_sort<K, E>(x, lane, false);
+    warp_sort<K, E>(x, lane);
     __syncwarp();
     store_blocked<K, E>(x, keys, lane);
     const K prev = shfl_up_key(x[E - 1]);

@@ -110,19 +110,30 @@ __device__ __forceinline__ void bitonic_cta_sort(K* keys) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     K x[E];
     load_blocked<K, E>(x, keys + warp * CH, lane);
-    warp_sort<K, E>(x, lane, (warp & 1) != 0);
+    warp_sort<K, E>(x, lane);
     store_blocked<K, E>(x, keys + warp * CH, lane);
     __syncthreads();
 #pragma unroll 1
     for (int k = 2 * CH; k <= N; k <<= 1) {
+        // flip stage: i against its mirror image inside the block of k keys
+        for (int t = threadIdx.x; t < N / 2; t += ESC_CTA_THREADS) {
+            const int h = k >> 1;
+            const int i = ((t & ~(h - 1)) << 1) | (t & (h - 1));
+            const int l = i ^ (k - 1);
+            const K ka = keys[i], kb = keys[l];
+            if (ka > kb) {
+                keys[i] = kb;
+                keys[l] = ka;
+            }
+        }
+        __syncthreads();
 #pragma unroll 1
-        for (int j = k >> 1; j >= CH; j >>= 1) {
+        for (int j = k >> 2; j >= CH; j >>= 1) {
             for (int t = threadIdx.x; t < N / 2; t += ESC_CTA_THREADS) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int l = i | j;
-                bool up = (i & k) == 0;
-                K ka = keys[i], kb = keys[l];
-                if ((ka > kb) == up) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const K ka = keys[i], kb = keys[l];
+                if (ka > kb) {
                     keys[i] = kb;
                     keys[l] = ka;
                 }
@@ -130,7 +141,7 @@ __device__ __forceinline__ void bitonic_cta_sort(K* keys) {
             __syncthreads();
         }
         load_blocked<K, E>(x, keys + warp * CH, lane);
-        warp_merge_tail<K, E>(x, lane, ((warp * CH) & k) == 0);
+        warp_merge_tail<K, E>(x, lane);
         store_blocked<K, E>(x, keys + warp * CH, lane);
         __syncthreads();
     }

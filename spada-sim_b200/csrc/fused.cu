@@ -39,7 +39,7 @@ __device__ __forceinline__ int sort_count(K* keys, int p, int lane) {
     __syncwarp();
     K x[E];
     load_blocked<K, E>(x, keys, lane);
-    warp_sort<K, E>(x, lane, false);
+    warp_sort<K, E>(x, lane);
     __syncwarp();
     store_blocked<K, E>(x, keys, lane);
     const K prev = shfl_up_key(x[E - 1]);
@@ -284,7 +284,7 @@ k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* _
                     __syncwarp();
                 }
                 const bool have = lane < p;
-                warp_sort<K, 1>(x, lane, false);
+                warp_sort<K, 1>(x, lane);
                 const uint32_t col = (uint32_t)(x[0] >> 5);
                 const double v = shfl_f64(prod, (int)(x[0] & (K)31));
                 const uint32_t col_prev = __shfl_up_sync(FULL, col, 1);

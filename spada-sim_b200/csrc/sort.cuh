@@ -62,59 +62,82 @@ __device__ __forceinline__ uint64_t shfl_up_key(uint64_t v) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-// One phase (all strides KK/2 .. 1) of the bitonic network over the 32*E keys a warp holds in
-// registers, element index e = lane*E + r.  `flip` inverts every comparison (descending).
-template <typename K, int E, int KK>
-__device__ __forceinline__ void bitonic_phase(K (&x)[E], int lane, bool flip) {
+// Bitonic network in its all-ascending form: phase KK merges two ascending halves of every block of
+// KK keys by first comparing element i with its mirror image i ^ (KK-1) ("flip"), then running
+// half-cleaners of strides KK/4 .. 1.  Every compare-exchange keeps the smaller key at the lower
+// index, so the register-to-register steps need no direction selects (two VIMNMX per pair) and
+// chunks never have to be sorted descending.  Element index e = lane*E + r.
+template <typename K>
+__device__ __forceinline__ void cmpx(K& a, K& b) {
+    const K lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo;
+    b = hi;
+}
+
+// half-cleaners of strides JS, JS/2, .. 1
+template <typename K, int E, int JS>
+__device__ __forceinline__ void half_cleaners(K (&x)[E], int lane) {
 #pragma unroll
-    for (int j = KK / 2; j > 0; j >>= 1) {
+    for (int j = JS; j > 0; j >>= 1) {
         if (j >= E) {
             const int lj = j / E;
             const bool lower = (lane & lj) == 0;
-            const bool up_lane = (KK >= E) ? (((lane * E) & KK) == 0) : true;
 #pragma unroll
             for (int r = 0; r < E; ++r) {
-                const bool up = ((KK >= E) ? up_lane : ((r & KK) == 0)) != flip;
-                K y = shfl_xor_key(x[r], lj);
-                K lo = x[r] < y ? x[r] : y, hi = x[r] < y ? y : x[r];
-                x[r] = (lower == up) ? lo : hi;
+                const K y = shfl_xor_key(x[r], lj);
+                const K lo = x[r] < y ? x[r] : y, hi = x[r] < y ? y : x[r];
+                x[r] = lower ? lo : hi;
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < E; ++r) {
-                if ((r & j) == 0) {
-                    const bool up = ((KK >= E) ? (((lane * E) & KK) == 0) : ((r & KK) == 0)) != flip;
-                    K a = x[r], b = x[r | j];
-                    K lo = a < b ? a : b, hi = a < b ? b : a;
-                    x[r] = up ? lo : hi;
-                    x[r | j] = up ? hi : lo;
-                }
-            }
+            for (int r = 0; r < E; ++r)
+                if ((r & j) == 0) cmpx(x[r], x[r | j]);
         }
     }
 }
 
 template <typename K, int E, int KK>
+__device__ __forceinline__ void bitonic_phase(K (&x)[E], int lane) {
+    if constexpr (KK <= E) {
+#pragma unroll
+        for (int r = 0; r < E; ++r)
+            if (r < (r ^ (KK - 1))) cmpx(x[r], x[r ^ (KK - 1)]);
+    } else {
+        constexpr int LM = KK / E - 1;
+        const bool lower = (lane & (KK / (2 * E))) == 0;
+        K y[E];
+#pragma unroll
+        for (int r = 0; r < E; ++r) y[r] = shfl_xor_key(x[E - 1 - r], LM);
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const K lo = x[r] < y[r] ? x[r] : y[r], hi = x[r] < y[r] ? y[r] : x[r];
+            x[r] = lower ? lo : hi;
+        }
+    }
+    if constexpr (KK >= 4) half_cleaners<K, E, KK / 4>(x, lane);
+}
+
+template <typename K, int E, int KK>
 struct ChunkSort {
-    static __device__ __forceinline__ void run(K (&x)[E], int lane, bool flip) {
-        ChunkSort<K, E, KK / 2>::run(x, lane, flip);
-        bitonic_phase<K, E, KK>(x, lane, flip);
+    static __device__ __forceinline__ void run(K (&x)[E], int lane) {
+        ChunkSort<K, E, KK / 2>::run(x, lane);
+        bitonic_phase<K, E, KK>(x, lane);
     }
 };
 template <typename K, int E>
 struct ChunkSort<K, E, 1> {
-    static __device__ __forceinline__ void run(K (&)[E], int, bool) {}
+    static __device__ __forceinline__ void run(K (&)[E], int) {}
 };
 
-// full sort of the warp's 32*E keys, ascending unless flip
+// ascending sort of the warp's 32*E keys
 template <typename K, int E>
-__device__ __forceinline__ void warp_sort(K (&x)[E], int lane, bool flip) {
-    ChunkSort<K, E, 32 * E>::run(x, lane, flip);
+__device__ __forceinline__ void warp_sort(K (&x)[E], int lane) {
+    ChunkSort<K, E, 32 * E>::run(x, lane);
 }
-// last log2(32*E) stages of a larger merge phase: the warp's chunk is bitonic, direction uniform
+// the strides 16*E .. 1 of a larger merge phase whose wider strides were done in shared memory
 template <typename K, int E>
-__device__ __forceinline__ void warp_merge_tail(K (&x)[E], int lane, bool up) {
-    bitonic_phase<K, E, 32 * E>(x, lane, !up);
+__device__ __forceinline__ void warp_merge_tail(K (&x)[E], int lane) {
+    half_cleaners<K, E, 16 * E>(x, lane);
 }
 
 }  // namespace spada
