@@ -107,9 +107,13 @@ constexpr int EXPAND_UNROLL = 4;  // independent B gathers in flight per lane
 // emit(seq, col, a_val, b_val): the B column id (and value when NUMERIC) are already loaded.  The loads
 // of EXPAND_UNROLL consecutive steps are issued back to back before any of them is consumed, so a
 // warp keeps several HBM/L2 round trips in flight instead of one.
-template <bool NUMERIC, bool BIG, bool LOAD_COL = true, typename F>
-__device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, int64_t p, int64_t a_end,
-                                             int lane, int seq_base, int& batch_total, F&& emit) {
+// expand_batch_long: B rows of at least `long_len` elements are taken out of the dealt stream and handed,
+// one at a time and warp-uniformly, to on_long(b_row_start, length, a_val) -- the TMA-staged path of the
+// huge bin hooks in here.
+template <bool NUMERIC, bool BIG, bool LOAD_COL, typename F, typename L>
+__device__ __forceinline__ void expand_batch_long(const DevCsr& a, const DevCsr& b, int64_t p, int64_t a_end,
+                                                  int lane, int seq_base, int& batch_total, int long_len, F&& emit,
+                                                  L&& on_long) {
     int64_t bs = 0;
     int len = 0;
     double av = 0.0;
@@ -122,8 +126,8 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
     int big_len = 0;
     unsigned big = 0;
     if (BIG) {
-        big = __ballot_sync(FULL, len > EXPAND_BIG_LEN);
-        if (len > EXPAND_BIG_LEN) {
+        big = __ballot_sync(FULL, len >= long_len);
+        if (len >= long_len) {
             big_len = len;
             len = 0;
         }
@@ -194,10 +198,49 @@ __device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, i
             int lj = __shfl_sync(FULL, big_len, j);
             double aj = 0.0;
             if (NUMERIC) aj = shfl_f64(av, j);
-            for (int t = lane; t < lj; t += 32)
-                emit(-1, LOAD_COL ? (uint32_t)ldg_i32(b.col + bsj + t) : 0u, aj, NUMERIC ? ldg_f64(b.val + bsj + t) : 0.0);
+            on_long(bsj, lj, aj);
         }
     }
+}
+
+template <bool NUMERIC, bool BIG, bool LOAD_COL = true, typename F>
+__device__ __forceinline__ void expand_batch(const DevCsr& a, const DevCsr& b, int64_t p, int64_t a_end,
+                                             int lane, int seq_base, int& batch_total, F&& emit) {
+    expand_batch_long<NUMERIC, BIG, LOAD_COL>(a, b, p, a_end, lane, seq_base, batch_total, EXPAND_BIG_LEN + 1, emit,
+                                              [&](int64_t bsj, int lj, double aj) {
+                                                  for (int t = lane; t < lj; t += 32)
+                                                      emit(-1, LOAD_COL ? (uint32_t)ldg_i32(b.col + bsj + t) : 0u, aj,
+                                                           NUMERIC ? ldg_f64(b.val + bsj + t) : 0.0);
+                                              });
+}
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier, 1-D, global -> shared -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 #endif
 

@@ -25,6 +25,42 @@ namespace spada {
 constexpr int HEAVY_THREADS = 256;
 constexpr int HEAVY_WARPS = HEAVY_THREADS / 32;
 constexpr uint32_t HEAVY_ITEM_PRODUCTS = 8192;
+constexpr int TMA_MIN_LEN = 64;   // B rows of at least this many elements are staged by TMA bulk copies
+constexpr int TMA_STAGE = 256;    // elements per staging buffer (1 KB of column ids + 2 KB of values per warp)
+
+// Streams one long B row through the warp's shared-memory staging buffer with cp.async.bulk:
+// lane 0 arms the warp's mbarrier with the byte count and issues the bulk copies (16-byte aligned
+// windows of the row, over-fetching at most 3 elements on either side), all lanes wait on the
+// barrier phase and consume the window.  use(col, b_val) is called per element of the row.
+template <bool NUMERIC, typename U>
+__device__ __forceinline__ void stream_row_tma(const DevCsr& b, int64_t bs, int len, int lane, uint32_t* st_col,
+                                               double* st_val, uint64_t* bar, uint32_t& phase, U&& use) {
+    const int64_t row_end = bs + len;
+    int64_t e0 = bs;
+    while (e0 < row_end) {
+        const int64_t start_al = e0 & ~(int64_t)3;
+        int64_t end_al = (row_end + 3) & ~(int64_t)3;
+        if (end_al - start_al > TMA_STAGE) end_al = start_al + TMA_STAGE;
+        const int64_t stop = end_al < row_end ? end_al : row_end;
+        if (end_al <= b.nnz) {
+            const uint32_t n_al = (uint32_t)(end_al - start_al);
+            if (lane == 0) {
+                mbar_expect_tx(bar, n_al * (NUMERIC ? 12u : 4u));
+                tma_load_1d(st_col, b.col + start_al, n_al * 4u, bar);
+                if (NUMERIC) tma_load_1d(st_val, b.val + start_al, n_al * 8u, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            for (int64_t e = e0 + lane; e < stop; e += 32) use(st_col[e - start_al], NUMERIC ? st_val[e - start_al] : 0.0);
+            __syncwarp();
+        } else {
+            // the aligned window would run past the end of B's arrays: plain loads for the tail
+            for (int64_t e = e0 + lane; e < stop; e += 32)
+                use((uint32_t)ldg_i32(b.col + e), NUMERIC ? ldg_f64(b.val + e) : 0.0);
+        }
+        e0 = stop;
+    }
+}
 
 __host__ __device__ inline uint32_t heavy_words(int64_t b_cols) { return (uint32_t)((b_cols + 31) / 32); }
 
@@ -84,7 +120,14 @@ __global__ void __launch_bounds__(HEAVY_THREADS)
 k_heavy_bits(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list,
              const uint32_t* __restrict__ flops, const int64_t* __restrict__ item_off,
              const uint32_t* __restrict__ item_row, uint32_t wave_lo, uint32_t wave_hi, uint2* ws, uint32_t words) {
+    __shared__ __align__(16) uint32_t s_col[HEAVY_WARPS][TMA_STAGE];
+    __shared__ uint64_t s_bar[HEAVY_WARPS];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (lane == 0) mbar_init(&s_bar[warp], 1);
+    __syncwarp();
+    uint32_t phase = 0;
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(b.col) & 15) == 0;
+    const int long_len = tma_ok ? TMA_MIN_LEN : EXPAND_BIG_LEN + 1;
     const int64_t it_end = item_off[wave_hi];
     for (int64_t it = item_off[wave_lo] + blockIdx.x; it < it_end; it += gridDim.x) {
         ItemRange R = item_range(a, row_begin, rows_list, flops, item_off, item_row, it);
@@ -94,10 +137,19 @@ k_heavy_bits(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__
         // that are already set need no atomic at all (the OR is idempotent).
         for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
             int bt;
-            expand_batch<false, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, uint32_t c, double, double) {
+            auto set_bit = [&](uint32_t c) {
                 uint32_t bit = 1u << (c & 31);
                 if (!(__ldcg(&w[c >> 5].x) & bit)) atomicOr(&w[c >> 5].x, bit);
-            });
+            };
+            expand_batch_long<false, true, true>(
+                a, b, pb + lane, R.a1, lane, 0, bt, long_len, [&](int, uint32_t c, double, double) { set_bit(c); },
+                [&](int64_t bsj, int lj, double) {
+                    if (tma_ok)
+                        stream_row_tma<false>(b, bsj, lj, lane, s_col[warp], nullptr, &s_bar[warp], phase,
+                                              [&](uint32_t c, double) { set_bit(c); });
+                    else
+                        for (int t = lane; t < lj; t += 32) set_bit((uint32_t)ldg_i32(b.col + bsj + t));
+                });
         }
     }
 }
@@ -164,7 +216,15 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
               const uint32_t* __restrict__ flops, const int64_t* __restrict__ item_off,
               const uint32_t* __restrict__ item_row, uint32_t wave_lo, uint32_t wave_hi, const uint2* ws,
               uint32_t words, const int64_t* __restrict__ c_ptr, double* __restrict__ c_val) {
+    __shared__ __align__(16) uint32_t s_col[HEAVY_WARPS][TMA_STAGE];
+    __shared__ __align__(16) double s_val[HEAVY_WARPS][TMA_STAGE];
+    __shared__ uint64_t s_bar[HEAVY_WARPS];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (lane == 0) mbar_init(&s_bar[warp], 1);
+    __syncwarp();
+    uint32_t phase = 0;
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(b.col) | reinterpret_cast<uintptr_t>(b.val)) & 15) == 0;
+    const int long_len = tma_ok ? TMA_MIN_LEN : EXPAND_BIG_LEN + 1;
     const int64_t it_end = item_off[wave_hi];
     for (int64_t it = item_off[wave_lo] + blockIdx.x; it < it_end; it += gridDim.x) {
         ItemRange R = item_range(a, row_begin, rows_list, flops, item_off, item_row, it);
@@ -177,8 +237,7 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
         bool pend = false;
         for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
             int bt;
-            expand_batch<true, true>(a, b, pb + lane, R.a1, lane, 0, bt, [&](int, uint32_t c, double av, double bv) {
-                double prod = __dmul_rn(av, bv);
+            auto add = [&](uint32_t c, double prod) {
                 uint2 e = __ldcg(&w[c >> 5]);
                 uint32_t pos = e.y + __popc(e.x & ((1u << (c & 31)) - 1u));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(out + pos));
@@ -186,7 +245,18 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
                 pend = true;
                 pend_pos = pos;
                 pend_v = prod;
-            });
+            };
+            expand_batch_long<true, true, true>(
+                a, b, pb + lane, R.a1, lane, 0, bt, long_len,
+                [&](int, uint32_t c, double av, double bv) { add(c, __dmul_rn(av, bv)); },
+                [&](int64_t bsj, int lj, double aj) {
+                    if (tma_ok)
+                        stream_row_tma<true>(b, bsj, lj, lane, s_col[warp], s_val[warp], &s_bar[warp], phase,
+                                             [&](uint32_t c, double bv) { add(c, __dmul_rn(aj, bv)); });
+                    else
+                        for (int t = lane; t < lj; t += 32)
+                            add((uint32_t)ldg_i32(b.col + bsj + t), __dmul_rn(aj, ldg_f64(b.val + bsj + t)));
+                });
         }
         if (pend) atomicAdd(out + pend_pos, pend_v);
     }

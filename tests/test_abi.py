@@ -63,3 +63,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".rs")):
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "liboracle" not in text and "import oracle" not in text and "oracle_spgemm" not in text, f
+
+
+def test_sass_is_sm100a_and_uses_bulk_copies(spada):
+    """The library is built for sm_100a only, and the long-B-row staging really compiles to TMA
+    bulk copies (SASS UBLKCP + mbarrier SYNCS), see csrc/heavy.cu stream_row_tma."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([cuobjdump, "-lelf", spada._abi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", elf))
+    assert archs == {"100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "k_heavy_accum", spada._abi.LIB_PATH], capture_output=True,
+                          text=True).stdout
+    if "UBLKCP" not in sass:   # older cuobjdump: -fun needs the mangled name; fall back to the whole file
+        sass = subprocess.run([cuobjdump, "-sass", spada._abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS.ARRIVE.TRANS64" in sass
