@@ -750,6 +750,16 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     }
 
     // huge rows: cut into items, bitmaps for one wave of rows at a time
+    // The shared-memory bitmap of the heavy bin covers 2^20 columns per pass; for wider B the heavy rows
+    // join the huge rows on the item path (measured on R-MAT, n = 2^21: two passes per row lose to it).
+    const bool heavy_in_smem = B.cols <= (1ll << 20);
+    if (!heavy_in_smem) {   // bins 9 and 10 are adjacent in perm[]: one combined list
+        pc.bin_rows[BIN_HUGE] += pc.bin_rows[BIN_HEAVY];
+        pc.bin_products[BIN_HUGE] += pc.bin_products[BIN_HEAVY];
+        perm_of_bin[BIN_HUGE] = perm_of_bin[BIN_HEAVY];
+        pc.bin_rows[BIN_HEAVY] = 0;
+        pc.bin_products[BIN_HEAVY] = 0;
+    }
     HeavyPlan HP{};
     const uint32_t n_heavy = pc.bin_rows[BIN_HUGE];
     if (n_heavy) {
