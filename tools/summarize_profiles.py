@@ -59,7 +59,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size"]
 out = [f"# {TAG} -- `ncu --set full --clock-control none --import-source on` summaries\n"]
-for rep, wl in (("prof_rect_numeric", "rect"), ("prof_er_fused", "er"), ("prof_poisson_tiny", "poisson")):
+for rep, wl in (("prof_rect_numeric", "rect"), ("prof_er_fused", "er"), ("prof_poisson_tiny", "poisson")):  # noqa
     p = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(p): continue
     recs, units = ncu_raw(p)
