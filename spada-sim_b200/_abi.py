@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspada_b200.so")
+# SPADA_B200_LIB lets a tuning run load an alternative build of the same library (never a different backend)
+LIB_PATH = os.environ.get("SPADA_B200_LIB") or os.path.join(_HERE, "lib", "libspada_b200.so")
 
 MAX_BINS = 16
 MAX_LAUNCHES = 48

@@ -103,7 +103,10 @@ __device__ __forceinline__ int64_t ldg_i64(const int64_t* p) { return __ldg(p); 
 // BIG: B rows longer than 2^24 are streamed one at a time by the whole warp (keeps the 32-bit
 // scan from overflowing); their seq is unused.
 constexpr int EXPAND_BIG_LEN = 1 << 24;
-constexpr int EXPAND_UNROLL = 4;  // independent B gathers in flight per lane
+#ifndef SPADA_EXPAND_UNROLL
+#define SPADA_EXPAND_UNROLL 2
+#endif
+constexpr int EXPAND_UNROLL = SPADA_EXPAND_UNROLL;  // independent B gathers in flight per lane
 // emit(seq, col, a_val, b_val): the B column id (and value when NUMERIC) are already loaded.  The loads
 // of EXPAND_UNROLL consecutive steps are issued back to back before any of them is consumed, so a
 // warp keeps several HBM/L2 round trips in flight instead of one.

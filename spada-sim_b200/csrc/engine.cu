@@ -270,6 +270,16 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
         h->opts.flags = SPADA_B200_FLAG_VALIDATE;
     }
     if (h->opts.lane_num == 0) h->opts.lane_num = 8;
+    // The accelerator argument of the reference CLI selects the window policy (main.rs:67-72,
+    // scheduler.rs:729-753); it never changes C.  Ip = row-wise [1, L]: every row its own group ->
+    // separate passes; Op = column-wise [L, 1] and MultiRow with R > 1: rows share a tile -> single
+    // pass; Spada = adaptive (the engine decides per operand).  Explicit flags win.
+    if (!(h->opts.flags & (SPADA_B200_FLAG_TWO_PHASE | SPADA_B200_FLAG_SINGLE_PASS))) {
+        if (h->opts.accelerator == SPADA_B200_ACC_IP) h->opts.flags |= SPADA_B200_FLAG_TWO_PHASE;
+        else if (h->opts.accelerator == SPADA_B200_ACC_OP) h->opts.flags |= SPADA_B200_FLAG_SINGLE_PASS;
+        else if (h->opts.accelerator == SPADA_B200_ACC_MULTIROW)
+            h->opts.flags |= h->opts.block_shape[0] > 1 ? SPADA_B200_FLAG_SINGLE_PASS : SPADA_B200_FLAG_TWO_PHASE;
+    }
     if (h->opts.device < 0) {
         CU(cudaGetDevice(&h->device));
     } else {

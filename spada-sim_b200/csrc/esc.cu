@@ -20,7 +20,10 @@
 
 namespace spada {
 
-constexpr int ESC_WARPS = 4;          // rows per CTA in the warp-per-row bins
+#ifndef SPADA_ESC_WARPS
+#define SPADA_ESC_WARPS 4
+#endif
+constexpr int ESC_WARPS = SPADA_ESC_WARPS;  // rows per CTA in the warp-per-row bins
 
 // =============================================================================================
 // warp-per-row kernels, N = 32 * E products at most

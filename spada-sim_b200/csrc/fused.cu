@@ -24,7 +24,10 @@
 namespace spada {
 
 constexpr int FUSED_WARPS = 8;  // warps per tile of the tiny-row kernel
-constexpr int LIGHT_WARPS = 4;  // warps per tile of the general kernel; each warp owns RPW consecutive rows
+#ifndef SPADA_LIGHT_WARPS
+#define SPADA_LIGHT_WARPS 4
+#endif
+constexpr int LIGHT_WARPS = SPADA_LIGHT_WARPS;  // warps per tile of the general kernel; each warp owns RPW consecutive rows
 
 #define FST_AGG (1ull << 62)
 #define FST_PREFIX (2ull << 62)

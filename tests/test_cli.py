@@ -74,9 +74,10 @@ def test_rust_binding_lists_every_abi_symbol():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["-p"]])
-def test_cli_cari_transcript(workdir, oracle, cari, spada, extra):
-    p = run_cli(workdir, "accuratesimu", "spada", "ss", "cari", "config/config_1mb_row1.json", *extra)
+@pytest.mark.parametrize("acc,extra", [("spada", []), ("spada", ["-p"]), ("ip", []), ("op", []), ("MultiRow", [])])
+def test_cli_cari_transcript(workdir, oracle, cari, spada, acc, extra):
+    # the accelerator picks the window policy (rows per tile), never the result
+    p = run_cli(workdir, "accuratesimu", acc, "ss", "cari", "config/config_1mb_row1.json", *extra)
     assert p.returncode == 0, p.stderr
     assert p.stdout.startswith(HEAD)
     tail = p.stdout[len(HEAD):].splitlines()

@@ -277,3 +277,16 @@ def test_rect_full_size_properties(engine, spada):
         if e > s:
             j = ix[s + (e - s) // 2]
             assert abs(c[i, j] - c[j, i]) <= 1e-12 * abs(c[i, j])
+
+
+@pytest.mark.parametrize("acc", ["ip", "op", "multirow", "spada"])
+def test_accelerator_policies_do_not_change_c(spada, oracle, acc):
+    # frontend.rs:33-41 / scheduler.rs:729-753: the accelerator only picks the window shape
+    if spada.device_count() == 0:
+        pytest.skip("no CUDA device")
+    a, b = spada.workloads.build("er", 1 / 256)
+    e = spada.Engine(accelerator=acc, block_shape=(4, 2))
+    try:
+        check(e.spgemm(a, b), oracle.spgemm(a, b, threads=oracle.max_threads()), True)
+    finally:
+        e.close()
