@@ -67,22 +67,83 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: an in-process NVML thread
+    (pynvml, 10 ms period -- a 0.3 s timed region still gets ~30 samples); `nvidia-smi -lms` as the
+    fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.samples = []          # (wall time, sm MHz, reasons bitmask)
+        self.smmax = None
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.p = None
+        self.f = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+            self._start_smi(index)
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.time(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _start_smi(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu=timestamp,{self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            time.sleep(1.0)   # nvidia-smi needs a moment before its first sample
         except OSError:
-            pass
+            self.p = None
 
     def stop(self, t0, t1):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv = self.nv
+            names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            win = [x for x in self.samples if t0 <= x[0] <= t1] or [x for x in self.samples if t0 - 0.05 <= x[0] <= t1 + 0.05]
+            reasons = set()
+            for _, _, rs in win:
+                for n_, bit in names.items():
+                    if rs & bit:
+                        reasons.add(n_)
+            if win:
+                out.update(sm_mhz=statistics.median(x[1] for x in win), sm_max_mhz=self.smmax, reasons=sorted(reasons),
+                           samples=len(win), source="nvml")
+            try:
+                nv.nvmlShutdown()
+            except Exception:
+                pass
+            return out
         if self.p is None:
             return out
         time.sleep(0.15)
@@ -101,8 +162,7 @@ class ClockSampler:
                 continue
             try:
                 ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                in_win = (t0 - 0.05) <= ts <= (t1 + 0.05)
-                if not in_win:
+                if not ((t0 - 0.05) <= ts <= (t1 + 0.05)):
                     continue
                 sm.append(float(r[1])); smmax = float(r[2])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -111,7 +171,8 @@ class ClockSampler:
             except ValueError:
                 continue
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=smmax, reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=smmax, reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi")
         return out
 
 

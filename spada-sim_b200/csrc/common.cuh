@@ -253,9 +253,9 @@ void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t row_begin, int6
                   uint32_t* flops, uint32_t* long_list, PlanCounters* ctr, cudaStream_t s);
 void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, uint32_t* perm,
                         PlanCounters* ctr, cudaStream_t s);
-void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t* out, cudaStream_t s);
-void launch_copy_rows(const uint32_t* flops, int64_t m, const int64_t* t_ptr, const int32_t* t_col, const double* t_val,
-                      const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t limit, uint32_t* out, cudaStream_t s);
+void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const int64_t* t_ptr, const int32_t* t_col,
+                      const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
 // stage 4
 void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out /* n+1 */, uint64_t* tile_state,
                          PlanCounters* ctr, cudaStream_t s);
@@ -324,6 +324,18 @@ void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int6
 void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                                 uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
                                 uint32_t* row_nnz_out = nullptr);
+// bucketed rows (bucket.cu): bins 6..9 in one pass per row (scratch mode); ovf = {count, rows...} collects the rows
+// whose columns are too skewed for the buckets, the two fallback launchers recompute them
+bool bucket_supported(int64_t b_cols);
+void launch_bucket_rows(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm, uint32_t rows,
+                        const uint32_t* flops, const int64_t* c_ptr, int32_t* c_col, double* c_val,
+                        uint32_t* row_nnz_out, uint32_t* ovf, cudaStream_t s);
+void launch_bucket_fallback(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
+                            const uint32_t* ovf, uint32_t max_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val,
+                            uint32_t* row_nnz_out, cudaStream_t s);
+void launch_heavy_smem_list(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
+                            const uint32_t* ovf, uint32_t max_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val,
+                            uint32_t* row_nnz_out, cudaStream_t s);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
 void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,

@@ -55,6 +55,13 @@ struct spada_b200 {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // Side streams: the CTA-per-row sort bins and the heavy/huge bins are independent of the warp-per-row
+    // bins until the row_ptr scan, and latency bound where the others are issue/bandwidth bound; they run
+    // concurrently and are joined back into `stream` by events (SPADA_B200_STREAMS=1 serialises them).
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int n_streams = 2;
+    uint32_t bucket_bins = 0x3c0;  // bins (bit b) whose rows go through the bucketed kernel in scratch mode: 6..9
     spada_b200_opts opts{};
     PlanCounters* d_ctr = nullptr;
     PlanCounters* h_ctr = nullptr;  // pinned
@@ -156,14 +163,14 @@ void dfree(spada_b200* h, T* p) {
     pool_free(h, (void*)p);
 }
 
-cudaEvent_t next_event(spada_b200* h) {
+cudaEvent_t next_event(spada_b200* h, cudaStream_t on = nullptr) {
     if (h->ev_used == h->events.size()) {
         cudaEvent_t e;
         cudaEventCreate(&e);
         h->events.push_back(e);
     }
     cudaEvent_t e = h->events[h->ev_used++];
-    cudaEventRecord(e, h->stream);
+    cudaEventRecord(e, on ? on : h->stream);
     return e;
 }
 
@@ -307,6 +314,20 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
     }
+    {
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, hi_prio));
+            CU(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        if (const char* e = getenv("SPADA_B200_BUCKET_BINS")) h->bucket_bins = (uint32_t)strtoul(e, nullptr, 0) & 0x3c0u;
+        if (const char* e = getenv("SPADA_B200_STREAMS")) {
+            int v = atoi(e);
+            if (v >= 1 && v <= 3) h->n_streams = v;
+        }
+    }
     CU(cudaMalloc((void**)&h->d_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_scalar, 64));
@@ -328,6 +349,14 @@ extern "C" void spada_b200_destroy(spada_b200_t* h) {
     pool_release_cached(h);
     for (auto& kv : h->pool_live) cudaFree(kv.first);  // objects the caller never freed
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (h->side[i]) {
+            cudaStreamSynchronize(h->side[i]);
+            cudaStreamDestroy(h->side[i]);
+        }
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     cudaFree(h->d_ctr);
     cudaFreeHost(h->h_ctr);
     cudaFreeHost(h->h_scalar);
@@ -587,17 +616,41 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
 
     h->ev_used = 0;
     std::vector<LaunchRec> recs;
-    auto begin_rec = [&](const char* name, int stage, uint32_t grid, uint64_t rows, uint64_t products) {
+    cudaStream_t rec_stream = s;
+    auto begin_rec = [&](const char* name, int stage, uint32_t grid, uint64_t rows, uint64_t products,
+                         cudaStream_t on = nullptr) {
         LaunchRec r{};
         snprintf(r.name, sizeof(r.name), "%s", name);
         r.stage = stage;
         r.grid = grid;
         r.rows = rows;
         r.products = products;
-        r.e0 = next_event(h);
+        rec_stream = on ? on : s;
+        r.e0 = next_event(h, rec_stream);
         recs.push_back(r);
     };
-    auto end_rec = [&]() { recs.back().e1 = next_event(h); };
+    auto end_rec = [&]() { recs.back().e1 = next_event(h, rec_stream); };
+    // side streams: sc = CTA-per-row sort bins, sh = heavy + huge bins (both = s when serialised)
+    cudaStream_t sc = h->n_streams >= 3 ? h->side[0] : s;
+    cudaStream_t sh = h->n_streams >= 2 ? h->side[1] : s;
+    bool forked = false;
+    auto fork = [&]() -> cudaError_t {   // side streams wait for everything enqueued on s so far
+        cudaError_t e = cudaEventRecord(h->ev_fork, s);
+        if (e == cudaSuccess && sc != s) e = cudaStreamWaitEvent(sc, h->ev_fork, 0);
+        if (e == cudaSuccess && sh != s) e = cudaStreamWaitEvent(sh, h->ev_fork, 0);
+        forked = true;
+        return e;
+    };
+    auto join = [&]() -> cudaError_t {   // s waits for both side streams
+        cudaError_t e = cudaSuccess;
+        cudaStream_t sides[2] = {sc, sh};
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            if (sides[i] == s) continue;
+            e = cudaEventRecord(h->ev_join[i], sides[i]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, h->ev_join[i], 0);
+        }
+        return e;
+    };
 
     uint32_t *d_flops = nullptr, *d_long = nullptr, *d_perm = nullptr, *d_nnz = nullptr;
     uint64_t* d_tiles = nullptr;
@@ -606,10 +659,15 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     int64_t *d_item_off = nullptr, *d_prod_ptr = nullptr;
     void* d_kstore = nullptr;
     uint32_t* d_masked = nullptr;
+    uint32_t* d_ovf = nullptr;
     int32_t* d_tcol = nullptr;
     double* d_tval = nullptr;
     uint32_t kernels = 0;
     auto cleanup = [&]() {
+        if (forked) {   // error paths: nothing may still run on a side stream when blocks go back to the pool
+            if (sc != s) cudaStreamSynchronize(sc);
+            if (sh != s) cudaStreamSynchronize(sh);
+        }
         dfree(h, d_flops);
         dfree(h, d_long);
         dfree(h, d_perm);
@@ -622,6 +680,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         dfree(h, d_prod_ptr);
         dfree(h, (char*)d_kstore);
         dfree(h, d_masked);
+        dfree(h, d_ovf);
         dfree(h, d_tcol);
         dfree(h, d_tval);
     };
@@ -723,8 +782,18 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     // laid out by product count; after the scan they are copied to their place -- one expansion, one sort.
     uint64_t sorted_products = 0;
     for (int bnum = 1; bnum <= 8; ++bnum) sorted_products += pc.bin_products[bnum];
+    // rows of bins 6..9 can take the bucketed kernel (bucket.cu) when the key layout covers B's width
+    const uint32_t bucket_bins = bucket_supported(B.cols) ? h->bucket_bins : 0u;
+    const bool heavy_bucket = !fused && h->two_phase_mode == 2 && (bucket_bins >> BIN_HEAVY & 1u) && pc.bin_rows[BIN_HEAVY] > 0;
+    if (heavy_bucket) sorted_products += pc.bin_products[BIN_HEAVY];
+    const uint32_t scratch_limit = heavy_bucket ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS;
     const bool scratch = !fused && h->two_phase_mode == 2 && sorted_products > 0 &&
                          (double)sorted_products * 12.0 <= 0.30 * (double)h->dev_total_mem;
+    const bool heavy_by_bucket = scratch && heavy_bucket;
+    uint32_t ovf_cap = 0;   // rows that may land on the bucket kernel's overflow list
+    if (scratch)
+        for (int bnum = 6; bnum <= BIN_HEAVY; ++bnum)
+            if (bucket_bins >> bnum & 1u) ovf_cap += pc.bin_rows[bnum];
     if (!fused && !scratch && h->two_phase_mode >= 1) {
         uint64_t sorted_rows = 0;
         for (int bnum = 1; bnum <= 8; ++bnum) {
@@ -752,18 +821,22 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         TRY(dalloc(h, &d_tcol, (size_t)sorted_products));
         TRY(dalloc(h, &d_tval, (size_t)sorted_products));
         begin_rec("scratch_ptr", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
-        launch_mask_sorted(d_flops, m, d_masked, s);
+        launch_mask_sorted(d_flops, m, heavy_by_bucket ? scratch_limit : ESC_MAX_PRODUCTS, d_masked, s);
         launch_scan_u32_i64(d_masked, m, d_prod_ptr, d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
         kernels += 2;
         end_rec();
+        if (ovf_cap) {
+            TRY(dalloc(h, &d_ovf, (size_t)ovf_cap + 1));
+            CUT(cudaMemsetAsync(d_ovf, 0, sizeof(uint32_t), s));
+        }
     }
 
     // huge rows: cut into items, bitmaps for one wave of rows at a time
     // The shared-memory bitmap of the heavy bin covers 2^20 columns per pass; for wider B the heavy rows
     // join the huge rows on the item path (measured on R-MAT, n = 2^21: two passes per row lose to it).
     const bool heavy_in_smem = B.cols <= (1ll << 20);
-    if (!heavy_in_smem) {   // bins 9 and 10 are adjacent in perm[]: one combined list
+    if (!heavy_in_smem && !heavy_by_bucket) {   // bins 9 and 10 are adjacent in perm[]: one combined list
         pc.bin_rows[BIN_HUGE] += pc.bin_rows[BIN_HEAVY];
         pc.bin_products[BIN_HUGE] += pc.bin_products[BIN_HEAVY];
         perm_of_bin[BIN_HUGE] = perm_of_bin[BIN_HEAVY];
@@ -787,51 +860,70 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     }
 
     // ---- stage 2: symbolic ------------------------------------------------------------------
+    CUT(fork());
     for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
         uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
         char name[32];
         snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
-        if (bnum == BIN_HEAVY) {
-            begin_rec(name, 2, rows, rows, pc.bin_products[bnum]);
-            launch_heavy_smem_symbolic(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
+        cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);   // the stream of this bin
+        if (scratch && bnum >= 6 && bnum <= BIN_HEAVY && (bucket_bins >> bnum & 1u) && (bnum < BIN_HEAVY || heavy_by_bucket)) {
+            snprintf(name, sizeof(name), "bucket_pass<%s>", bin_name(bnum));
+            begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
+            launch_bucket_rows(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_flops, d_prod_ptr, d_tcol, d_tval,
+                               d_nnz, d_ovf, sb);
+            kernels += 1;
+        } else if (bnum == BIN_HEAVY) {
+            begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
+            launch_heavy_smem_symbolic(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, sb);
             kernels += 1;
         } else if (bnum == BIN_HUGE) {
             const uint32_t* hl = perm_of_bin[bnum];
             const bool detail = HP.n_waves == 1;  // per-kernel records for a single wave, one record otherwise
-            if (!detail) begin_rec(name, 2, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum]);
+            if (!detail) begin_rec(name, 2, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum], sb);
             for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
                 uint32_t hi = std::min(rows, lo + HP.wave_rows);
-                if (detail) begin_rec("sym_huge_clear", 2, 0, hi - lo, 0);
-                CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), s));
+                if (detail) begin_rec("sym_huge_clear", 2, 0, hi - lo, 0, sb);
+                CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), sb));
                 if (detail) end_rec();
-                if (detail) begin_rec("sym_huge_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                if (detail) begin_rec("sym_huge_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum], sb);
                 launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
-                                  h->sm_count, s);
+                                  h->sm_count, sb);
                 if (detail) end_rec();
-                if (detail) begin_rec("sym_huge_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum]);
-                launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, s);
+                if (detail) begin_rec("sym_huge_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum], sb);
+                launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, sb);
                 kernels += 2;
             }
         } else if (scratch) {
             snprintf(name, sizeof(name), "sort_pass<%s>", bin_name(bnum));
-            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
-            launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_prod_ptr, d_tcol, d_tval, s,
+            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum], sb);
+            launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_prod_ptr, d_tcol, d_tval, sb,
                                d_nnz);
             kernels += 1;
         } else {
-            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
+            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum], sb);
             if (keep_keys && bnum <= 5)
                 launch_esc_symbolic_keep(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz,
-                                         d_prod_ptr, d_kstore, s);
+                                         d_prod_ptr, d_kstore, sb);
             else if (keep_keys && bnum <= 8)
                 launch_cta_symbolic_keep(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz,
-                                         d_prod_ptr, d_kstore, s);
+                                         d_prod_ptr, d_kstore, sb);
             else
-                launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, s);
+                launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, sb);
             kernels += 1;
         }
         CUT(cudaGetLastError());
+        end_rec();
+    }
+    CUT(join());
+    if (ovf_cap) {   // rows the buckets could not take (skewed columns): usually none, two near-empty launches
+        begin_rec("bucket_fallback", 2, 0, 0, 0);
+        launch_bucket_fallback(A, B, (int64_t)row_begin, d_flops, d_ovf, ovf_cap, d_prod_ptr, d_tcol, d_tval, d_nnz, s);
+        if (heavy_by_bucket)
+            launch_heavy_smem_list(A, B, (int64_t)row_begin, d_flops, d_ovf, pc.bin_rows[BIN_HEAVY], d_prod_ptr, d_tcol,
+                                   d_tval, d_nnz, s);
+        CUT(cudaGetLastError());
+        kernels += heavy_by_bucket ? 2 : 1;
         end_rec();
     }
 
@@ -866,9 +958,11 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     }
 
     // ---- stage 3: numeric -------------------------------------------------------------------
+    CUT(fork());
     if (scratch) {
         begin_rec("copy_rows", 3, (uint32_t)((m + 7) / 8), (uint64_t)m, sorted_products);
-        launch_copy_rows(d_flops, m, d_prod_ptr, d_tcol, d_tval, R->ptr, R->col, R->val, s);
+        launch_copy_rows(d_flops, m, heavy_by_bucket ? scratch_limit : ESC_MAX_PRODUCTS, d_prod_ptr, d_tcol, d_tval,
+                         R->ptr, R->col, R->val, s);
         CUT(cudaGetLastError());
         kernels += 1;
         end_rec();
@@ -876,49 +970,53 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
         uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
-        if (scratch && bnum <= 8) continue;
+        if (scratch && (bnum <= 8 || (bnum == BIN_HEAVY && heavy_by_bucket))) continue;
         char name[32];
         snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
+        cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);
         if (bnum == BIN_HEAVY) {
-            begin_rec(name, 3, rows, rows, pc.bin_products[bnum]);
-            launch_heavy_smem_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
+            begin_rec(name, 3, rows, rows, pc.bin_products[bnum], sb);
+            launch_heavy_smem_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, sb);
             kernels += 1;
         } else if (bnum == BIN_HUGE) {
             const uint32_t* hl = perm_of_bin[bnum];
             const bool ws_valid = HP.n_waves == 1;  // bitmaps + ranks of the symbolic stage are still resident
-            if (!ws_valid) begin_rec(name, 3, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum]);
+            if (!ws_valid) begin_rec(name, 3, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum], sb);
             for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
                 uint32_t hi = std::min(rows, lo + HP.wave_rows);
                 if (!ws_valid) {
-                    CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), s));
+                    CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), sb));
                     launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws,
-                                      HP, h->sm_count, s);
-                    launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, nullptr, s);
+                                      HP, h->sm_count, sb);
+                    launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, nullptr, sb);
                     kernels += 2;
                 }
-                if (ws_valid) begin_rec("num_huge_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum]);
-                launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, R->ptr, R->col, R->val, s);
+                if (ws_valid) begin_rec("num_huge_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum], sb);
+                launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, R->ptr, R->col, R->val, sb);
                 if (ws_valid) end_rec();
-                if (ws_valid) begin_rec("num_huge_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum]);
+                if (ws_valid) begin_rec("num_huge_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum], sb);
                 launch_heavy_accum(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
-                                   R->ptr, R->val, h->sm_count, s);
+                                   R->ptr, R->val, h->sm_count, sb);
                 kernels += 2;
             }
         } else {
-            begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum]);
+            begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum], sb);
             if (keep_keys && bnum <= 5)
                 launch_esc_numeric_presorted(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr,
-                                             R->col, R->val, d_prod_ptr, d_kstore, s);
+                                             R->col, R->val, d_prod_ptr, d_kstore, sb);
             else if (keep_keys && bnum <= 8)
                 launch_cta_numeric_presorted(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr,
-                                             R->col, R->val, d_prod_ptr, d_kstore, s);
+                                             R->col, R->val, d_prod_ptr, d_kstore, sb);
             else
-                launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, s);
+                launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, sb);
             kernels += 1;
         }
         CUT(cudaGetLastError());
         end_rec();
     }
+    CUT(join());
+    forked = false;
+    cudaEvent_t e_end = next_event(h, s);
     cleanup();
     CUT(cudaStreamSynchronize(s));
     CUT(cudaGetLastError());
@@ -948,7 +1046,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             L.nnz = 0;
         }
     }
-    if (!recs.empty()) cudaEventElapsedTime(&st.ms_total, recs.front().e0, recs.back().e1);
+    if (!recs.empty()) cudaEventElapsedTime(&st.ms_total, recs.front().e0, e_end);
 #undef TRY
 #undef CUT
     *out = R;

@@ -105,18 +105,13 @@ k_heavy_smem_symbolic(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __r
     if (threadIdx.x == 0) row_nnz[r] = nnz;
 }
 
-__global__ void __launch_bounds__(HS_THREADS)
-k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list, uint32_t n_rows,
-                     const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
-    extern __shared__ __align__(16) uint32_t s_u32[];
-    uint32_t* bm = s_u32;
-    uint32_t* coarse = s_u32 + HS_WORDS;
-    __shared__ uint32_t s_warp[HS_WARPS];
-    const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
+// bitmap -> ranks -> column ids -> values of one row; the row's slice of C starts at cbase (its values
+// are zeroed here, range by range, once the ranks are known).  Returns nnz of the row.
+__device__ __forceinline__ uint32_t hs_numeric_row(const DevCsr& a, const DevCsr& b, int64_t row_begin, uint32_t r,
+                                                   int64_t cbase, int32_t* __restrict__ c_col,
+                                                   double* __restrict__ c_val, uint32_t* bm, uint32_t* coarse,
+                                                   uint32_t* s_warp) {
     const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
-    const int64_t cbase = c_ptr[r];
-    const int64_t z = c_ptr[r + 1] - cbase;
-    for (int64_t i = threadIdx.x; i < z; i += HS_THREADS) c_val[cbase + i] = 0.0;
     uint32_t pass_base = 0;  // outputs of the column ranges already done
     for (int64_t c0 = 0; c0 < b.cols; c0 += (int64_t)HS_WORDS * 32) {
         const int64_t c1 = (c0 + (int64_t)HS_WORDS * 32 < b.cols) ? c0 + (int64_t)HS_WORDS * 32 : b.cols;
@@ -140,6 +135,7 @@ k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __re
             if (g < groups) coarse[g] = run + ex;
             run += total;
         }
+        for (uint32_t i = pass_base + threadIdx.x; i < run; i += HS_THREADS) c_val[cbase + i] = 0.0;
         __syncthreads();
         // column ids of this range, in order
         for (uint32_t w = threadIdx.x; w < words; w += HS_THREADS) {
@@ -168,6 +164,34 @@ k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __re
         pass_base = run;
         __syncthreads();
     }
+    return pass_base;
+}
+
+__global__ void __launch_bounds__(HS_THREADS)
+k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list, uint32_t n_rows,
+                     const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+    extern __shared__ __align__(16) uint32_t s_u32[];
+    __shared__ uint32_t s_warp[HS_WARPS];
+    const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
+    hs_numeric_row(a, b, row_begin, r, c_ptr[r], c_col, c_val, s_u32, s_u32 + HS_WORDS, s_warp);
+}
+
+// overflow rows of the bucket kernel with more than 4096 products (device-side list {count, rows...}):
+// computed in one go into a slice of capacity >= nnz (the scratch CSR), nnz recorded
+__global__ void __launch_bounds__(HS_THREADS)
+k_heavy_smem_list(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ flops,
+                  const uint32_t* __restrict__ ovf, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
+                  double* __restrict__ c_val, uint32_t* __restrict__ row_nnz_out) {
+    extern __shared__ __align__(16) uint32_t s_u32[];
+    __shared__ uint32_t s_warp[HS_WARPS];
+    const uint32_t n_rows = ovf[0];
+    for (uint32_t i = blockIdx.x; i < n_rows; i += gridDim.x) {
+        const uint32_t r = ovf[1 + i];
+        if (flops[r] <= ESC_MAX_PRODUCTS) continue;  // launch_bucket_fallback
+        const uint32_t nnz = hs_numeric_row(a, b, row_begin, r, c_ptr[r], c_col, c_val, s_u32, s_u32 + HS_WORDS, s_warp);
+        if (row_nnz_out && threadIdx.x == 0) row_nnz_out[r] = nnz;
+        __syncthreads();
+    }
 }
 
 void launch_heavy_smem_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
@@ -192,6 +216,19 @@ void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_beg
         attr = true;
     }
     k_heavy_smem_numeric<<<n_rows, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, rows_list, n_rows, c_ptr, c_col, c_val);
+}
+
+void launch_heavy_smem_list(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
+                            const uint32_t* ovf, uint32_t max_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val,
+                            uint32_t* row_nnz_out, cudaStream_t s) {
+    if (max_rows == 0) return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_heavy_smem_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM);
+        attr = true;
+    }
+    const unsigned grid = max_rows < 148u ? max_rows : 148u;
+    k_heavy_smem_list<<<grid, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, flops, ovf, c_ptr, c_col, c_val, row_nnz_out);
 }
 
 }  // namespace spada

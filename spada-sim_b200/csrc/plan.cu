@@ -249,27 +249,28 @@ void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out, uint64_t* 
 // Two-phase mode, sort bins: the first pass writes finished rows to a scratch CSR laid out by
 // product count (an upper bound of every row's nnz); after the row_ptr scan they are copied to
 // their final place.  k_mask_sorted yields the per-row scratch sizes, k_copy_rows moves the rows.
-__global__ void k_mask_sorted(const uint32_t* __restrict__ flops, int64_t m, uint32_t* __restrict__ out) {
+__global__ void k_mask_sorted(const uint32_t* __restrict__ flops, int64_t m, uint32_t limit, uint32_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) {
         uint32_t f = flops[i];
-        out[i] = (f <= ESC_MAX_PRODUCTS) ? f : 0u;
+        out[i] = (f <= limit) ? f : 0u;
     }
 }
-void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t* out, cudaStream_t s) {
-    if (m > 0) k_mask_sorted<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(flops, m, out);
+// limit: rows with at most that many products go through the scratch CSR
+void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t limit, uint32_t* out, cudaStream_t s) {
+    if (m > 0) k_mask_sorted<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(flops, m, limit, out);
 }
 
 constexpr int COPY_WARPS = 8;
 __global__ void __launch_bounds__(COPY_WARPS * 32)
-k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, const int64_t* __restrict__ t_ptr,
+k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, uint32_t limit, const int64_t* __restrict__ t_ptr,
             const int32_t* __restrict__ t_col, const double* __restrict__ t_val, const int64_t* __restrict__ c_ptr,
             int32_t* __restrict__ c_col, double* __restrict__ c_val) {
     const int lane = lane_id();
     const int64_t r = (int64_t)blockIdx.x * COPY_WARPS + (threadIdx.x >> 5);
     if (r >= m) return;
     const uint32_t f = flops[r];
-    if (f == 0 || f > ESC_MAX_PRODUCTS) return;  // empty rows have nothing; heavy rows are written by their own kernels
+    if (f == 0 || f > limit) return;  // empty rows have nothing; rows above the limit are written by their own kernels
     const int64_t src = t_ptr[r], dst = c_ptr[r];
     const int n = (int)(c_ptr[r + 1] - dst);
     for (int j = lane; j < n; j += 32) {
@@ -277,11 +278,11 @@ k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, const int64_t* __rest
         c_val[dst + j] = t_val[src + j];
     }
 }
-void launch_copy_rows(const uint32_t* flops, int64_t m, const int64_t* t_ptr, const int32_t* t_col, const double* t_val,
-                      const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const int64_t* t_ptr, const int32_t* t_col,
+                      const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
     if (m > 0)
-        k_copy_rows<<<(unsigned)((m + COPY_WARPS - 1) / COPY_WARPS), COPY_WARPS * 32, 0, s>>>(flops, m, t_ptr, t_col, t_val,
-                                                                                          c_ptr, c_col, c_val);
+        k_copy_rows<<<(unsigned)((m + COPY_WARPS - 1) / COPY_WARPS), COPY_WARPS * 32, 0, s>>>(flops, m, limit, t_ptr, t_col,
+                                                                                          t_val, c_ptr, c_col, c_val);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -188,6 +188,39 @@ def test_high_compression_row(engine, oracle):
     run(engine, oracle, a, b2)
 
 
+def _widen(b, n_cols, shift=0):
+    """Same entries, columns moved by `shift`, in a matrix that is n_cols wide."""
+    return sp.csr_matrix((b.data, b.indices + shift, b.indptr), shape=(b.shape[0], n_cols))
+
+
+@pytest.mark.parametrize("ka,lb,width", [(30, 30, 64), (50, 40, 300), (100, 90, 700), (200, 60, 2000), (90, 80, 1 << 14)])
+def test_skewed_columns_overflow_the_buckets(engine, oracle, ka, lb, width):
+    # bucket.cu cuts B's column space into equal ranges; here every product of a row lands in a narrow
+    # band of a 2^20-wide B, so buckets (or passes) overflow and the rows take the fallback kernels
+    a = random_csr(120, 400, row_nnz=ka, seed=ka + 1)
+    b = _widen(random_csr(400, width, row_nnz=min(lb, width), seed=lb + 2), 1 << 20, shift=(1 << 19) + 77)
+    run(engine, oracle, a, b, exact=(ka * min(lb, width) <= 4096))
+
+
+def test_bucket_rows_mixed_lengths(engine, oracle):
+    # rows of 513 .. ~40000 products side by side: one-pass buckets, multi-pass rows, the odd empty bucket
+    rng = np.random.default_rng(21)
+    lens = rng.choice([0, 30, 70, 130, 260, 520, 900, 2500], size=400, p=[.05, .2, .2, .2, .15, .1, .07, .03])
+    a = random_csr(400, 6000, row_nnz=lens, seed=22)
+    b = random_csr(6000, 1 << 20, row_nnz=rng.integers(10, 26, size=6000), seed=23)
+    r = engine.spgemm(a, b)
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    ip, ix, dx = r.to_host()
+    assert np.array_equal(ip, ref[0]) and np.array_equal(ix, ref[1])
+    f = oracle.flops(a, b)
+    one_pass = np.repeat(f <= 4096, np.diff(ref[0]))
+    assert np.array_equal(dx[one_pass].view(np.uint64), ref[2][one_pass].view(np.uint64))
+    assert (np.abs(dx[~one_pass] - ref[2][~one_pass]) <= TOL * np.abs(ref[2][~one_pass])).all()
+    # tiny column space: more buckets than columns
+    b2 = random_csr(6000, 48, row_nnz=rng.integers(8, 20, size=6000), seed=24)
+    run(engine, oracle, a, b2, exact=False)
+
+
 def test_usize_layout_matches(engine, oracle):
     a = random_csr(300, 200, density=0.05, seed=16)
     b = random_csr(200, 250, density=0.05, seed=17)
