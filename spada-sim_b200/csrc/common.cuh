@@ -249,7 +249,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // ---- launchers (implemented in the .cu files, called by engine.cu) ------------------------
 // stage 1
-void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t row_begin, int64_t m,
+void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t b_rows, uint32_t* b_len, int64_t row_begin, int64_t m,
                   uint32_t* flops, uint32_t* long_list, PlanCounters* ctr, cudaStream_t s);
 void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, uint32_t* perm,
                         PlanCounters* ctr, cudaStream_t s);
@@ -293,8 +293,10 @@ bool esc_needs_wide_keys(int bin, int64_t b_cols);
 // stage 2 / 3, heavy bin (9): one CTA per row, bitmap in shared memory (heavy_smem.cu)
 void launch_heavy_smem_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
                                 uint32_t n_rows, uint32_t* row_nnz, cudaStream_t s);
+// row_nnz_out (nullable): one-shot mode -- c_ptr addresses scratch rows of capacity >= nnz, nnz is recorded
 void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
-                               uint32_t n_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+                               uint32_t n_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                               uint32_t* row_nnz_out = nullptr);
 // stage 2 / 3, huge bin (10): rows are cut into items (~8192 products) spread over the grid (heavy.cu)
 struct HeavyPlan {
     uint32_t words;      // bitmap words per row = ceil(B.cols / 32)

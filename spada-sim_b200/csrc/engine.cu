@@ -61,7 +61,9 @@ struct spada_b200 {
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int n_streams = 2;
-    uint32_t bucket_bins = 0x3c0;  // bins (bit b) whose rows go through the bucketed kernel in scratch mode: 6..9
+    uint32_t bucket_bins = 0;      // bins (bit b, 6..9) whose rows take the bucketed kernel of bucket.cu in scratch mode
+                                   // (SPADA_B200_BUCKET_BINS; off by default: measured slower than the bitonic / bitmap kernels)
+    bool heavy_oneshot = true;     // heavy bin in scratch mode: bitmap + ranks + values in ONE kernel into a scratch row
     spada_b200_opts opts{};
     PlanCounters* d_ctr = nullptr;
     PlanCounters* h_ctr = nullptr;  // pinned
@@ -322,6 +324,7 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
             CU(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        if (const char* e = getenv("SPADA_B200_HEAVY_ONESHOT")) h->heavy_oneshot = atoi(e) != 0;
         if (const char* e = getenv("SPADA_B200_BUCKET_BINS")) h->bucket_bins = (uint32_t)strtoul(e, nullptr, 0) & 0x3c0u;
         if (const char* e = getenv("SPADA_B200_STREAMS")) {
             int v = atoi(e);
@@ -524,7 +527,11 @@ namespace {
 int run_flops(spada_b200* h, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m, uint32_t* d_flops,
               uint32_t* d_long) {
     CU(cudaMemsetAsync(h->d_ctr, 0, sizeof(PlanCounters), h->stream));
-    launch_flops(a, b.ptr, row_begin, m, d_flops, d_long, h->d_ctr, h->stream);
+    uint32_t* d_blen = nullptr;   // lengths of B's rows, 4 B each (freed right away: same-stream reuse is ordered)
+    int rc = dalloc(h, &d_blen, (size_t)std::max<int64_t>(b.rows, 1));
+    if (rc) return rc;
+    launch_flops(a, b.ptr, b.rows, d_blen, row_begin, m, d_flops, d_long, h->d_ctr, h->stream);
+    dfree(h, d_blen);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(PlanCounters), cudaMemcpyDeviceToHost, h->stream));
     return 0;
@@ -721,7 +728,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     TRY(dalloc(h, &d_tiles, std::max(scan_tile_state_words(m), fused_tile_state_words(m))));
     begin_rec("flop_count", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
     TRY(run_flops(h, A, B, (int64_t)row_begin, m, d_flops, d_long));
-    kernels += 2;
+    kernels += 3;
     end_rec();
     CUT(cudaMemsetAsync(d_nnz, 0, (size_t)m * sizeof(uint32_t), s));
     CUT(cudaStreamSynchronize(s));  // host read-back #1: bin sizes
@@ -785,11 +792,16 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     // rows of bins 6..9 can take the bucketed kernel (bucket.cu) when the key layout covers B's width
     const uint32_t bucket_bins = bucket_supported(B.cols) ? h->bucket_bins : 0u;
     const bool heavy_bucket = !fused && h->two_phase_mode == 2 && (bucket_bins >> BIN_HEAVY & 1u) && pc.bin_rows[BIN_HEAVY] > 0;
-    if (heavy_bucket) sorted_products += pc.bin_products[BIN_HEAVY];
-    const uint32_t scratch_limit = heavy_bucket ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS;
+    // heavy bin (shared-memory bitmap, B at most 2^20 columns wide): one kernel per row into a scratch row instead of
+    // a symbolic and a numeric kernel around the scan -- one expansion less, 0.39 ms of 8 on the rect config
+    const bool heavy_oneshot = !fused && h->two_phase_mode == 2 && !heavy_bucket && h->heavy_oneshot &&
+                               B.cols <= (1ll << 20) && pc.bin_rows[BIN_HEAVY] > 0;
+    if (heavy_bucket || heavy_oneshot) sorted_products += pc.bin_products[BIN_HEAVY];
+    const uint32_t scratch_limit = (heavy_bucket || heavy_oneshot) ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS;
     const bool scratch = !fused && h->two_phase_mode == 2 && sorted_products > 0 &&
                          (double)sorted_products * 12.0 <= 0.30 * (double)h->dev_total_mem;
     const bool heavy_by_bucket = scratch && heavy_bucket;
+    const bool heavy_in_scratch = scratch && (heavy_bucket || heavy_oneshot);
     uint32_t ovf_cap = 0;   // rows that may land on the bucket kernel's overflow list
     if (scratch)
         for (int bnum = 6; bnum <= BIN_HEAVY; ++bnum)
@@ -821,7 +833,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         TRY(dalloc(h, &d_tcol, (size_t)sorted_products));
         TRY(dalloc(h, &d_tval, (size_t)sorted_products));
         begin_rec("scratch_ptr", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
-        launch_mask_sorted(d_flops, m, heavy_by_bucket ? scratch_limit : ESC_MAX_PRODUCTS, d_masked, s);
+        launch_mask_sorted(d_flops, m, heavy_in_scratch ? scratch_limit : ESC_MAX_PRODUCTS, d_masked, s);
         launch_scan_u32_i64(d_masked, m, d_prod_ptr, d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
         kernels += 2;
@@ -836,7 +848,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     // The shared-memory bitmap of the heavy bin covers 2^20 columns per pass; for wider B the heavy rows
     // join the huge rows on the item path (measured on R-MAT, n = 2^21: two passes per row lose to it).
     const bool heavy_in_smem = B.cols <= (1ll << 20);
-    if (!heavy_in_smem && !heavy_by_bucket) {   // bins 9 and 10 are adjacent in perm[]: one combined list
+    if (!heavy_in_smem && !heavy_in_scratch) {   // bins 9 and 10 are adjacent in perm[]: one combined list
         pc.bin_rows[BIN_HUGE] += pc.bin_rows[BIN_HEAVY];
         pc.bin_products[BIN_HUGE] += pc.bin_products[BIN_HEAVY];
         perm_of_bin[BIN_HUGE] = perm_of_bin[BIN_HEAVY];
@@ -872,6 +884,12 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
             launch_bucket_rows(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_flops, d_prod_ptr, d_tcol, d_tval,
                                d_nnz, d_ovf, sb);
+            kernels += 1;
+        } else if (bnum == BIN_HEAVY && heavy_in_scratch) {
+            snprintf(name, sizeof(name), "oneshot<%s>", bin_name(bnum));
+            begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
+            launch_heavy_smem_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_prod_ptr, d_tcol, d_tval, sb,
+                                      d_nnz);
             kernels += 1;
         } else if (bnum == BIN_HEAVY) {
             begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
@@ -961,7 +979,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     CUT(fork());
     if (scratch) {
         begin_rec("copy_rows", 3, (uint32_t)((m + 7) / 8), (uint64_t)m, sorted_products);
-        launch_copy_rows(d_flops, m, heavy_by_bucket ? scratch_limit : ESC_MAX_PRODUCTS, d_prod_ptr, d_tcol, d_tval,
+        launch_copy_rows(d_flops, m, heavy_in_scratch ? scratch_limit : ESC_MAX_PRODUCTS, d_prod_ptr, d_tcol, d_tval,
                          R->ptr, R->col, R->val, s);
         CUT(cudaGetLastError());
         kernels += 1;
@@ -970,7 +988,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
         uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
-        if (scratch && (bnum <= 8 || (bnum == BIN_HEAVY && heavy_by_bucket))) continue;
+        if (scratch && (bnum <= 8 || (bnum == BIN_HEAVY && heavy_in_scratch))) continue;
         char name[32];
         snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
         cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);

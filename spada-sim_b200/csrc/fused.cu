@@ -18,6 +18,9 @@
 //
 // Reference logic replaced: one PE pass (simulator.rs:86-111, 143-171, 199-230), write_psums
 // (simulator.rs:955-983) and the indptr maintenance of CsrMatStorage::write (storage.rs:196-210).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -210,112 +213,90 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
 // the same decoupled look-back as above.
 constexpr int TINY_RPW = 4;
 constexpr int TINY_TILE = FUSED_WARPS * TINY_RPW;
+constexpr int TINY_LD = 40;  // row stride of the staging arrays: the four 8-lane groups of a warp land on disjoint banks
 
+// one row (1..32 products) by a whole warp: leaves the finished row in rc/rv, returns its nnz
 template <typename K>
-__global__ void __launch_bounds__(FUSED_WARPS * 32)
-k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
-             const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
-             double* __restrict__ c_val, unsigned long long* tile_state) {
-    __shared__ uint32_t s_col[TINY_TILE][32];
-    __shared__ double s_val[TINY_TILE][32];
-    __shared__ uint32_t s_nnz[TINY_TILE];   // nnz of every row of the tile
-    __shared__ uint32_t s_off[TINY_TILE];   // exclusive offsets inside the tile
-    __shared__ uint32_t s_light;            // bit rt set <=> row rt was computed here
-    __shared__ unsigned long long s_excl;
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x;
-    if (threadIdx.x == 0) s_light = 0u;
-    __syncthreads();
-
-#pragma unroll 1
-    for (int q = 0; q < TINY_RPW; ++q) {
-        const int rt = warp * TINY_RPW + q;
-        const int64_t r = (int64_t)tile * TINY_TILE + rt;
-        int nnz = 0;
-        if (r < m) {
-            const uint32_t pf = flops[r];
-            const int bn = (pf >= 1u && pf <= 32u) ? 1 : (pf == 0u ? 0 : 2);
-            if (bn == 1) {
-                const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
-                uint32_t* rc = s_col[rt];
-                double* rv = s_val[rt];
-                K x[1];
-                double prod = 0.0;
-                int p;
-                if (a_end - a_begin <= 32) {
-                    // the whole A row is one batch: one product per lane, nothing staged
-                    int64_t bs = 0;
-                    int len = 0;
-                    double av = 0.0;
-                    if (lane < (int)(a_end - a_begin)) {
-                        const int32_t k = ldg_i32(a.col + a_begin + lane);
-                        av = ldg_f64(a.val + a_begin + lane);
-                        bs = ldg_i64(b.ptr + k);
-                        len = (int)(ldg_i64(b.ptr + k + 1) - bs);
-                    }
-                    const int off = warp_excl_scan(len, lane, p);
-                    int j = 0;
-#pragma unroll
-                    for (int st = 16; st > 0; st >>= 1) {
-                        const int o = __shfl_sync(FULL, off, j + st);
-                        if (o <= lane) j += st;
-                    }
-                    const int oj = __shfl_sync(FULL, off, j);
-                    const int64_t bsj = shfl_i64(bs, j);
-                    const double aj = shfl_f64(av, j);
-                    x[0] = KeyTraits<K>::sentinel;
-                    if (lane < p) {
-                        const int64_t qq = bsj + (lane - oj);
-                        x[0] = ((K)(uint32_t)ldg_i32(b.col + qq) << 5) | (K)lane;
-                        prod = __dmul_rn(aj, ldg_f64(b.val + qq));
-                    }
-                } else {
-                    // more than 32 A entries (most of them meeting empty B rows): stage through shared memory
-                    p = 0;
-                    for (int64_t pb = a_begin; pb < a_end; pb += 32) {
-                        int bt;
-                        expand_batch<true, false>(a, b, pb + lane, a_end, lane, p, bt,
-                                                  [&](int sq, uint32_t c, double av, double bv) {
-                                                      rc[sq] = c;
-                                                      rv[sq] = __dmul_rn(av, bv);
-                                                  });
-                        p += bt;
-                    }
-                    __syncwarp();
-                    x[0] = lane < p ? (((K)rc[lane] << 5) | (K)lane) : KeyTraits<K>::sentinel;
-                    prod = lane < p ? rv[lane] : 0.0;
-                    __syncwarp();
-                }
-                const bool have = lane < p;
-                warp_sort<K, 1>(x, lane);
-                const uint32_t col = (uint32_t)(x[0] >> 5);
-                const double v = shfl_f64(prod, (int)(x[0] & (K)31));
-                const uint32_t col_prev = __shfl_up_sync(FULL, col, 1);
-                const bool head = have && (lane == 0 || col_prev != col);
-                const unsigned hm = __ballot_sync(FULL, head);
-                // run length of a head = distance to the next head (or to the end of the row)
-                const unsigned later = lane < 31 ? (hm >> (lane + 1)) : 0u;
-                const int run = head ? (later ? __ffs(later) : (p - lane)) : 0;
-                const int max_run = __reduce_max_sync(FULL, run);
-                double sum = v;
-                for (int d = 1; d < max_run; ++d) {
-                    const double nv = shfl_f64(v, (lane + d) & 31);
-                    if (d < run) sum = __dadd_rn(sum, nv);
-                }
-                if (head) {
-                    const int pos = __popc(hm & ((1u << lane) - 1u));
-                    rc[pos] = col;
-                    rv[pos] = sum;
-                }
-                nnz = __popc(hm);
-                if (lane == 0) atomicOr(&s_light, 1u << rt);
-            } else if (bn >= 2) {
-                nnz = (int)pre_nnz[r];   // counted by its own symbolic kernel
-            }
+__device__ __forceinline__ int tiny_row_warp(const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t r,
+                                             uint32_t* rc, double* rv, int lane) {
+    const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+    K x[1];
+    double prod = 0.0;
+    int p;
+    if (a_end - a_begin <= 32) {
+        // the whole A row is one batch: one product per lane, nothing staged
+        int64_t bs = 0;
+        int len = 0;
+        double av = 0.0;
+        if (lane < (int)(a_end - a_begin)) {
+            const int32_t k = ldg_i32(a.col + a_begin + lane);
+            av = ldg_f64(a.val + a_begin + lane);
+            bs = ldg_i64(b.ptr + k);
+            len = (int)(ldg_i64(b.ptr + k + 1) - bs);
         }
-        if (lane == 0) s_nnz[rt] = (uint32_t)nnz;
+        const int off = warp_excl_scan(len, lane, p);
+        int j = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+            const int o = __shfl_sync(FULL, off, j + st);
+            if (o <= lane) j += st;
+        }
+        const int oj = __shfl_sync(FULL, off, j);
+        const int64_t bsj = shfl_i64(bs, j);
+        const double aj = shfl_f64(av, j);
+        x[0] = KeyTraits<K>::sentinel;
+        if (lane < p) {
+            const int64_t qq = bsj + (lane - oj);
+            x[0] = ((K)(uint32_t)ldg_i32(b.col + qq) << 5) | (K)lane;
+            prod = __dmul_rn(aj, ldg_f64(b.val + qq));
+        }
+    } else {
+        // more than 32 A entries (most of them meeting empty B rows): stage through shared memory
+        p = 0;
+        for (int64_t pb = a_begin; pb < a_end; pb += 32) {
+            int bt;
+            expand_batch<true, false>(a, b, pb + lane, a_end, lane, p, bt, [&](int sq, uint32_t c, double av, double bv) {
+                rc[sq] = c;
+                rv[sq] = __dmul_rn(av, bv);
+            });
+            p += bt;
+        }
+        __syncwarp();
+        x[0] = lane < p ? (((K)rc[lane] << 5) | (K)lane) : KeyTraits<K>::sentinel;
+        prod = lane < p ? rv[lane] : 0.0;
+        __syncwarp();
     }
-    __syncthreads();
+    const bool have = lane < p;
+    warp_sort<K, 1>(x, lane);
+    const uint32_t col = (uint32_t)(x[0] >> 5);
+    const double v = shfl_f64(prod, (int)(x[0] & (K)31));
+    const uint32_t col_prev = __shfl_up_sync(FULL, col, 1);
+    const bool head = have && (lane == 0 || col_prev != col);
+    const unsigned hm = __ballot_sync(FULL, head);
+    // run length of a head = distance to the next head (or to the end of the row)
+    const unsigned later = lane < 31 ? (hm >> (lane + 1)) : 0u;
+    const int run = head ? (later ? __ffs(later) : (p - lane)) : 0;
+    const int max_run = __reduce_max_sync(FULL, run);
+    double sum = v;
+    for (int d = 1; d < max_run; ++d) {
+        const double nv = shfl_f64(v, (lane + d) & 31);
+        if (d < run) sum = __dadd_rn(sum, nv);
+    }
+    if (head) {
+        const int pos = __popc(hm & ((1u << lane) - 1u));
+        rc[pos] = col;
+        rv[pos] = sum;
+    }
+    return __popc(hm);
+}
+
+// the tile's 32 finished rows wait in shared memory: scan their counts, look back for the tile's base,
+// write row_ptr and copy the rows out (a warp stores its four rows as one contiguous stream)
+__device__ __forceinline__ void tiny_tile_finish(uint32_t tile, int64_t m, uint32_t (*s_col)[TINY_LD], double (*s_val)[TINY_LD],
+                                                 uint32_t* s_nnz, uint32_t* s_off, uint32_t* s_light,
+                                                 unsigned long long* s_excl, int64_t* __restrict__ c_ptr,
+                                                 int32_t* __restrict__ c_col, double* __restrict__ c_val,
+                                                 unsigned long long* tile_state, int lane, int warp) {
     if (warp == 0) {
         // exclusive scan of the 32 row counts, then the look-back for the tile's base
         const uint32_t n = s_nnz[lane];
@@ -353,14 +334,14 @@ k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* _
             }
             if (lane == 0) atomicExch(&tile_state[tile], FST_PREFIX | (excl + tile_total));
         }
-        if (lane == 0) s_excl = excl;
+        if (lane == 0) *s_excl = excl;
     }
     __syncthreads();
     // row_ptr: one thread per row of the tile
     if (threadIdx.x < TINY_TILE) {
         const int64_t r = (int64_t)tile * TINY_TILE + threadIdx.x;
         if (r < m) {
-            const int64_t base = (int64_t)(s_excl + s_off[threadIdx.x]);
+            const int64_t base = (int64_t)(*s_excl + s_off[threadIdx.x]);
             c_ptr[r] = base;
             if (r == m - 1) c_ptr[m] = base + s_nnz[threadIdx.x];
         }
@@ -369,8 +350,8 @@ k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* _
     const int rt0 = warp * TINY_RPW;
     const uint32_t n0 = s_nnz[rt0], n1 = s_nnz[rt0 + 1], n2 = s_nnz[rt0 + 2], n3 = s_nnz[rt0 + 3];
     const uint32_t c1 = n0, c2 = n0 + n1, c3 = n0 + n1 + n2, tot = c3 + n3;
-    const int64_t wbase = (int64_t)(s_excl + s_off[rt0]);
-    const uint32_t lightmask = (s_light >> rt0) & 0xfu;
+    const int64_t wbase = (int64_t)(*s_excl + s_off[rt0]);
+    const uint32_t lightmask = (*s_light >> rt0) & 0xfu;
     for (uint32_t e = lane; e < tot; e += 32) {
         const int q = (e >= c1) + (e >= c2) + (e >= c3);
         if ((lightmask >> q) & 1u) {
@@ -379,6 +360,208 @@ k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* _
             c_val[wbase + e] = s_val[rt0 + q][idx];
         }
     }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
+k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
+             const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
+             double* __restrict__ c_val, unsigned long long* tile_state) {
+    __shared__ uint32_t s_col[TINY_TILE][TINY_LD];
+    __shared__ double s_val[TINY_TILE][TINY_LD];
+    __shared__ uint32_t s_nnz[TINY_TILE];   // nnz of every row of the tile
+    __shared__ uint32_t s_off[TINY_TILE];   // exclusive offsets inside the tile
+    __shared__ uint32_t s_light;            // bit rt set <=> row rt was computed here
+    __shared__ unsigned long long s_excl;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (threadIdx.x == 0) s_light = 0u;
+    __syncthreads();
+
+#pragma unroll 1
+    for (int q = 0; q < TINY_RPW; ++q) {
+        const int rt = warp * TINY_RPW + q;
+        const int64_t r = (int64_t)tile * TINY_TILE + rt;
+        int nnz = 0;
+        if (r < m) {
+            const uint32_t pf = flops[r];
+            if (pf >= 1u && pf <= 32u) {
+                nnz = tiny_row_warp<K>(a, b, row_begin, r, s_col[rt], s_val[rt], lane);
+                if (lane == 0) atomicOr(&s_light, 1u << rt);
+            } else if (pf > 32u) {
+                nnz = (int)pre_nnz[r];   // counted by its own symbolic kernel
+            }
+        }
+        if (lane == 0) s_nnz[rt] = (uint32_t)nnz;
+    }
+    __syncthreads();
+    tiny_tile_finish(tile, m, s_col, s_val, s_nnz, s_off, &s_light, &s_excl, c_ptr, c_col, c_val, tile_state, lane, warp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiny rows, four at a time: a warp is cut into four groups of 8 lanes, every group owns one row
+// (at most 8 A entries, at most 32 products = 8 lanes x 4 keys).  Spada's window [R, L/R] with
+// R = 4 rows sharing the 32 lanes: the scan of the B-row lengths, the search of a product's A entry
+// and the 32-key sorting network all stay inside the group (shuffles of width 8, xor masks < 8), so one
+// warp instruction advances four rows.  Measured against k_fused_tiny on the 5-point stencil: see
+// profiles/.  Rows that do not fit (more than 8 A entries) fall back to the whole-warp path above.
+template <typename K>
+__device__ __forceinline__ K shfl_up1_w8(K v);
+template <>
+__device__ __forceinline__ uint32_t shfl_up1_w8<uint32_t>(uint32_t v) { return __shfl_up_sync(FULL, v, 1, 8); }
+template <>
+__device__ __forceinline__ uint64_t shfl_up1_w8<uint64_t>(uint64_t v) {
+    const uint32_t lo = __shfl_up_sync(FULL, (uint32_t)v, 1, 8);
+    const uint32_t hi = __shfl_up_sync(FULL, (uint32_t)(v >> 32), 1, 8);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(FUSED_WARPS * 32)
+k_fused_tiny4(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
+              const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
+              double* __restrict__ c_val, unsigned long long* tile_state) {
+    __shared__ uint32_t s_col[TINY_TILE][TINY_LD];   // finished rows (compacted), staged for the coalesced store
+    __shared__ double s_val[TINY_TILE][TINY_LD];     // first the products by arrival index, then the finished rows
+    __shared__ uint32_t t_col[TINY_TILE][TINY_LD];   // the sorted row, read by the run sums
+    __shared__ double t_val[TINY_TILE][TINY_LD];
+    __shared__ uint32_t s_nnz[TINY_TILE];
+    __shared__ uint32_t s_off[TINY_TILE];
+    __shared__ uint32_t s_light;
+    __shared__ unsigned long long s_excl;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int g = lane >> 3, sub = lane & 7;
+    const uint32_t tile = blockIdx.x;
+    if (threadIdx.x == 0) s_light = 0u;
+    __syncthreads();
+
+    {
+        const int rt = warp * TINY_RPW + g;
+        const int64_t r = (int64_t)tile * TINY_TILE + rt;
+        uint32_t pf = 0;
+        int64_t a_begin = 0;
+        int a_len = 0;
+        if (r < m) {
+            pf = flops[r];
+            a_begin = a.ptr[row_begin + r];
+            a_len = (int)(a.ptr[row_begin + r + 1] - a_begin);
+        }
+        const bool mine = pf >= 1u && pf <= 32u;   // computed here
+        const bool fits = !mine || a_len <= 8;
+        if (__all_sync(FULL, fits)) {
+            // ---- four rows at once -------------------------------------------------------------------
+            int len = 0;
+            int64_t bs = 0;
+            double av = 0.0;
+            if (mine && sub < a_len) {
+                const int32_t k = ldg_i32(a.col + a_begin + sub);
+                av = ldg_f64(a.val + a_begin + sub);
+                bs = ldg_i64(b.ptr + k);
+                len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+            }
+            int x = len;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, x, d, 8);
+                if (sub >= d) x += y;
+            }
+            const int off = x - len;
+            const int p = __shfl_sync(FULL, x, 7, 8);
+            K key[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int sq = e * 8 + sub;
+                int j = 0;
+#pragma unroll
+                for (int st = 4; st > 0; st >>= 1) {
+                    const int o = __shfl_sync(FULL, off, j + st, 8);
+                    if (o <= sq) j += st;
+                }
+                const int oj = __shfl_sync(FULL, off, j, 8);
+                const int bs_lo = __shfl_sync(FULL, (int)(bs & 0xffffffffll), j, 8);
+                const int bs_hi = __shfl_sync(FULL, (int)(bs >> 32), j, 8);
+                const long long avb = __double_as_longlong(av);
+                const int av_lo = __shfl_sync(FULL, (int)(avb & 0xffffffffll), j, 8);
+                const int av_hi = __shfl_sync(FULL, (int)(avb >> 32), j, 8);
+                key[e] = KeyTraits<K>::sentinel;
+                if (sq < p) {
+                    const int64_t qq = (((int64_t)bs_hi << 32) | (uint32_t)bs_lo) + (sq - oj);
+                    const double aj = __longlong_as_double(((long long)av_hi << 32) | (uint32_t)av_lo);
+                    key[e] = ((K)(uint32_t)ldg_i32(b.col + qq) << 5) | (K)sq;
+                    s_val[rt][sq] = __dmul_rn(aj, ldg_f64(b.val + qq));
+                }
+            }
+            __syncwarp();
+            ChunkSort<K, 4, 32>::run(key, lane);   // strides < 8 lanes: every group sorts its own 32 keys
+            uint32_t col[4];
+            double v[4];
+            unsigned validbits = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool valid = key[q] != KeyTraits<K>::sentinel;
+                col[q] = (uint32_t)(key[q] >> 5);
+                v[q] = valid ? s_val[rt][(int)(key[q] & (K)31)] : 0.0;
+                validbits |= (valid ? 1u : 0u) << q;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((validbits >> q) & 1u) {
+                    t_col[rt][sub * 4 + q] = col[q];
+                    t_val[rt][sub * 4 + q] = v[q];
+                }
+            const K prevk = shfl_up1_w8<K>(key[3]);
+            unsigned headbits = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t pc = (q == 0) ? (uint32_t)(prevk >> 5) : col[q - 1];
+                const bool first = (sub == 0 && q == 0);
+                if (((validbits >> q) & 1u) && (first || pc != col[q])) headbits |= 1u << q;
+            }
+            const int hc = __popc(headbits);
+            int hx = hc;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, hx, d, 8);
+                if (sub >= d) hx += y;
+            }
+            const int nnz = __shfl_sync(FULL, hx, 7, 8);
+            __syncwarp();   // products all fetched, sorted row visible: s_val may now take the finished row
+            int o = hx - hc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((headbits >> q) & 1u) {
+                    double sum = v[q];
+                    for (int jj = sub * 4 + q + 1; jj < p && t_col[rt][jj] == col[q]; ++jj) sum = __dadd_rn(sum, t_val[rt][jj]);
+                    s_col[rt][o] = col[q];
+                    s_val[rt][o] = sum;
+                    ++o;
+                }
+            if (sub == 0) {
+                s_nnz[rt] = mine ? (uint32_t)nnz : ((r < m && pf > 32u) ? pre_nnz[r] : 0u);
+                if (mine) atomicOr(&s_light, 1u << rt);
+            }
+        } else {
+            // ---- a row with more than 8 A entries: the warp takes its four rows one after the other -------
+#pragma unroll 1
+            for (int q = 0; q < TINY_RPW; ++q) {
+                const int rtq = warp * TINY_RPW + q;
+                const int64_t rq = (int64_t)tile * TINY_TILE + rtq;
+                int nnz = 0;
+                if (rq < m) {
+                    const uint32_t pq = flops[rq];
+                    if (pq >= 1u && pq <= 32u) {
+                        nnz = tiny_row_warp<K>(a, b, row_begin, rq, s_col[rtq], s_val[rtq], lane);
+                        if (lane == 0) atomicOr(&s_light, 1u << rtq);
+                    } else if (pq > 32u) {
+                        nnz = (int)pre_nnz[rq];
+                    }
+                }
+                if (lane == 0) s_nnz[rtq] = (uint32_t)nnz;
+            }
+        }
+    }
+    __syncthreads();
+    tiny_tile_finish(tile, m, s_col, s_val, s_nnz, s_off, &s_light, &s_excl, c_ptr, c_col, c_val, tile_state, lane, warp);
 }
 
 constexpr int fused_rpw(int nmax) { return nmax <= 32 ? 4 : (nmax <= 64 ? 2 : 1); }
@@ -427,7 +610,20 @@ void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t r
     if (max_bin == 1) {
         size_t tiles = (size_t)((m + TINY_TILE - 1) / TINY_TILE);
         cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
-        if ((uint64_t)b.cols < (1ull << 27))
+        static int quad = -1;   // SPADA_B200_TINY=warp keeps the one-row-per-warp kernel (A/B measurements)
+        if (quad < 0) {
+            const char* e = getenv("SPADA_B200_TINY");
+            quad = (e && !strcmp(e, "warp")) ? 0 : 1;
+        }
+        const bool narrow = (uint64_t)b.cols < (1ull << 27);
+        if (quad) {
+            if (narrow)
+                k_fused_tiny4<uint32_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
+                    a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+            else
+                k_fused_tiny4<uint64_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
+                    a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+        } else if (narrow)
             k_fused_tiny<uint32_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
                 a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
         else

@@ -169,11 +169,13 @@ __device__ __forceinline__ uint32_t hs_numeric_row(const DevCsr& a, const DevCsr
 
 __global__ void __launch_bounds__(HS_THREADS)
 k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list, uint32_t n_rows,
-                     const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+                     const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val,
+                     uint32_t* __restrict__ row_nnz_out) {
     extern __shared__ __align__(16) uint32_t s_u32[];
     __shared__ uint32_t s_warp[HS_WARPS];
     const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
-    hs_numeric_row(a, b, row_begin, r, c_ptr[r], c_col, c_val, s_u32, s_u32 + HS_WORDS, s_warp);
+    const uint32_t nnz = hs_numeric_row(a, b, row_begin, r, c_ptr[r], c_col, c_val, s_u32, s_u32 + HS_WORDS, s_warp);
+    if (row_nnz_out && threadIdx.x == 0) row_nnz_out[r] = nnz;   // one-shot mode: the slice at c_ptr[r] is a scratch row
 }
 
 // overflow rows of the bucket kernel with more than 4096 products (device-side list {count, rows...}):
@@ -207,7 +209,8 @@ void launch_heavy_smem_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_be
 }
 
 void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
-                               uint32_t n_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+                               uint32_t n_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                               uint32_t* row_nnz_out) {
     if (n_rows == 0) return;
     static bool attr = false;
     if (!attr) {
@@ -215,7 +218,8 @@ void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_beg
         cudaFuncSetAttribute(k_heavy_smem_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM);
         attr = true;
     }
-    k_heavy_smem_numeric<<<n_rows, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, rows_list, n_rows, c_ptr, c_col, c_val);
+    k_heavy_smem_numeric<<<n_rows, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, rows_list, n_rows, c_ptr, c_col, c_val,
+                                                             row_nnz_out);
 }
 
 void launch_heavy_smem_list(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,

@@ -16,10 +16,16 @@ constexpr int FLOPS_THREADS = 256;
 constexpr int LONG_ROW = 256;  // A rows longer than this are counted by a whole CTA
 
 // ---------------------------------------------------------------------------------------
-// K1a: one thread per A row.  HBM traffic: A.row_ptr + A.col streamed once, B.row_ptr gathered
-// (8 B x 2 per A nonzero, L2 resident for the benchmark sizes: 8(k+1) <= 34 MB).
+// K1a: one thread per A row.  HBM traffic: A.row_ptr + A.col streamed once; the length of B row k comes
+// from a compact u32 table (4 B per B row, built by k_row_lengths: one gather per A nonzero instead of two
+// 8-byte row_ptr reads, and 4(k) <= 17 MB of L2 instead of 34 MB for the benchmark sizes).
+__global__ void k_row_lengths(const int64_t* __restrict__ ptr, int64_t rows, uint32_t* __restrict__ len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) len[i] = (uint32_t)(ptr[i + 1] - ptr[i]);
+}
+
 __global__ void __launch_bounds__(FLOPS_THREADS)
-k_flops(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin, int64_t m,
+k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t m,
         uint32_t* __restrict__ flops, uint32_t* __restrict__ long_list, PlanCounters* ctr) {
     __shared__ uint32_t s_rows[NUM_BINS];
     __shared__ unsigned long long s_prod[NUM_BINS];
@@ -29,22 +35,35 @@ k_flops(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin, int64_t 
     }
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * FLOPS_THREADS + threadIdx.x;
+    int b = -1;   // bin of this thread's row, -1: nothing to count here
+    unsigned long long f = 0;
     if (i < m) {
         int64_t s = a.ptr[row_begin + i], e = a.ptr[row_begin + i + 1];
         if (e - s > LONG_ROW) {
             uint32_t slot = atomicAdd(&ctr->long_rows, 1u);
             long_list[slot] = (uint32_t)i;
         } else {
-            unsigned long long f = 0;
-            for (int64_t p = s; p < e; ++p) {
-                int32_t k = ldg_i32(a.col + p);
-                f += (unsigned long long)(ldg_i64(b_ptr + k + 1) - ldg_i64(b_ptr + k));
-            }
+            for (int64_t p = s; p < e; ++p) f += (unsigned long long)__ldg(b_len + ldg_i32(a.col + p));
             uint32_t f32 = f > 0xffffffffull ? 0xffffffffu : (uint32_t)f;
             flops[i] = f32;
-            int b = bin_of(f32);
-            atomicAdd(&s_rows[b], 1u);
-            atomicAdd(&s_prod[b], f);
+            b = bin_of(f32);
+            if (f >> 32) {   // cannot happen below 2^32 products per row; counted directly
+                atomicAdd(&s_rows[b], 1u);
+                atomicAdd(&s_prod[b], f);
+                b = -1;
+            }
+        }
+    }
+    // one shared-memory update per (warp, bin): the lanes of a bin are found with match.any, their counts summed
+    // with redux (16-bit halves, so 32 lanes cannot overflow) -- per-thread 64-bit shared atomics on one address
+    // serialised the whole CTA when every row falls in the same bin (stencils)
+    const unsigned grp = __match_any_sync(FULL, b);
+    if (b >= 0) {
+        const unsigned lo = __reduce_add_sync(grp, (unsigned)(f & 0xffffull));
+        const unsigned hi = __reduce_add_sync(grp, (unsigned)(f >> 16));
+        if (lane_id() == __ffs(grp) - 1) {
+            atomicAdd(&s_rows[b], (uint32_t)__popc(grp));
+            atomicAdd(&s_prod[b], ((unsigned long long)hi << 16) + lo);
         }
     }
     __syncthreads();
@@ -59,7 +78,7 @@ k_flops(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin, int64_t 
 // independent gathers per thread in flight.
 constexpr int FLOPS_LONG_THREADS = 1024;
 __global__ void __launch_bounds__(FLOPS_LONG_THREADS)
-k_flops_long(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin,
+k_flops_long(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin,
              uint32_t* __restrict__ flops, const uint32_t* __restrict__ long_list, PlanCounters* ctr) {
     __shared__ unsigned long long s_warp[FLOPS_LONG_THREADS / 32];
     uint32_t n_long = ctr->long_rows;
@@ -76,7 +95,7 @@ k_flops_long(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin,
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (k[u] >= 0) f += (unsigned long long)(ldg_i64(b_ptr + k[u] + 1) - ldg_i64(b_ptr + k[u]));
+                if (k[u] >= 0) f += (unsigned long long)__ldg(b_len + k[u]);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
@@ -96,12 +115,14 @@ k_flops_long(DevCsr a, const int64_t* __restrict__ b_ptr, int64_t row_begin,
     }
 }
 
-void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t row_begin, int64_t m, uint32_t* flops,
-                  uint32_t* long_list, PlanCounters* ctr, cudaStream_t s) {
+// b_len: workspace of b_rows u32 (filled here with the lengths of B's rows)
+void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t b_rows, uint32_t* b_len, int64_t row_begin, int64_t m,
+                  uint32_t* flops, uint32_t* long_list, PlanCounters* ctr, cudaStream_t s) {
     if (m <= 0) return;
+    if (b_rows > 0) k_row_lengths<<<(unsigned)((b_rows + 255) / 256), 256, 0, s>>>(b_ptr, b_rows, b_len);
     unsigned grid = (unsigned)((m + FLOPS_THREADS - 1) / FLOPS_THREADS);
-    k_flops<<<grid, FLOPS_THREADS, 0, s>>>(a, b_ptr, row_begin, m, flops, long_list, ctr);
-    k_flops_long<<<148 * 2, FLOPS_LONG_THREADS, 0, s>>>(a, b_ptr, row_begin, flops, long_list, ctr);
+    k_flops<<<grid, FLOPS_THREADS, 0, s>>>(a, b_len, row_begin, m, flops, long_list, ctr);
+    k_flops_long<<<148 * 2, FLOPS_LONG_THREADS, 0, s>>>(a, b_len, row_begin, flops, long_list, ctr);
 }
 
 // ---------------------------------------------------------------------------------------
