@@ -305,6 +305,7 @@ def main():
         same = [b is a] if rank == 0 else [None]
         dist.broadcast_object_list(same, src=0)
         db, _kb = (da, _ka) if same[0] else D.broadcast_csr(eng, b, device)
+        db.prepare()                                         # fiber store of the replicated B (not timed, like the broadcast)
         bounds = D.plan_bounds(eng, da, db, world, device)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         dims = (da.shape[0], da.shape[1], db.shape[1], da.nnz, db.nnz)

@@ -157,6 +157,12 @@ SPADA_B200_API int spada_b200_upload32(spada_b200_t *h, const spada_csr_view32 *
 SPADA_B200_API int spada_b200_csr_wrap_device(spada_b200_t *h, uint64_t rows, uint64_t cols, uint64_t nnz,
                                const int64_t *d_indptr, const int32_t *d_indices,
                                const double *d_data, spada_b200_csr_t **out);
+/* Builds the operand's fiber store: one packed (start, length) descriptor per row and, when rows average >= 6
+ * nonzeros, a copy whose rows start on 64-byte boundaries -- the layout the kernels gather B rows from (the
+ * engine-side counterpart of CsrMatStorage::init_with_gemm laying B out for the fiber cache, storage.rs:214-239,
+ * 460-).  Uploaded operands get it automatically the first time they are used as B; call this for wrapped device
+ * arrays (it snapshots them: call again after changing them -- free and re-wrap).  ms_or_null: device time. */
+SPADA_B200_API int spada_b200_csr_prepare(spada_b200_t *h, spada_b200_csr_t *m, float *ms_or_null);
 SPADA_B200_API int spada_b200_csr_shape(const spada_b200_csr_t *m, uint64_t *rows, uint64_t *cols, uint64_t *nnz);
 SPADA_B200_API int spada_b200_csr_device_ptrs(const spada_b200_csr_t *m, const int64_t **d_indptr,
                                const int32_t **d_indices, const double **d_data);

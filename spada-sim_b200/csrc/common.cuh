@@ -62,7 +62,16 @@ struct DevCsr {
     const int32_t* col;   // nnz
     const double* val;    // nnz
     int64_t rows, cols, nnz;
+    // B side only (nullable): the operand's FIBER STORE.  desc[k] = (start << 24) | length of row k inside col/val,
+    // which then point at a copy whose rows start on 16-element boundaries (64-byte DRAM atoms for the column ids,
+    // 128 bytes for the values): one 8-byte descriptor instead of two row_ptr reads per visited B row, and a short
+    // B row costs one DRAM atom per array instead of the two an unaligned row straddles.  ptr stays the canonical
+    // row_ptr (lengths only).  Built by launch_fiber_* (plan.cu) at upload time -- the device-side counterpart of
+    // CsrMatStorage::init_with_gemm (storage.rs:214-239) laying B out for the fiber cache (storage.rs:460-).
+    const unsigned long long* desc;
 };
+constexpr int FIBER_LEN_BITS = 24;   // rows of 2^24 or more elements: no fiber store (desc == nullptr)
+constexpr int FIBER_PAD = 16;
 
 #ifdef __CUDACC__
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -92,6 +101,30 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
 __device__ __forceinline__ int32_t ldg_i32(const int32_t* p) { return __ldg(p); }
 __device__ __forceinline__ double ldg_f64(const double* p) { return __ldg(p); }
 __device__ __forceinline__ int64_t ldg_i64(const int64_t* p) { return __ldg(p); }
+
+// stores of finished rows (C and the scratch CSR are written once and not read again by the kernel that writes them):
+// cache-streaming (evict-first) so that 3+ GB of output do not push B's rows and descriptors out of L2
+#ifndef SPADA_STREAM_STORES
+#define SPADA_STREAM_STORES 1
+#endif
+__device__ __forceinline__ void st_out(int32_t* p, int32_t v) {
+    if (SPADA_STREAM_STORES) __stcs(p, v); else *p = v;
+}
+__device__ __forceinline__ void st_out(double* p, double v) {
+    if (SPADA_STREAM_STORES) __stcs(p, v); else *p = v;
+}
+
+// where row k of B starts inside b.col / b.val and how long it is
+__device__ __forceinline__ void b_row(const DevCsr& b, int32_t k, int64_t& bs, int& len) {
+    if (b.desc) {
+        const unsigned long long d = __ldg(b.desc + k);
+        bs = (int64_t)(d >> FIBER_LEN_BITS);
+        len = (int)(d & ((1ull << FIBER_LEN_BITS) - 1ull));
+    } else {
+        bs = ldg_i64(b.ptr + k);
+        len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+    }
+}
 
 // ---- product expansion ---------------------------------------------------------------------
 // A warp walks 32 A nonzeros (one per lane: lane l owns position p, if p < a_end), scans the
@@ -123,8 +156,7 @@ __device__ __forceinline__ void expand_batch_long(const DevCsr& a, const DevCsr&
     if (p < a_end) {
         int32_t k = ldg_i32(a.col + p);
         if (NUMERIC) av = ldg_f64(a.val + p);
-        bs = ldg_i64(b.ptr + k);
-        len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+        b_row(b, k, bs, len);
     }
     int big_len = 0;
     unsigned big = 0;
@@ -256,6 +288,11 @@ void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, u
 void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t limit, uint32_t* out, cudaStream_t s);
 void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const int64_t* t_ptr, const int32_t* t_col,
                       const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+// fiber store of a B operand (see DevCsr::desc): padded row lengths -> (scan) -> starts -> descriptors + aligned copy
+void launch_fiber_lengths(const int64_t* ptr, int64_t rows, uint32_t pad, uint32_t* padded_len, PlanCounters* ctr,
+                          cudaStream_t s);
+void launch_fiber_fill(const DevCsr& m, const int64_t* start, unsigned long long* desc, int32_t* gcol, double* gval,
+                       cudaStream_t s);
 // stage 4
 void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out /* n+1 */, uint64_t* tile_state,
                          PlanCounters* ctr, cudaStream_t s);
@@ -326,18 +363,6 @@ void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int6
 void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                                 uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
                                 uint32_t* row_nnz_out = nullptr);
-// bucketed rows (bucket.cu): bins 6..9 in one pass per row (scratch mode); ovf = {count, rows...} collects the rows
-// whose columns are too skewed for the buckets, the two fallback launchers recompute them
-bool bucket_supported(int64_t b_cols);
-void launch_bucket_rows(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm, uint32_t rows,
-                        const uint32_t* flops, const int64_t* c_ptr, int32_t* c_col, double* c_val,
-                        uint32_t* row_nnz_out, uint32_t* ovf, cudaStream_t s);
-void launch_bucket_fallback(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
-                            const uint32_t* ovf, uint32_t max_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val,
-                            uint32_t* row_nnz_out, cudaStream_t s);
-void launch_heavy_smem_list(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
-                            const uint32_t* ovf, uint32_t max_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val,
-                            uint32_t* row_nnz_out, cudaStream_t s);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
 void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,

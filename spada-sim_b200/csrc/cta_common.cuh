@@ -39,8 +39,7 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
         if (p < a_end) {
             int32_t k = ldg_i32(a.col + p);
             if (NUMERIC) av = ldg_f64(a.val + p);
-            bs = ldg_i64(b.ptr + k);
-            len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+            b_row(b, k, bs, len);
         }
         int wtotal;
         int woff = warp_excl_scan(len, lane, wtotal);
@@ -194,8 +193,8 @@ __device__ __forceinline__ int cta_reduce_store(const K* keys, const double* val
                 sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
             }
             const int oo = o + __popc(hm[e] & ((1u << lane) - 1u));
-            c_col[cbase + oo] = (int32_t)(col[e] + col_offset);
-            c_val[cbase + oo] = sum;
+            st_out(c_col + (cbase + oo), (int32_t)(col[e] + col_offset));
+            st_out(c_val + (cbase + oo), sum);
         }
         o += __popc(hm[e]);
     }

@@ -61,8 +61,10 @@ struct spada_b200 {
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int n_streams = 2;
-    uint32_t bucket_bins = 0;      // bins (bit b, 6..9) whose rows take the bucketed kernel of bucket.cu in scratch mode
-                                   // (SPADA_B200_BUCKET_BINS; off by default: measured slower than the bitonic / bitmap kernels)
+    int fiber_pad = -1;            // SPADA_B200_FIBER_PAD: -1 auto (16 when rows average >= 6 nonzeros, else descriptors
+                                   // only), 0 no fiber store, 1 descriptors only, 16 always pad
+    int64_t heavy_smem_cols = 1ll << 20;  // widest B whose heavy rows use the shared-memory bitmap (one column-range pass
+                                   // per 2^20 columns; SPADA_B200_HEAVY_SMEM_COLS); wider: the item path of the huge bin
     bool heavy_oneshot = true;     // heavy bin in scratch mode: bitmap + ranks + values in ONE kernel into a scratch row
     spada_b200_opts opts{};
     PlanCounters* d_ctr = nullptr;
@@ -83,6 +85,14 @@ struct spada_b200_csr {
     spada_b200* h;
     DevCsr d;
     bool owned;
+    // fiber store (DevCsr::desc): built on first use as the B operand for owned matrices, or by
+    // spada_b200_csr_prepare for wrapped ones; engine-owned pool blocks
+    bool fib_ready = false;          // build attempted (desc stays NULL when the operand cannot have one)
+    unsigned long long* desc = nullptr;
+    int32_t* gcol = nullptr;         // NULL: descriptors address the canonical arrays (no padding)
+    double* gval = nullptr;
+    int64_t fib_extent = 0;          // elements of gcol / gval (>= nnz)
+    float fib_ms = 0.f;
 };
 
 struct spada_b200_result {
@@ -324,8 +334,9 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
             CU(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        if (const char* e = getenv("SPADA_B200_FIBER_PAD")) h->fiber_pad = atoi(e);
+        if (const char* e = getenv("SPADA_B200_HEAVY_SMEM_COLS")) h->heavy_smem_cols = atoll(e);
         if (const char* e = getenv("SPADA_B200_HEAVY_ONESHOT")) h->heavy_oneshot = atoi(e) != 0;
-        if (const char* e = getenv("SPADA_B200_BUCKET_BINS")) h->bucket_bins = (uint32_t)strtoul(e, nullptr, 0) & 0x3c0u;
         if (const char* e = getenv("SPADA_B200_STREAMS")) {
             int v = atoi(e);
             if (v >= 1 && v <= 3) h->n_streams = v;
@@ -513,6 +524,12 @@ extern "C" int spada_b200_csr_device_ptrs(const spada_b200_csr_t* m, const int64
 
 extern "C" void spada_b200_csr_free(spada_b200_csr_t* m) {
     if (!m) return;
+    if (m->desc || m->gcol || m->gval) {
+        DeviceGuard g(m->h->device);
+        dfree(m->h, m->desc);
+        dfree(m->h, m->gcol);
+        dfree(m->h, m->gval);
+    }
     if (m->owned) {
         DeviceGuard g(m->h->device);
         dfree(m->h, const_cast<int64_t*>(m->d.ptr));
@@ -520,6 +537,77 @@ extern "C" void spada_b200_csr_free(spada_b200_csr_t* m) {
         dfree(m->h, const_cast<double*>(m->d.val));
     }
     delete m;
+}
+
+// ---- fiber store of a B operand ---------------------------------------------------------------
+namespace {
+int build_fibers(spada_b200* h, spada_b200_csr* c) {
+    if (c->fib_ready) return 0;
+    c->fib_ready = true;
+    const DevCsr& d = c->d;
+    int pad = h->fiber_pad;
+    if (pad < 0) pad = (d.rows > 0 && d.nnz >= 6 * d.rows) ? FIBER_PAD : 1;
+    if (pad == 0 || d.rows == 0 || d.nnz == 0) return 0;
+    if (pad > 1) pad = FIBER_PAD;
+    cudaStream_t s = h->stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    uint32_t* d_len = nullptr;
+    int64_t* d_start = nullptr;
+    uint64_t* d_tiles = nullptr;
+    int rc = 0;
+    auto done = [&](int code) {
+        dfree(h, d_len);
+        dfree(h, d_start);
+        dfree(h, d_tiles);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return code;
+    };
+    if ((rc = dalloc(h, &d_len, (size_t)d.rows))) return done(rc);
+    CU(cudaMemsetAsync(h->d_ctr, 0, sizeof(PlanCounters), s));
+    launch_fiber_lengths(d.ptr, d.rows, (uint32_t)pad, d_len, h->d_ctr, s);
+    int64_t total = d.nnz;
+    if (pad > 1) {
+        if ((rc = dalloc(h, &d_start, (size_t)d.rows + 1))) return done(rc);
+        if ((rc = dalloc(h, &d_tiles, scan_tile_state_words(d.rows)))) return done(rc);
+        launch_scan_u32_i64(d_len, d.rows, d_start, d_tiles, h->d_ctr, s);
+        if (cudaMemcpyAsync(h->h_scalar, d_start + d.rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            return done(fail(SPADA_B200_CUDA_ERROR, "fiber store: copy failed"));
+    }
+    if (cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(PlanCounters), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return done(fail(SPADA_B200_CUDA_ERROR, "fiber store: %s", cudaGetErrorString(cudaGetLastError())));
+    if (h->h_ctr->invalid_rows) return done(0);   // a row of 2^24 or more elements: the kernels use row_ptr
+    if (pad > 1) total = h->h_scalar[0];
+    if ((rc = dalloc(h, &c->desc, (size_t)d.rows))) return done(rc);
+    if (pad > 1) {
+        if ((rc = dalloc(h, &c->gcol, (size_t)total)) || (rc = dalloc(h, &c->gval, (size_t)total))) {
+            dfree(h, c->desc);
+            dfree(h, c->gcol);
+            c->desc = nullptr;
+            c->gcol = nullptr;
+            return done(rc == SPADA_B200_OOM ? 0 : rc);   // no room for the copy: run without it
+        }
+    }
+    c->fib_extent = total;
+    launch_fiber_fill(d, d_start, c->desc, c->gcol, c->gval, s);
+    cudaEventRecord(e1, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return done(fail(SPADA_B200_CUDA_ERROR, "fiber store: fill failed"));
+    cudaEventElapsedTime(&c->fib_ms, e0, e1);
+    return done(0);
+}
+}  // namespace
+
+extern "C" int spada_b200_csr_prepare(spada_b200_t* h, spada_b200_csr_t* m, float* ms_or_null) {
+    if (!h || !m) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    DeviceGuard g(h->device);
+    int rc = build_fibers(h, m);
+    if (ms_or_null) *ms_or_null = m->fib_ms;
+    return rc;
 }
 
 // ---- stage 1 alone ------------------------------------------------------------------------
@@ -604,10 +692,21 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
                     (unsigned long long)row_end, (long long)a->d.rows);
     DeviceGuard g(h->device);
     cudaStream_t s = h->stream;
-    const DevCsr& A = a->d;
-    const DevCsr& B = b->d;
-    const int64_t m = (int64_t)(row_end - row_begin);
     int rc;
+    // owned operands get their fiber store the first time they are used as B (wrapped ones: spada_b200_csr_prepare)
+    if (b->owned && !b->fib_ready && (rc = build_fibers(h, const_cast<spada_b200_csr*>(b)))) return rc;
+    const DevCsr& A = a->d;
+    DevCsr Bv = b->d;
+    if (b->desc) {
+        Bv.desc = b->desc;
+        if (b->gcol) {
+            Bv.col = b->gcol;
+            Bv.val = b->gval;
+            Bv.nnz = b->fib_extent;   // extent of the arrays the kernels index (bulk-copy bounds, heavy.cu)
+        }
+    }
+    const DevCsr& B = Bv;
+    const int64_t m = (int64_t)(row_end - row_begin);
 
     spada_b200_result* R = new (std::nothrow) spada_b200_result;
     if (!R) return fail(SPADA_B200_OOM, "host allocation failed");
@@ -618,7 +717,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     spada_b200_stats& st = R->stats;
     st.rows = (uint64_t)m;
     st.cols = (uint64_t)B.cols;
-    st.nnz_b = (uint64_t)B.nnz;
+    st.nnz_b = (uint64_t)b->d.nnz;
     if ((rc = dalloc(h, &R->ptr, (size_t)m + 1))) { delete R; return rc; }
 
     h->ev_used = 0;
@@ -666,7 +765,6 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     int64_t *d_item_off = nullptr, *d_prod_ptr = nullptr;
     void* d_kstore = nullptr;
     uint32_t* d_masked = nullptr;
-    uint32_t* d_ovf = nullptr;
     int32_t* d_tcol = nullptr;
     double* d_tval = nullptr;
     uint32_t kernels = 0;
@@ -687,7 +785,6 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         dfree(h, d_prod_ptr);
         dfree(h, (char*)d_kstore);
         dfree(h, d_masked);
-        dfree(h, d_ovf);
         dfree(h, d_tcol);
         dfree(h, d_tval);
     };
@@ -789,23 +886,15 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     // laid out by product count; after the scan they are copied to their place -- one expansion, one sort.
     uint64_t sorted_products = 0;
     for (int bnum = 1; bnum <= 8; ++bnum) sorted_products += pc.bin_products[bnum];
-    // rows of bins 6..9 can take the bucketed kernel (bucket.cu) when the key layout covers B's width
-    const uint32_t bucket_bins = bucket_supported(B.cols) ? h->bucket_bins : 0u;
-    const bool heavy_bucket = !fused && h->two_phase_mode == 2 && (bucket_bins >> BIN_HEAVY & 1u) && pc.bin_rows[BIN_HEAVY] > 0;
     // heavy bin (shared-memory bitmap, B at most 2^20 columns wide): one kernel per row into a scratch row instead of
     // a symbolic and a numeric kernel around the scan -- one expansion less, 0.39 ms of 8 on the rect config
-    const bool heavy_oneshot = !fused && h->two_phase_mode == 2 && !heavy_bucket && h->heavy_oneshot &&
-                               B.cols <= (1ll << 20) && pc.bin_rows[BIN_HEAVY] > 0;
-    if (heavy_bucket || heavy_oneshot) sorted_products += pc.bin_products[BIN_HEAVY];
-    const uint32_t scratch_limit = (heavy_bucket || heavy_oneshot) ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS;
+    const bool heavy_oneshot = !fused && h->two_phase_mode == 2 && h->heavy_oneshot &&
+                               B.cols <= h->heavy_smem_cols && pc.bin_rows[BIN_HEAVY] > 0;
+    if (heavy_oneshot) sorted_products += pc.bin_products[BIN_HEAVY];
+    const uint32_t scratch_limit = heavy_oneshot ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS;
     const bool scratch = !fused && h->two_phase_mode == 2 && sorted_products > 0 &&
                          (double)sorted_products * 12.0 <= 0.30 * (double)h->dev_total_mem;
-    const bool heavy_by_bucket = scratch && heavy_bucket;
-    const bool heavy_in_scratch = scratch && (heavy_bucket || heavy_oneshot);
-    uint32_t ovf_cap = 0;   // rows that may land on the bucket kernel's overflow list
-    if (scratch)
-        for (int bnum = 6; bnum <= BIN_HEAVY; ++bnum)
-            if (bucket_bins >> bnum & 1u) ovf_cap += pc.bin_rows[bnum];
+    const bool heavy_in_scratch = scratch && heavy_oneshot;
     if (!fused && !scratch && h->two_phase_mode >= 1) {
         uint64_t sorted_rows = 0;
         for (int bnum = 1; bnum <= 8; ++bnum) {
@@ -838,16 +927,12 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         CUT(cudaGetLastError());
         kernels += 2;
         end_rec();
-        if (ovf_cap) {
-            TRY(dalloc(h, &d_ovf, (size_t)ovf_cap + 1));
-            CUT(cudaMemsetAsync(d_ovf, 0, sizeof(uint32_t), s));
-        }
     }
 
     // huge rows: cut into items, bitmaps for one wave of rows at a time
     // The shared-memory bitmap of the heavy bin covers 2^20 columns per pass; for wider B the heavy rows
     // join the huge rows on the item path (measured on R-MAT, n = 2^21: two passes per row lose to it).
-    const bool heavy_in_smem = B.cols <= (1ll << 20);
+    const bool heavy_in_smem = B.cols <= h->heavy_smem_cols;
     if (!heavy_in_smem && !heavy_in_scratch) {   // bins 9 and 10 are adjacent in perm[]: one combined list
         pc.bin_rows[BIN_HUGE] += pc.bin_rows[BIN_HEAVY];
         pc.bin_products[BIN_HUGE] += pc.bin_products[BIN_HEAVY];
@@ -879,13 +964,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         char name[32];
         snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
         cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);   // the stream of this bin
-        if (scratch && bnum >= 6 && bnum <= BIN_HEAVY && (bucket_bins >> bnum & 1u) && (bnum < BIN_HEAVY || heavy_by_bucket)) {
-            snprintf(name, sizeof(name), "bucket_pass<%s>", bin_name(bnum));
-            begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
-            launch_bucket_rows(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_flops, d_prod_ptr, d_tcol, d_tval,
-                               d_nnz, d_ovf, sb);
-            kernels += 1;
-        } else if (bnum == BIN_HEAVY && heavy_in_scratch) {
+        if (bnum == BIN_HEAVY && heavy_in_scratch) {
             snprintf(name, sizeof(name), "oneshot<%s>", bin_name(bnum));
             begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
             launch_heavy_smem_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_prod_ptr, d_tcol, d_tval, sb,
@@ -934,17 +1013,6 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         end_rec();
     }
     CUT(join());
-    if (ovf_cap) {   // rows the buckets could not take (skewed columns): usually none, two near-empty launches
-        begin_rec("bucket_fallback", 2, 0, 0, 0);
-        launch_bucket_fallback(A, B, (int64_t)row_begin, d_flops, d_ovf, ovf_cap, d_prod_ptr, d_tcol, d_tval, d_nnz, s);
-        if (heavy_by_bucket)
-            launch_heavy_smem_list(A, B, (int64_t)row_begin, d_flops, d_ovf, pc.bin_rows[BIN_HEAVY], d_prod_ptr, d_tcol,
-                                   d_tval, d_nnz, s);
-        CUT(cudaGetLastError());
-        kernels += heavy_by_bucket ? 2 : 1;
-        end_rec();
-    }
-
     int64_t nnz_c = 0;
     if (!fused) {
         // ---- stage 4: row_ptr ---------------------------------------------------------------

@@ -117,8 +117,8 @@ k_esc_numeric_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __rest
                 sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
             }
             int o = out_base + __popc(hm & ((1u << lane) - 1u));
-            c_col[cbase + o] = (int32_t)col;
-            c_val[cbase + o] = sum;
+            st_out(c_col + (cbase + o), (int32_t)col);
+            st_out(c_val + (cbase + o), sum);
         }
         out_base += __popc(hm);
     }
@@ -217,8 +217,8 @@ k_esc_numeric_presorted_warp(DevCsr a, DevCsr b, int64_t row_begin, const uint32
                 sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
             }
             const int o = out_base + __popc(hm & ((1u << lane) - 1u));
-            c_col[cbase + o] = (int32_t)col;
-            c_val[cbase + o] = sum;
+            st_out(c_col + (cbase + o), (int32_t)col);
+            st_out(c_val + (cbase + o), sum);
         }
         out_base += __popc(hm);
     }

@@ -86,8 +86,8 @@ __device__ __forceinline__ void reduce_store(const K* keys, const double* vals, 
                 sum = __dadd_rn(sum, vals[(int)(kj & (K)((1u << SBK) - 1u))]);
             }
             const int o = out_base + __popc(hm & ((1u << lane) - 1u));
-            c_col[base + o] = (int32_t)col;
-            c_val[base + o] = sum;
+            st_out(c_col + (base + o), (int32_t)col);
+            st_out(c_val + (base + o), sum);
         }
         out_base += __popc(hm);
     }
@@ -231,8 +231,7 @@ __device__ __forceinline__ int tiny_row_warp(const DevCsr& a, const DevCsr& b, i
         if (lane < (int)(a_end - a_begin)) {
             const int32_t k = ldg_i32(a.col + a_begin + lane);
             av = ldg_f64(a.val + a_begin + lane);
-            bs = ldg_i64(b.ptr + k);
-            len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+            b_row(b, k, bs, len);
         }
         const int off = warp_excl_scan(len, lane, p);
         int j = 0;
@@ -356,8 +355,8 @@ __device__ __forceinline__ void tiny_tile_finish(uint32_t tile, int64_t m, uint3
         const int q = (e >= c1) + (e >= c2) + (e >= c3);
         if ((lightmask >> q) & 1u) {
             const uint32_t idx = e - (q == 0 ? 0u : (q == 1 ? c1 : (q == 2 ? c2 : c3)));
-            c_col[wbase + e] = (int32_t)s_col[rt0 + q][idx];
-            c_val[wbase + e] = s_val[rt0 + q][idx];
+            st_out(c_col + (wbase + e), (int32_t)s_col[rt0 + q][idx]);
+            st_out(c_val + (wbase + e), s_val[rt0 + q][idx]);
         }
     }
 }
@@ -456,8 +455,7 @@ k_fused_tiny4(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
             if (mine && sub < a_len) {
                 const int32_t k = ldg_i32(a.col + a_begin + sub);
                 av = ldg_f64(a.val + a_begin + sub);
-                bs = ldg_i64(b.ptr + k);
-                len = (int)(ldg_i64(b.ptr + k + 1) - bs);
+                b_row(b, k, bs, len);
             }
             int x = len;
 #pragma unroll

@@ -178,24 +178,6 @@ k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __re
     if (row_nnz_out && threadIdx.x == 0) row_nnz_out[r] = nnz;   // one-shot mode: the slice at c_ptr[r] is a scratch row
 }
 
-// overflow rows of the bucket kernel with more than 4096 products (device-side list {count, rows...}):
-// computed in one go into a slice of capacity >= nnz (the scratch CSR), nnz recorded
-__global__ void __launch_bounds__(HS_THREADS)
-k_heavy_smem_list(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ flops,
-                  const uint32_t* __restrict__ ovf, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
-                  double* __restrict__ c_val, uint32_t* __restrict__ row_nnz_out) {
-    extern __shared__ __align__(16) uint32_t s_u32[];
-    __shared__ uint32_t s_warp[HS_WARPS];
-    const uint32_t n_rows = ovf[0];
-    for (uint32_t i = blockIdx.x; i < n_rows; i += gridDim.x) {
-        const uint32_t r = ovf[1 + i];
-        if (flops[r] <= ESC_MAX_PRODUCTS) continue;  // launch_bucket_fallback
-        const uint32_t nnz = hs_numeric_row(a, b, row_begin, r, c_ptr[r], c_col, c_val, s_u32, s_u32 + HS_WORDS, s_warp);
-        if (row_nnz_out && threadIdx.x == 0) row_nnz_out[r] = nnz;
-        __syncthreads();
-    }
-}
-
 void launch_heavy_smem_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
                                 uint32_t n_rows, uint32_t* row_nnz, cudaStream_t s) {
     if (n_rows == 0) return;
@@ -220,19 +202,6 @@ void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_beg
     }
     k_heavy_smem_numeric<<<n_rows, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, rows_list, n_rows, c_ptr, c_col, c_val,
                                                              row_nnz_out);
-}
-
-void launch_heavy_smem_list(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
-                            const uint32_t* ovf, uint32_t max_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val,
-                            uint32_t* row_nnz_out, cudaStream_t s) {
-    if (max_rows == 0) return;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_heavy_smem_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM);
-        attr = true;
-    }
-    const unsigned grid = max_rows < 148u ? max_rows : 148u;
-    k_heavy_smem_list<<<grid, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, flops, ovf, c_ptr, c_col, c_val, row_nnz_out);
 }
 
 }  // namespace spada

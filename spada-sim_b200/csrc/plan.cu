@@ -295,8 +295,8 @@ k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, uint32_t limit, const
     const int64_t src = t_ptr[r], dst = c_ptr[r];
     const int n = (int)(c_ptr[r + 1] - dst);
     for (int j = lane; j < n; j += 32) {
-        c_col[dst + j] = t_col[src + j];
-        c_val[dst + j] = t_val[src + j];
+        st_out(c_col + dst + j, t_col[src + j]);
+        st_out(c_val + dst + j, t_val[src + j]);
     }
 }
 void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const int64_t* t_ptr, const int32_t* t_col,
@@ -304,6 +304,44 @@ void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const in
     if (m > 0)
         k_copy_rows<<<(unsigned)((m + COPY_WARPS - 1) / COPY_WARPS), COPY_WARPS * 32, 0, s>>>(flops, m, limit, t_ptr, t_col,
                                                                                           t_val, c_ptr, c_col, c_val);
+}
+
+// ---------------------------------------------------------------------------------------
+// Fiber store of a B operand (DevCsr::desc): rows re-laid on FIBER_PAD-element boundaries + one packed
+// (start, length) descriptor per row.  HBM traffic: 12 B read + 12 B written per nonzero, once per operand.
+__global__ void k_fiber_lengths(const int64_t* __restrict__ ptr, int64_t rows, uint32_t pad, uint32_t* __restrict__ out,
+                                PlanCounters* ctr) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) {
+        const int64_t len = ptr[i + 1] - ptr[i];
+        if (len >= (1ll << FIBER_LEN_BITS)) atomicAdd(&ctr->invalid_rows, 1u);   // no descriptor can hold it
+        out[i] = (uint32_t)((len + pad - 1) / pad * pad);
+    }
+}
+void launch_fiber_lengths(const int64_t* ptr, int64_t rows, uint32_t pad, uint32_t* padded_len, PlanCounters* ctr,
+                          cudaStream_t s) {
+    if (rows > 0) k_fiber_lengths<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(ptr, rows, pad, padded_len, ctr);
+}
+
+// 16 lanes per row; start == nullptr: descriptors into the canonical arrays (no copy)
+__global__ void __launch_bounds__(256)
+k_fiber_fill(DevCsr m, const int64_t* __restrict__ start, unsigned long long* __restrict__ desc,
+             int32_t* __restrict__ gcol, double* __restrict__ gval) {
+    const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4;
+    const int sub = threadIdx.x & 15;
+    if (r >= m.rows) return;
+    const int64_t s0 = m.ptr[r], len = m.ptr[r + 1] - s0;
+    const int64_t d0 = start ? start[r] : s0;
+    if (sub == 0) desc[r] = ((unsigned long long)d0 << FIBER_LEN_BITS) | (unsigned long long)len;
+    if (start)
+        for (int64_t j = sub; j < len; j += 16) {
+            gcol[d0 + j] = m.col[s0 + j];
+            gval[d0 + j] = m.val[s0 + j];
+        }
+}
+void launch_fiber_fill(const DevCsr& m, const int64_t* start, unsigned long long* desc, int32_t* gcol, double* gval,
+                       cudaStream_t s) {
+    if (m.rows > 0) k_fiber_fill<<<(unsigned)((m.rows * 16 + 255) / 256), 256, 0, s>>>(m, start, desc, gcol, gval);
 }
 
 // ---------------------------------------------------------------------------------------

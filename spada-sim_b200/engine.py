@@ -39,6 +39,13 @@ class DeviceCsr:
         check(lib().spada_b200_csr_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def prepare(self) -> float:
+        """Builds the fiber store the kernels gather B rows from (automatic for uploaded operands on their first
+        use as B; needed for wrapped device arrays).  Returns the device time in ms."""
+        ms = C.c_float(0.0)
+        check(lib().spada_b200_csr_prepare(self.engine._h, self._h, C.byref(ms)))
+        return ms.value
+
     def free(self):
         if self._h is not None:
             if self.engine._h is not None:   # a destroyed engine already released every device block

@@ -103,6 +103,7 @@ extern "C" {
         h: *mut spada_b200_t, rows: u64, cols: u64, nnz: u64, d_indptr: *const i64, d_indices: *const i32,
         d_data: *const f64, out: *mut *mut spada_b200_csr_t,
     ) -> c_int;
+    pub fn spada_b200_csr_prepare(h: *mut spada_b200_t, m: *mut spada_b200_csr_t, ms_or_null: *mut f32) -> c_int;
     pub fn spada_b200_csr_shape(m: *const spada_b200_csr_t, rows: *mut u64, cols: *mut u64, nnz: *mut u64) -> c_int;
     pub fn spada_b200_csr_device_ptrs(
         m: *const spada_b200_csr_t, d_indptr: *mut *const i64, d_indices: *mut *const i32, d_data: *mut *const f64,

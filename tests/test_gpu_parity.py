@@ -194,16 +194,16 @@ def _widen(b, n_cols, shift=0):
 
 
 @pytest.mark.parametrize("ka,lb,width", [(30, 30, 64), (50, 40, 300), (100, 90, 700), (200, 60, 2000), (90, 80, 1 << 14)])
-def test_skewed_columns_overflow_the_buckets(engine, oracle, ka, lb, width):
-    # bucket.cu cuts B's column space into equal ranges; here every product of a row lands in a narrow
-    # band of a 2^20-wide B, so buckets (or passes) overflow and the rows take the fallback kernels
+def test_skewed_columns(engine, oracle, ka, lb, width):
+    # every product of a row lands in a narrow band of a 2^20-wide B: long runs of equal columns in the sort bins,
+    # a handful of hot words in the heavy bin's bitmap
     a = random_csr(120, 400, row_nnz=ka, seed=ka + 1)
     b = _widen(random_csr(400, width, row_nnz=min(lb, width), seed=lb + 2), 1 << 20, shift=(1 << 19) + 77)
     run(engine, oracle, a, b, exact=(ka * min(lb, width) <= 4096))
 
 
-def test_bucket_rows_mixed_lengths(engine, oracle):
-    # rows of 513 .. ~40000 products side by side: one-pass buckets, multi-pass rows, the odd empty bucket
+def test_long_rows_mixed_lengths(engine, oracle):
+    # rows of 513 .. ~40000 products side by side: CTA-per-row sort bins and the heavy bin in one call
     rng = np.random.default_rng(21)
     lens = rng.choice([0, 30, 70, 130, 260, 520, 900, 2500], size=400, p=[.05, .2, .2, .2, .15, .1, .07, .03])
     a = random_csr(400, 6000, row_nnz=lens, seed=22)
@@ -216,9 +216,41 @@ def test_bucket_rows_mixed_lengths(engine, oracle):
     one_pass = np.repeat(f <= 4096, np.diff(ref[0]))
     assert np.array_equal(dx[one_pass].view(np.uint64), ref[2][one_pass].view(np.uint64))
     assert (np.abs(dx[~one_pass] - ref[2][~one_pass]) <= TOL * np.abs(ref[2][~one_pass])).all()
-    # tiny column space: more buckets than columns
+    # tiny column space: every output column is hit hundreds of times
     b2 = random_csr(6000, 48, row_nnz=rng.integers(8, 20, size=6000), seed=24)
     run(engine, oracle, a, b2, exact=False)
+
+
+@pytest.mark.parametrize("pad", ["0", "1", "16"])
+def test_fiber_store_layouts(spada, oracle, monkeypatch, pad):
+    # B is gathered from its fiber store: no store / descriptors into the canonical arrays / rows on 64-byte boundaries
+    if spada.device_count() == 0:
+        pytest.skip("no CUDA device")
+    monkeypatch.setenv("SPADA_B200_FIBER_PAD", pad)
+    e = spada.Engine(two_phase=True)
+    try:
+        rng = np.random.default_rng(31)
+        for ka, lb, n in [(3, 4, 900), (16, 16, 1 << 18), (40, 50, 5000), (300, 40, 5000), (300, 230, 5000)]:
+            a = random_csr(150, 700, row_nnz=ka, seed=ka + 40)
+            b = random_csr(700, n, row_nnz=rng.integers(0, 2 * lb, size=700), seed=lb + 41)
+            run(e, oracle, a, b, exact=False)
+        a = random_csr(400, 400, density=0.03, seed=42)     # A x A: one operand on both sides
+        da = e.upload(a)
+        check(e.spgemm_dev(da, da), oracle.spgemm(a, a, threads=oracle.max_threads()), True)
+    finally:
+        e.close()
+
+
+def test_prepare_wrapped_operand(engine, oracle):
+    a = random_csr(300, 500, row_nnz=12, seed=43)
+    b = random_csr(500, 4000, row_nnz=np.random.default_rng(44).integers(0, 30, size=500), seed=45)
+    da, db = engine.upload(a), engine.upload(b)
+    p, c, v = db.device_ptrs()
+    wb = engine.wrap_device(b.shape[0], b.shape[1], b.nnz, p, c, v, keepalive=db)
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    check(engine.spgemm_dev(da, wb), ref, True)      # wrapped arrays: row_ptr path
+    assert wb.prepare() >= 0.0
+    check(engine.spgemm_dev(da, wb), ref, True)      # same arrays through the fiber store
 
 
 def test_usize_layout_matches(engine, oracle):
