@@ -53,6 +53,8 @@ static int run(int argc, char** argv) {
                   cfg.bandwidth_per_channel);
     sim.execute();
     std::vector<CsrRow> result = sim.get_exec_result();
+    if (const char* sink = std::getenv("SPADA_B200_DUMP_C"))   // result sink: all of C + digest (stderr keeps stdout = the reference's)
+        std::fprintf(stderr, "%s\n", dump_result(sink, result, dram_b.mat_shape[0]).c_str());
     auto a_count = sim.get_a_mat_stat(), b_count = sim.get_b_mat_stat(), c_count = sim.get_c_mat_stat();
     auto cache_count = sim.get_cache_stat();
     std::printf("-----Result-----\n");

@@ -447,6 +447,44 @@ struct CsrRow {
                " data: " + debug_list_f64(data.begin(), data.begin() + n);
     }
 };
+// ---- result sink (the reference prints ten rows of C and drops the rest, main.rs:113-116) ----------
+// dump_result writes all of C as a Matrix Market coordinate file (1-based, %.17g: every f64 round-trips) and returns
+// a one-line digest: nnz, sum of the values, FNV-1a-64 over the little-endian (indptr u64 | column ids u64 | values f64).
+inline uint64_t fnv1a64(const void* p, size_t n, uint64_t h = 14695981039346656037ull) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) {
+        h ^= b[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+inline std::string dump_result(const std::string& path, const std::vector<CsrRow>& rows, size_t n_cols) {
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    size_t nnz = 0;
+    for (const CsrRow& r : rows) nnz += r.len();
+    std::fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n%zu %zu %zu\n", rows.size(), n_cols, nnz);
+    uint64_t h = 14695981039346656037ull, ptr = 0;
+    double sum = 0.0;
+    h = fnv1a64(&ptr, 8, h);
+    for (const CsrRow& r : rows) {
+        ptr += r.len();
+        h = fnv1a64(&ptr, 8, h);
+    }
+    for (const CsrRow& r : rows) h = fnv1a64(r.indptr.data(), 8 * r.indptr.size(), h);
+    for (const CsrRow& r : rows) {
+        h = fnv1a64(r.data.data(), 8 * r.data.size(), h);
+        for (size_t j = 0; j < r.len(); ++j) {
+            std::fprintf(f, "%zu %llu %.17g\n", r.rowptr + 1, (unsigned long long)r.indptr[j] + 1, r.data[j]);
+            sum += r.data[j];
+        }
+    }
+    std::fclose(f);
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "C dumped: nnz %zu sum %.17g fnv1a64 %016llx", nnz, sum, (unsigned long long)h);
+    return buf;
+}
+
 struct CsrMatStorage {  // storage.rs:150-160
     std::vector<double> data;
     std::vector<uint64_t> indptr, indices;

@@ -98,3 +98,43 @@ def test_cli_cari_transcript(workdir, oracle, cari, spada, acc, extra):
         assert [int(x) for x in m.group(2).split(", ")] == cj[cp[r]:cp[r] + 5].tolist()
         vals = np.array([float(x) for x in m.group(3).split(", ")])
         assert np.allclose(vals, cx[cp[r]:cp[r] + 5], rtol=1e-12, atol=0)   # -p never changes C (simulator.rs:1039-1060)
+
+
+def test_result_sink_roundtrip(tmp_path, spada):
+    # SPADA_B200_DUMP_C: Matrix Market text that round-trips every f64, FNV-1a-64 digest
+    main = __import__("importlib").import_module("spada-sim_b200.main")
+    assert main.fnv1a64(b"") == 0xcbf29ce484222325 and main.fnv1a64(b"a") == 0xaf63dc4c8601ec8c   # published vectors
+    rng = np.random.default_rng(3)
+    import scipy.sparse as sp
+    c = sp.random(37, 23, density=0.2, format="csr", random_state=rng); c.sort_indices()
+    c.data = rng.uniform(-1, 1, c.nnz) * 10.0 ** rng.integers(-30, 30, c.nnz)
+    line = main.dump_result(str(tmp_path / "c.mtx"), c.indptr, c.indices, c.data, c.shape[1])
+    assert line.startswith(f"C dumped: nnz {c.nnz} sum ")
+    back = scipy.io.mmread(str(tmp_path / "c.mtx")).tocsr(); back.sort_indices()
+    assert back.shape == c.shape and np.array_equal(back.indptr, c.indptr) and np.array_equal(back.indices, c.indices)
+    assert np.array_equal(back.data.view(np.uint64), c.data.view(np.uint64))
+
+
+@pytest.mark.gpu
+def test_cli_result_sink(workdir, oracle, cari, spada):
+    env = dict(os.environ, PYTHONPATH=ROOT, SPADA_B200_DUMP_C=str(workdir / "c_py.mtx"))
+    p = subprocess.run([sys.executable, "-W", "ignore", "-m", "spada-sim_b200", "accuratesimu", "spada", "ss", "cari",
+                        "config/config_1mb_row1.json"], cwd=workdir, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.startswith(HEAD)                      # stdout stays the reference's transcript
+    assert re.search(r"C dumped: nnz 160000 sum 7833\.70723\d+ fnv1a64 [0-9a-f]{16}", p.stderr)
+    g = spada.GEMM.from_mat("cari", cari)
+    cp, cj, cx = oracle.spgemm(g.a, g.b)
+    outs = [workdir / "c_py.mtx"]
+    binary = os.path.join(ROOT, "spada-sim_b200", "bin", "spada-sim")
+    if os.path.exists(binary):
+        env["SPADA_B200_DUMP_C"] = str(workdir / "c_cpp.mtx")
+        q = subprocess.run([binary, "accuratesimu", "spada", "ss", "cari", "config/config_1mb_row1.json"], cwd=workdir,
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert q.returncode == 0, q.stderr
+        assert re.search(r"C dumped: nnz 160000 sum 7833\.70723\d+ fnv1a64 [0-9a-f]{16}", q.stderr)
+        outs.append(workdir / "c_cpp.mtx")
+    for path in outs:
+        c = scipy.io.mmread(str(path)).tocsr(); c.sort_indices()
+        assert c.shape == (400, 400) and np.array_equal(c.indptr, cp) and np.array_equal(c.indices, cj)
+        assert (np.abs(c.data - cx) <= 1e-12 * np.abs(cx)).all()
