@@ -163,9 +163,15 @@ SPADA_B200_API int spada_b200_csr_wrap_device(spada_b200_t *h, uint64_t rows, ui
  * 460-).  Uploaded operands get it automatically the first time they are used as B; call this for wrapped device
  * arrays (it snapshots them: call again after changing them -- free and re-wrap).  ms_or_null: device time. */
 SPADA_B200_API int spada_b200_csr_prepare(spada_b200_t *h, spada_b200_csr_t *m, float *ms_or_null);
+/* B = A^T as a new device operand (canonical CSR: ascending column ids = A's row ids).  Replaces the host-side
+ * transpose of GEMM::from_mat for non-square SS workloads (gemm.rs:41-53: `transpose_into().to_csr()`); values are
+ * moved, not computed, so the result is bit-identical to the reference's / scipy's. */
+SPADA_B200_API int spada_b200_transpose(spada_b200_t *h, const spada_b200_csr_t *a, spada_b200_csr_t **out);
 SPADA_B200_API int spada_b200_csr_shape(const spada_b200_csr_t *m, uint64_t *rows, uint64_t *cols, uint64_t *nnz);
 SPADA_B200_API int spada_b200_csr_device_ptrs(const spada_b200_csr_t *m, const int64_t **d_indptr,
                                const int32_t **d_indices, const double **d_data);
+/* device operand -> caller-allocated host arrays (int64 indptr [rows+1], int32 indices, float64 data) */
+SPADA_B200_API int spada_b200_csr_download32(const spada_b200_csr_t *m, int64_t *indptr, int32_t *indices, double *data);
 SPADA_B200_API void spada_b200_csr_free(spada_b200_csr_t *m);
 
 /* ---- the hot path: replaces Simulator::execute + get_exec_result ---------------------- */

@@ -293,6 +293,15 @@ void launch_fiber_lengths(const int64_t* ptr, int64_t rows, uint32_t pad, uint32
                           cudaStream_t s);
 void launch_fiber_fill(const DevCsr& m, const int64_t* start, unsigned long long* desc, int32_t* gcol, double* gval,
                        cudaStream_t s);
+// device transpose (transpose.cu): stable LSD radix sort of the entry indices by column id
+int transpose_passes(int64_t cols);
+int64_t transpose_tiles(int64_t nnz);
+void launch_entry_rows(const DevCsr& a, uint32_t* erow, uint32_t* col_count, cudaStream_t s);
+void launch_radix_hist(const int32_t* keys, int64_t n, int shift, uint32_t* hist, cudaStream_t s);
+void launch_radix_scatter(const int32_t* keys, const uint32_t* pay, int64_t n, int shift, const int64_t* offs,
+                          int32_t* keys_out, uint32_t* pay_out, cudaStream_t s);
+void launch_transpose_gather(const uint32_t* pay, const uint32_t* erow, const double* val, int64_t n, int32_t* t_col,
+                             double* t_val, cudaStream_t s);
 // stage 4
 void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out /* n+1 */, uint64_t* tile_state,
                          PlanCounters* ctr, cudaStream_t s);

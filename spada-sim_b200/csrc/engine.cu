@@ -522,6 +522,20 @@ extern "C" int spada_b200_csr_device_ptrs(const spada_b200_csr_t* m, const int64
     return 0;
 }
 
+extern "C" int spada_b200_csr_download32(const spada_b200_csr_t* m, int64_t* indptr, int32_t* indices, double* data) {
+    if (!m || !indptr) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    if (m->d.nnz && (!indices || !data)) return fail(SPADA_B200_INVALID_ARG, "NULL output array");
+    spada_b200* h = m->h;
+    DeviceGuard g(h->device);
+    CU(cudaMemcpyAsync(indptr, m->d.ptr, (size_t)(m->d.rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (m->d.nnz) {
+        CU(cudaMemcpyAsync(indices, m->d.col, (size_t)m->d.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(data, m->d.val, (size_t)m->d.nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" void spada_b200_csr_free(spada_b200_csr_t* m) {
     if (!m) return;
     if (m->desc || m->gcol || m->gval) {
@@ -608,6 +622,77 @@ extern "C" int spada_b200_csr_prepare(spada_b200_t* h, spada_b200_csr_t* m, floa
     int rc = build_fibers(h, m);
     if (ms_or_null) *ms_or_null = m->fib_ms;
     return rc;
+}
+
+// ---- B = A^T on the device: replaces GEMM::from_mat's transpose_into().to_csr() (gemm.rs:44-46) --------------
+extern "C" int spada_b200_transpose(spada_b200_t* h, const spada_b200_csr_t* a, spada_b200_csr_t** out) {
+    if (!h || !a || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    const DevCsr& A = a->d;
+    if (A.nnz >= (1ll << 32)) return fail(SPADA_B200_TOO_LARGE, "transpose: nnz >= 2^32");
+    if (A.rows >= (1ll << 31)) return fail(SPADA_B200_TOO_LARGE, "transpose: rows >= 2^31 (they become column ids)");
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    int rc;
+    int64_t* ptr;
+    int32_t* col;
+    double* val;
+    spada_b200_csr* c;
+    if ((rc = make_csr(h, (uint64_t)A.cols, (uint64_t)A.rows, (uint64_t)A.nnz, &c, &ptr, &col, &val))) return rc;
+    const int64_t n = A.nnz, k = A.cols;
+    const int passes = transpose_passes(k);
+    const int64_t tiles = transpose_tiles(n);
+    uint32_t *d_erow = nullptr, *d_cnt = nullptr, *d_hist = nullptr, *d_pay[2] = {nullptr, nullptr};
+    int32_t* d_key[2] = {nullptr, nullptr};
+    int64_t* d_offs = nullptr;
+    uint64_t* d_tiles = nullptr;
+    auto done = [&](int code) {
+        dfree(h, d_erow);
+        dfree(h, d_cnt);
+        dfree(h, d_hist);
+        dfree(h, d_pay[0]);
+        dfree(h, d_pay[1]);
+        dfree(h, d_key[0]);
+        dfree(h, d_key[1]);
+        dfree(h, d_offs);
+        dfree(h, d_tiles);
+        if (code) spada_b200_csr_free(c);
+        return code;
+    };
+    if (n == 0 || k == 0) {
+        if (cudaMemsetAsync(ptr, 0, (size_t)(k + 1) * sizeof(int64_t), s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess)
+            return done(fail(SPADA_B200_CUDA_ERROR, "transpose: %s", cudaGetErrorString(cudaGetLastError())));
+        *out = c;
+        return done(0);
+    }
+    const size_t scan_n = (size_t)std::max<int64_t>(k, (int64_t)256 * tiles);
+    if ((rc = dalloc(h, &d_erow, (size_t)n)) || (rc = dalloc(h, &d_cnt, (size_t)k)) ||
+        (rc = dalloc(h, &d_tiles, scan_tile_state_words((int64_t)scan_n))))
+        return done(rc);
+    if (passes > 0) {
+        if ((rc = dalloc(h, &d_hist, (size_t)256 * tiles)) || (rc = dalloc(h, &d_offs, (size_t)256 * tiles + 1)) ||
+            (rc = dalloc(h, &d_key[0], (size_t)n)) || (rc = dalloc(h, &d_pay[0], (size_t)n)))
+            return done(rc);
+        if (passes > 1 && ((rc = dalloc(h, &d_key[1], (size_t)n)) || (rc = dalloc(h, &d_pay[1], (size_t)n)))) return done(rc);
+    }
+    cudaMemsetAsync(d_cnt, 0, (size_t)k * sizeof(uint32_t), s);
+    launch_entry_rows(A, d_erow, d_cnt, s);
+    launch_scan_u32_i64(d_cnt, k, ptr, d_tiles, h->d_ctr, s);   // row_ptr of A^T
+    const int32_t* key_in = A.col;
+    const uint32_t* pay_in = nullptr;   // pass 0: payload = entry index
+    for (int p = 0; p < passes; ++p) {
+        launch_radix_hist(key_in, n, 8 * p, d_hist, s);
+        launch_scan_u32_i64(d_hist, (int64_t)256 * tiles, d_offs, d_tiles, h->d_ctr, s);
+        launch_radix_scatter(key_in, pay_in, n, 8 * p, d_offs, d_key[p & 1], d_pay[p & 1], s);
+        key_in = d_key[p & 1];
+        pay_in = d_pay[p & 1];
+    }
+    launch_transpose_gather(pay_in, d_erow, A.val, n, col, val, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return done(fail(SPADA_B200_CUDA_ERROR, "transpose: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = c;
+    return done(0);
 }
 
 // ---- stage 1 alone ------------------------------------------------------------------------

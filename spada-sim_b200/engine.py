@@ -39,6 +39,14 @@ class DeviceCsr:
         check(lib().spada_b200_csr_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def to_scipy(self) -> sp.csr_matrix:
+        """Copies the operand back to the host (int64 indptr, int32 indices, float64 data)."""
+        ip = np.empty(self.shape[0] + 1, dtype=np.int64)
+        ix = np.empty(max(self.nnz, 1), dtype=np.int32)
+        dx = np.empty(max(self.nnz, 1), dtype=np.float64)
+        check(lib().spada_b200_csr_download32(self._h, _ptr(ip, C.c_int64), _ptr(ix, C.c_int32), _ptr(dx, C.c_double)))
+        return sp.csr_matrix((dx[:self.nnz], ix[:self.nnz], ip), shape=self.shape)
+
     def prepare(self) -> float:
         """Builds the fiber store the kernels gather B rows from (automatic for uploaded operands on their first
         use as B; needed for wrapped device arrays).  Returns the device time in ms."""
@@ -191,6 +199,12 @@ class Engine:
         else:
             v, keep = self._view32(m)
             check(lib().spada_b200_upload32(self._h, C.byref(v), C.byref(out)))
+        return DeviceCsr(self, out)
+
+    def transpose(self, a: DeviceCsr) -> DeviceCsr:
+        """B = A^T on the device (GEMM::from_mat's transpose for non-square SS workloads, gemm.rs:41-53)."""
+        out = C.c_void_p()
+        check(lib().spada_b200_transpose(self._h, a._h, C.byref(out)))
         return DeviceCsr(self, out)
 
     def wrap_device(self, rows, cols, nnz, d_indptr: int, d_indices: int, d_data: int, keepalive=None) -> DeviceCsr:

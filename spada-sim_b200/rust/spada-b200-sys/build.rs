@@ -1,6 +1,6 @@
 // build.rs -- compiles the sm_100a kernels with nvcc and links them into the Rust binary.
 //
-// Inputs : ../../csrc/*.cu (plan, esc, esc_cta_bitonic, fused, heavy, heavy_smem, engine)
+// Inputs : ../../csrc/*.cu (plan, esc, esc_cta_bitonic, fused, transpose, heavy, heavy_smem, engine)
 //          + ../../csrc/{common,sort,cta_common}.cuh + ../../../include/spada_b200.h
 // Output : $OUT_DIR/libspada_b200.a, linked statically together with cudart.
 // There is exactly one code path: sm_100a.  No Triton, no multi-backend dispatch, no CPU fallback.
@@ -16,7 +16,7 @@ fn main() {
     let cuda_lib = env::var("CUDA_LIB_DIR").unwrap_or_else(|_| "/usr/local/cuda/lib64".to_string());
 
     let mut objects = vec![];
-    for unit in ["plan", "esc", "esc_cta_bitonic", "fused", "heavy", "heavy_smem", "engine"].iter() {
+    for unit in ["plan", "esc", "esc_cta_bitonic", "fused", "transpose", "heavy", "heavy_smem", "engine"].iter() {
         let src = csrc.join(format!("{}.cu", unit));
         let obj = out.join(format!("{}.o", unit));
         println!("cargo:rerun-if-changed={}", src.display());

@@ -104,10 +104,12 @@ extern "C" {
         d_data: *const f64, out: *mut *mut spada_b200_csr_t,
     ) -> c_int;
     pub fn spada_b200_csr_prepare(h: *mut spada_b200_t, m: *mut spada_b200_csr_t, ms_or_null: *mut f32) -> c_int;
+    pub fn spada_b200_transpose(h: *mut spada_b200_t, a: *const spada_b200_csr_t, out: *mut *mut spada_b200_csr_t) -> c_int;
     pub fn spada_b200_csr_shape(m: *const spada_b200_csr_t, rows: *mut u64, cols: *mut u64, nnz: *mut u64) -> c_int;
     pub fn spada_b200_csr_device_ptrs(
         m: *const spada_b200_csr_t, d_indptr: *mut *const i64, d_indices: *mut *const i32, d_data: *mut *const f64,
     ) -> c_int;
+    pub fn spada_b200_csr_download32(m: *const spada_b200_csr_t, indptr: *mut i64, indices: *mut i32, data: *mut f64) -> c_int;
     pub fn spada_b200_csr_free(m: *mut spada_b200_csr_t);
     pub fn spada_b200_spgemm_dev(
         h: *mut spada_b200_t, a: *const spada_b200_csr_t, b: *const spada_b200_csr_t, row_begin: u64, row_end: u64,

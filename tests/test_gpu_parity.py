@@ -253,6 +253,27 @@ def test_prepare_wrapped_operand(engine, oracle):
     check(engine.spgemm_dev(da, wb), ref, True)      # same arrays through the fiber store
 
 
+@pytest.mark.parametrize("shape,row_nnz", [((1, 1), 1), ((400, 1200), 30), ((3000, 70000), None), ((5000, 257), 12),
+                                            ((64, 1 << 22), 3000), ((2000, 300), 0)])
+def test_device_transpose_matches_scipy(engine, shape, row_nnz):
+    # gemm.rs:41-53: B = A^T as CSR for non-square SS workloads -- values moved, structure bit-identical to scipy
+    rng = np.random.default_rng(shape[0] + shape[1])
+    lens = rng.integers(0, 40, size=shape[0]) if row_nnz is None else row_nnz
+    a = random_csr(shape[0], shape[1], row_nnz=lens, seed=51, values="signed")
+    t = engine.transpose(engine.upload(a)).to_scipy()
+    ref = a.T.tocsr(); ref.sort_indices()
+    assert t.shape == ref.shape
+    assert np.array_equal(t.indptr, ref.indptr) and np.array_equal(t.indices, ref.indices)
+    assert np.array_equal(t.data.view(np.uint64), ref.data.view(np.uint64))
+
+
+def test_transposed_operand_feeds_the_hot_path(engine, oracle, cari, spada):
+    g = spada.GEMM.from_mat("cari", cari)                 # host transpose, as the reference does it
+    da = engine.upload(g.a)
+    db = engine.transpose(da)                             # device transpose
+    check(engine.spgemm_dev(da, db), oracle.spgemm(g.a, g.b, threads=oracle.max_threads()), False)
+
+
 def test_usize_layout_matches(engine, oracle):
     a = random_csr(300, 200, density=0.05, seed=16)
     b = random_csr(200, 250, density=0.05, seed=17)
