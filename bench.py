@@ -311,6 +311,20 @@ def main():
         dims = (da.shape[0], da.shape[1], db.shape[1], da.nnz, db.nnz)
     m, k, n, nnz_a, nnz_b = dims
 
+    # GEMM::from_mat's transpose (gemm.rs:41-53) on the device, timed once for the record (not part of a step:
+    # the workload builder already holds B = A^T on the host, like the reference after its loader)
+    transpose_ms = None
+    if world == 1 and b is not a and a.shape[0] != a.shape[1]:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.transpose(da).free()                             # warm-up (pool blocks)
+        t0.record()
+        dt = eng.transpose(da)
+        t1.record()
+        torch.cuda.synchronize()
+        assert dt.shape == db.shape and dt.nnz == db.nnz
+        transpose_ms = t0.elapsed_time(t1)
+        dt.free()
+
     gathered = None
 
     def step():
@@ -368,6 +382,32 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- per-launch durations: the engine overlaps the heavy / huge bins with the sort bins on a side stream, so the
+    # event times of the timed region overlap too.  For the roofline every kernel is timed alone: a second handle with
+    # SPADA_B200_FLAG_SERIAL over the same device arrays, 3 warm-up + 5 recorded steps, CUDA events on its stream.
+    timing_note = "launch times from the timed region"
+    if world == 1:
+        ser = pkg.Engine(device=local_rank, validate=False, stream=stream.cuda_stream, two_phase=args.two_phase,
+                         single_pass=args.single_pass, serial=True)
+        sa = ser.wrap_device(da.shape[0], da.shape[1], da.nnz, *da.device_ptrs(), keepalive=da)
+        sb = sa if db is da else ser.wrap_device(db.shape[0], db.shape[1], db.nnz, *db.device_ptrs(), keepalive=db)
+        sb.prepare()
+        per_launch = {}
+        for it in range(8):
+            r_ = ser.spgemm_dev(sa, sb, lo, hi)
+            if it >= 3:
+                for L in r_.stats()["launches"]:
+                    d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": L["products"], "rows": L["rows"],
+                                                          "grid": L["grid"]})
+                    d["ms"] += L["ms"]; d["n"] += 1
+            r_ = None
+        sa.free()
+        if sb is not sa:
+            sb.free()
+        ser.close()
+        timing_note = ("launch times from 5 serialised steps after the timed region (SPADA_B200_FLAG_SERIAL): the timed "
+                       "steps run the heavy/huge bins on a side stream beside the sort bins")
+
     # ---- roofline of the dominant kernel launch ----------------------------------------------------
     peak, peak_src = peaks()
     alg_bytes = pkg.workloads.algorithmic_bytes(nnz_a, m, nnz_b, k, nnz_c)
@@ -386,7 +426,7 @@ def main():
         traffic = json.load(open(tp)).get(args.workload, {}).get(dom_name)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": dom_name, "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
-                "peak_source": peak_src,
+                "peak_source": peak_src, "timing": timing_note,
                 "whole_path": {"algorithmic_bytes": alg_bytes, "ms": ms_per_step,
                                "achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9,
                                "frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -450,7 +490,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[args.workload], "scale": args.scale, "m": m, "k": k, "n": n,
-                   "nnz_a": nnz_a, "nnz_b": nnz_b, "products": products, "nnz_c": nnz_c,
+                   "nnz_a": nnz_a, "nnz_b": nnz_b, "products": products, "nnz_c": nnz_c, "device_transpose_ms": transpose_ms,
                    "l2": "inputs+output larger than L2 (no flush)" if alg_bytes > 4 * 126e6 else "working set near L2 size",
                    "parallelism": f"rows of A sharded over {world} GPU(s) by equal product count; B replicated; C all-gathered"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

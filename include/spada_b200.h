@@ -103,6 +103,9 @@ typedef struct spada_b200_opts {
                                           allocated with capacity = intermediate-product count).  With neither
                                           flag the engine picks: single pass when one bin holds >= 80 % of the rows */
 
+#define SPADA_B200_FLAG_SERIAL 8u     /* every kernel on the one stream (the engine otherwise runs the heavy / huge bins
+                                          on a side stream beside the sort bins): clean per-launch times for profiling */
+
 typedef struct spada_b200 spada_b200_t;               /* engine handle (streams, workspace pool) */
 typedef struct spada_b200_csr spada_b200_csr_t;       /* device-resident operand */
 typedef struct spada_b200_result spada_b200_result_t; /* device-resident C (engine owned) */

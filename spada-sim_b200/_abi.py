@@ -21,6 +21,7 @@ ACCELERATORS = {"ip": 0, "op": 1, "multirow": 2, "spada": 3}
 FLAG_VALIDATE = 1
 FLAG_TWO_PHASE = 2
 FLAG_SINGLE_PASS = 4
+FLAG_SERIAL = 8
 
 
 class CsrView(C.Structure):

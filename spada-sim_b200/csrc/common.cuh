@@ -288,6 +288,8 @@ void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, u
 void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t limit, uint32_t* out, cudaStream_t s);
 void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const int64_t* t_ptr, const int32_t* t_col,
                       const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+void launch_copy_rows_list(const uint32_t* rows_list, uint32_t n_rows, const int64_t* t_ptr, const int32_t* t_col,
+                           const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
 // fiber store of a B operand (see DevCsr::desc): padded row lengths -> (scan) -> starts -> descriptors + aligned copy
 void launch_fiber_lengths(const int64_t* ptr, int64_t rows, uint32_t pad, uint32_t* padded_len, PlanCounters* ctr,
                           cudaStream_t s);

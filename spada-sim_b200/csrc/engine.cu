@@ -55,9 +55,11 @@ struct spada_b200 {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // Side streams: the CTA-per-row sort bins and the heavy/huge bins are independent of the warp-per-row
-    // bins until the row_ptr scan, and latency bound where the others are issue/bandwidth bound; they run
-    // concurrently and are joined back into `stream` by events (SPADA_B200_STREAMS=1 serialises them).
+    // Side streams: the heavy / huge bins (latency bound: one 1024-thread CTA per SM, atomics) are independent of the
+    // sort bins until the row_ptr scan and run beside them on a second stream, joined back into `stream` by events
+    // (rect config: 7.96 -> 7.47 ms per step).  SPADA_B200_STREAMS=3 also moves the CTA-per-row sort bins aside (no
+    // gain measured); SPADA_B200_FLAG_SERIAL / SPADA_B200_STREAMS=1 serialise everything, which is what the
+    // per-launch event times of the stats are meaningful for.
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int n_streams = 2;
@@ -341,6 +343,7 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
             int v = atoi(e);
             if (v >= 1 && v <= 3) h->n_streams = v;
         }
+        if (h->opts.flags & SPADA_B200_FLAG_SERIAL) h->n_streams = 1;
     }
     CU(cudaMalloc((void**)&h->d_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
@@ -1132,8 +1135,12 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     CUT(fork());
     if (scratch) {
         begin_rec("copy_rows", 3, (uint32_t)((m + 7) / 8), (uint64_t)m, sorted_products);
-        launch_copy_rows(d_flops, m, heavy_in_scratch ? scratch_limit : ESC_MAX_PRODUCTS, d_prod_ptr, d_tcol, d_tval,
-                         R->ptr, R->col, R->val, s);
+        launch_copy_rows(d_flops, m, ESC_MAX_PRODUCTS, d_prod_ptr, d_tcol, d_tval, R->ptr, R->col, R->val, s);
+        if (heavy_in_scratch) {   // the heavy bin's scratch rows: one CTA per row
+            launch_copy_rows_list(perm_of_bin[BIN_HEAVY], pc.bin_rows[BIN_HEAVY], d_prod_ptr, d_tcol, d_tval, R->ptr,
+                                  R->col, R->val, s);
+            kernels += 1;
+        }
         CUT(cudaGetLastError());
         kernels += 1;
         end_rec();

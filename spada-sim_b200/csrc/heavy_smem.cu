@@ -3,7 +3,7 @@
 //
 // The global-bitmap path of heavy.cu touches one cold 32-byte sector per product in each of
 // its passes (measured: 160-210 B of DRAM traffic per product, 27-40 G atomics/s).  Here the
-// bitmap of up to 2^20 columns (128 KB) plus one rank per 8 words (16 KB) fit the 227 KB of
+// bitmap of up to 2^20 columns (128 KB) plus one 16-bit rank per word (64 KB) fit the 227 KB of
 // shared memory a B200 CTA can have, so setting bits and looking ranks up never leaves the SM;
 // only the value accumulation uses global atomics, into the row's own slice of C (a few hundred
 // KB per row, <= 148 rows in flight: L2 resident).  B matrices wider than 2^20 columns are
@@ -21,8 +21,8 @@ constexpr int HS_THREADS = 1024;
 constexpr int HS_WARPS = HS_THREADS / 32;
 constexpr int HS_WORDS = 32768;                 // bitmap words per pass: 2^20 columns
 constexpr int HS_GROUP = 8;                     // words per rank group
-constexpr int HS_GROUPS = HS_WORDS / HS_GROUP;  // 4096 coarse ranks
-constexpr size_t HS_SMEM = sizeof(uint32_t) * (HS_WORDS + HS_GROUPS);
+// bitmap (128 KB) + one 16-bit rank per word (64 KB): 192 KB of the 227 KB a CTA can have
+constexpr size_t HS_SMEM = sizeof(uint32_t) * HS_WORDS + sizeof(uint16_t) * HS_WORDS;
 
 __device__ __forceinline__ uint32_t hs_block_sum(uint32_t v, uint32_t* s_warp) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -109,7 +109,7 @@ k_heavy_smem_symbolic(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __r
 // are zeroed here, range by range, once the ranks are known).  Returns nnz of the row.
 __device__ __forceinline__ uint32_t hs_numeric_row(const DevCsr& a, const DevCsr& b, int64_t row_begin, uint32_t r,
                                                    int64_t cbase, int32_t* __restrict__ c_col,
-                                                   double* __restrict__ c_val, uint32_t* bm, uint32_t* coarse,
+                                                   double* __restrict__ c_val, uint32_t* bm, uint16_t* rank16,
                                                    uint32_t* s_warp) {
     const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
     uint32_t pass_base = 0;  // outputs of the column ranges already done
@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t hs_numeric_row(const DevCsr& a, const DevCsr
         const uint32_t words = (uint32_t)((c1 - c0 + 31) / 32);
         const uint32_t groups = (words + HS_GROUP - 1) / HS_GROUP;
         hs_set_bits(a, b, a_begin, a_end, bm, words, (uint32_t)c0, (uint32_t)c1);
-        // ranks: coarse[g] = outputs before group g (within the whole row)
+        // ranks: rank16[w] = outputs of this column range before word w (block scan over groups of 8 words)
         uint32_t run = pass_base;
         for (uint32_t gb = 0; gb < groups; gb += HS_THREADS) {
             const uint32_t g = gb + threadIdx.x;
@@ -132,7 +132,17 @@ __device__ __forceinline__ uint32_t hs_numeric_row(const DevCsr& a, const DevCsr
             }
             uint32_t total;
             const uint32_t ex = hs_block_excl_scan(s, s_warp, total);
-            if (g < groups) coarse[g] = run + ex;
+            if (g < groups) {
+                uint32_t before = run + ex - pass_base;   // < 65536: a row of this bin has at most 65536 products
+#pragma unroll
+                for (int j = 0; j < HS_GROUP; ++j) {
+                    const uint32_t w = g * HS_GROUP + j;
+                    if (w < words) {
+                        rank16[w] = (uint16_t)before;
+                        before += __popc(bm[w]);
+                    }
+                }
+            }
             run += total;
         }
         for (uint32_t i = pass_base + threadIdx.x; i < run; i += HS_THREADS) c_val[cbase + i] = 0.0;
@@ -141,9 +151,7 @@ __device__ __forceinline__ uint32_t hs_numeric_row(const DevCsr& a, const DevCsr
         for (uint32_t w = threadIdx.x; w < words; w += HS_THREADS) {
             uint32_t bits = bm[w];
             if (bits) {
-                uint32_t pos = coarse[w / HS_GROUP];
-                for (uint32_t w2 = (w / HS_GROUP) * HS_GROUP; w2 < w; ++w2) pos += __popc(bm[w2]);
-                int64_t o = cbase + pos;
+                int64_t o = cbase + pass_base + rank16[w];
                 while (bits) {
                     const int bit = __ffs(bits) - 1;
                     bits &= bits - 1;
@@ -156,8 +164,7 @@ __device__ __forceinline__ uint32_t hs_numeric_row(const DevCsr& a, const DevCsr
             if (c >= (uint32_t)c0 && c < (uint32_t)c1) {
                 const uint32_t d = c - (uint32_t)c0;
                 const uint32_t w = d >> 5;
-                uint32_t pos = coarse[w / HS_GROUP] + __popc(bm[w] & ((1u << (d & 31)) - 1u));
-                for (uint32_t w2 = (w / HS_GROUP) * HS_GROUP; w2 < w; ++w2) pos += __popc(bm[w2]);
+                const uint32_t pos = pass_base + rank16[w] + __popc(bm[w] & ((1u << (d & 31)) - 1u));
                 atomicAdd(&c_val[cbase + pos], __dmul_rn(av, bv));
             }
         });
@@ -174,7 +181,7 @@ k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __re
     extern __shared__ __align__(16) uint32_t s_u32[];
     __shared__ uint32_t s_warp[HS_WARPS];
     const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
-    const uint32_t nnz = hs_numeric_row(a, b, row_begin, r, c_ptr[r], c_col, c_val, s_u32, s_u32 + HS_WORDS, s_warp);
+    const uint32_t nnz = hs_numeric_row(a, b, row_begin, r, c_ptr[r], c_col, c_val, s_u32, reinterpret_cast<uint16_t*>(s_u32 + HS_WORDS), s_warp);
     if (row_nnz_out && threadIdx.x == 0) row_nnz_out[r] = nnz;   // one-shot mode: the slice at c_ptr[r] is a scratch row
 }
 

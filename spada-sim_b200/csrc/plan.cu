@@ -306,6 +306,25 @@ void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const in
                                                                                           t_val, c_ptr, c_col, c_val);
 }
 
+// long scratch rows (the heavy bin in one-shot mode): one CTA per row of the list, a warp per row would leave
+// a tail of 300-iteration warps behind the rest of the copy
+__global__ void __launch_bounds__(256)
+k_copy_rows_list(const uint32_t* __restrict__ rows_list, const int64_t* __restrict__ t_ptr,
+                 const int32_t* __restrict__ t_col, const double* __restrict__ t_val, const int64_t* __restrict__ c_ptr,
+                 int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+    const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
+    const int64_t src = t_ptr[r], dst = c_ptr[r];
+    const int64_t n = c_ptr[r + 1] - dst;
+    for (int64_t j = threadIdx.x; j < n; j += 256) {
+        st_out(c_col + dst + j, t_col[src + j]);
+        st_out(c_val + dst + j, t_val[src + j]);
+    }
+}
+void launch_copy_rows_list(const uint32_t* rows_list, uint32_t n_rows, const int64_t* t_ptr, const int32_t* t_col,
+                           const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
+    if (n_rows > 0) k_copy_rows_list<<<n_rows, 256, 0, s>>>(rows_list, t_ptr, t_col, t_val, c_ptr, c_col, c_val);
+}
+
 // ---------------------------------------------------------------------------------------
 // Fiber store of a B operand (DevCsr::desc): rows re-laid on FIBER_PAD-element boundaries + one packed
 // (start, length) descriptor per row.  HBM traffic: 12 B read + 12 B written per nonzero, once per operand.

@@ -136,7 +136,7 @@ class Engine:
 
     def __init__(self, device: int = -1, accelerator: str = "spada", lane_num: int = 8,
                  block_shape=(1, 10000000), validate: bool = True, stream: Optional[int] = None,
-                 two_phase: bool = False, single_pass: bool = False):
+                 two_phase: bool = False, single_pass: bool = False, serial: bool = False):
         opts = _abi.Opts()
         opts.device = device
         opts.accelerator = _abi.ACCELERATORS[accelerator.lower()]
@@ -144,7 +144,7 @@ class Engine:
         opts.block_shape[0] = min(int(block_shape[0]), 0xffffffff)
         opts.block_shape[1] = min(int(block_shape[1]), 0xffffffff)
         opts.flags = (_abi.FLAG_VALIDATE if validate else 0) | (_abi.FLAG_TWO_PHASE if two_phase else 0) | \
-            (_abi.FLAG_SINGLE_PASS if single_pass else 0)
+            (_abi.FLAG_SINGLE_PASS if single_pass else 0) | (_abi.FLAG_SERIAL if serial else 0)
         opts.stream = stream
         h = C.c_void_p()
         check(lib().spada_b200_create(C.byref(opts), C.byref(h)))
