@@ -266,6 +266,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--two-phase", action="store_true", help="force separate symbolic/numeric passes (exact-size C)")
     ap.add_argument("--single-pass", action="store_true", help="force the fused single pass for rows <= 512 products")
+    ap.add_argument("--gather-waves", type=int, default=1,
+                    help="N > 1: row waves per rank; with more than one, the all-gather of wave j overlaps the computation "
+                         "of wave j+1 (measured at N=2 on rect: 6.9 / 8.7 / 9.3 ms per step for 1 / 2 / 3 waves -- the NCCL "
+                         "copy kernels queue behind the SpGEMM kernels and every wave adds host round trips, so 1 is the default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -306,8 +310,9 @@ def main():
         dist.broadcast_object_list(same, src=0)
         db, _kb = (da, _ka) if same[0] else D.broadcast_csr(eng, b, device)
         db.prepare()                                         # fiber store of the replicated B (not timed, like the broadcast)
-        bounds = D.plan_bounds(eng, da, db, world, device)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        waves = max(1, args.gather_waves)
+        bounds = D.plan_bounds(eng, da, db, world * waves, device)   # shard j * world + r = wave j of rank r
+        lo, hi = 0, 0
         dims = (da.shape[0], da.shape[1], db.shape[1], da.nnz, db.nnz)
     m, k, n, nnz_a, nnz_b = dims
 
@@ -326,23 +331,37 @@ def main():
         dt.free()
 
     gathered = None
+    wave_gather = None
+    if world > 1:
+        cap = torch.zeros(1, dtype=torch.int64, device=device)
+        if rank == 0:
+            cap[0] = eng.flops(da, db)               # nnz(C) <= intermediate products
+        dist.broadcast(cap, src=0)
+        wave_gather = D.WaveGather(m, int(cap[0]), device)
 
     def step():
+        """One pass of the hot path; returns the stats of the engine calls it made."""
         nonlocal gathered
-        res = eng.spgemm_dev(da, db, lo, hi)
-        if world > 1:
+        if world == 1:
+            return [eng.spgemm_dev(da, db, lo, hi).stats()]
+        wave_gather.reset()
+        stats = []
+        for j in range(waves):
+            s_ = j * world + rank
+            res = eng.spgemm_dev(da, db, int(bounds[s_]), int(bounds[s_ + 1]))
+            stats.append(res.stats())
             lp, lc, lv = D.result_views(res, device)
-            gathered = D.allgather_csr(lp, lc, lv, out=gathered)
-        return res
+            wave_gather.add(lp, lc, lv, keepalive=res)       # asynchronous: wave j travels while wave j+1 is computed
+        gathered = wave_gather.finish()
+        return stats
 
     for _ in range(args.warmup):
-        res = step()
-    st0 = res.stats()
-    tot = torch.tensor([st0["products"], st0["nnz_c"]], dtype=torch.int64, device=device)
+        sts = step()
+    tot = torch.tensor([sum(x["products"] for x in sts), sum(x["nnz_c"] for x in sts)], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(tot)
     products, nnz_c = int(tot[0]), int(tot[1])
-    res = None
+    st0 = {"products": sum(x["products"] for x in sts), "bins": sts[0]["bins"]}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.synchronize()
@@ -355,15 +374,12 @@ def main():
     t_wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        res = step()
-        st = res.stats()                      # host-side copy of event timings already taken by the engine
-        launches += st["n_launches"]
-        compute_ms += st["ms_total"]
-        for L in st["launches"]:
-            d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": L["products"], "rows": L["rows"],
-                                                  "grid": L["grid"]})
-            d["ms"] += L["ms"]; d["n"] += 1
-        res = None
+        for st in step():                     # host-side copies of event timings already taken by the engine
+            launches += st["n_launches"]
+            compute_ms += st["ms_total"]
+            for L in st["launches"]:
+                d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": 0, "rows": L["rows"], "grid": L["grid"]})
+                d["ms"] += L["ms"]; d["n"] += 1; d["products"] += L["products"]
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -397,9 +413,9 @@ def main():
             r_ = ser.spgemm_dev(sa, sb, lo, hi)
             if it >= 3:
                 for L in r_.stats()["launches"]:
-                    d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": L["products"], "rows": L["rows"],
+                    d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": 0, "rows": L["rows"],
                                                           "grid": L["grid"]})
-                    d["ms"] += L["ms"]; d["n"] += 1
+                    d["ms"] += L["ms"]; d["n"] += 1; d["products"] += L["products"]
             r_ = None
         sa.free()
         if sb is not sa:
@@ -415,7 +431,7 @@ def main():
     dom_ms = dom["ms"] / dom["n"]
     # algorithmic bytes of one launch = whole-path compulsory bytes x the launch's share of products
     local_products = st0["products"]
-    share = (dom["products"] / local_products) if local_products else 1.0
+    share = (dom["products"] / dom["n"] / local_products) if local_products else 1.0   # products of ONE launch
     if dom["products"] == 0:
         share = 1.0
     dom_bytes = alg_bytes / world * share
@@ -492,7 +508,8 @@ def main():
         "config": {"workload": WORKLOAD_DESC[args.workload], "scale": args.scale, "m": m, "k": k, "n": n,
                    "nnz_a": nnz_a, "nnz_b": nnz_b, "products": products, "nnz_c": nnz_c, "device_transpose_ms": transpose_ms,
                    "l2": "inputs+output larger than L2 (no flush)" if alg_bytes > 4 * 126e6 else "working set near L2 size",
-                   "parallelism": f"rows of A sharded over {world} GPU(s) by equal product count; B replicated; C all-gathered"},
+                   "parallelism": f"rows of A sharded over {world} GPU(s) by equal product count; B replicated; C all-gathered"
+                                  + (f" in {waves} waves overlapped with the computation" if world > 1 and waves > 1 else "")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "compute_only": {"ms_per_step": compute_ms / args.steps,
                          "value": 2.0 * products / (compute_ms / args.steps * 1e-3) / 1e9 if compute_ms else None,

@@ -1258,6 +1258,9 @@ int spgemm_host(spada_b200_t* h, const View* a, const View* b, spada_b200_result
         return rc;
     }
     cudaEventRecord(e1, h->stream);
+    // one-shot operands: re-laying B for a single product costs more than the aligned rows win back
+    // (rect: +2.5 ms of build against -0.1 ms of kernel time), the kernels gather through row_ptr
+    db->fib_ready = true;
     rc = spada_b200_spgemm_dev(h, da, db, 0, UINT64_MAX, out);
     if (rc == 0) {
         cudaEventSynchronize(e1);

@@ -168,3 +168,113 @@ def allgather_csr(local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: t
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return g_ptr, g_col, g_val
+
+
+class WaveGather:
+    """All-gather of C overlapped with the computation, in waves.
+
+    The rows of A are cut into ``world * waves`` contiguous shards of equal product count; shard
+    ``j * world + r`` belongs to rank ``r`` and wave ``j``, so wave j of all ranks together is one
+    contiguous block of C's rows.  As soon as a rank has computed its shard of wave j it starts the
+    exchange of that wave (asynchronous NCCL work on the communicator's own stream) and goes on
+    computing wave j+1: the 3 GB of C cross NVLink while the SMs are busy, instead of after them.
+    Final offsets of a wave are known when the wave starts (everything before it is already counted),
+    so two ranks (and gloo) receive straight into place; more than two ranks on GPUs use NCCL's
+    all-gather on buffers padded to the wave's largest shard and compact them afterwards
+    (see ``allgather_csr`` for the measurements behind that choice).
+
+    ``capacity`` bounds nnz(C) (the intermediate-product count does); the arrays are allocated once and
+    reused across steps.
+    """
+
+    def __init__(self, total_rows: int, capacity: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dev = device
+        self.g_ptr = torch.empty(total_rows + 1, dtype=torch.int64, device=device)
+        self.g_col = torch.empty(max(capacity, 1), dtype=torch.int32, device=device)
+        self.g_val = torch.empty(max(capacity, 1), dtype=torch.float64, device=device)
+        self.reset()
+
+    def reset(self):
+        self.g_ptr[:1] = 0
+        self.rows_done = 0
+        self.nnz_done = 0
+        self.pending = []     # (works, compaction closures, keepalive)
+
+    def add(self, local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: torch.Tensor, keepalive=None):
+        """Starts the exchange of the next wave; (local_ptr, local_col, local_val) is this rank's shard of it
+        (row_ptr starting at 0)."""
+        world, rank, dev, group = self.world, self.rank, self.dev, self.group
+        mine = torch.tensor([local_ptr.numel() - 1, local_col.numel()], dtype=torch.int64, device=dev)
+        sizes = torch.empty(world * 2, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, mine, group=group)
+        sizes = sizes.view(world, 2).cpu()
+        rows, nnzs = sizes[:, 0].tolist(), sizes[:, 1].tolist()
+        row_off = self.rows_done + np.concatenate([[0], np.cumsum(rows)])
+        nnz_off = self.nnz_done + np.concatenate([[0], np.cumsum(nnzs)])
+        if int(nnz_off[-1]) > self.g_col.numel():
+            raise RuntimeError("WaveGather: capacity below nnz(C)")
+        g_ptr, g_col, g_val = self.g_ptr, self.g_col, self.g_val
+        r0, n0 = int(row_off[rank]), int(nnz_off[rank])
+        g_ptr[r0 + 1:r0 + 1 + rows[rank]] = local_ptr[1:] + n0
+        g_col[n0:n0 + nnzs[rank]] = local_col
+        g_val[n0:n0 + nnzs[rank]] = local_val
+        works, after = [], []
+        if world > 2 and dev.type == "cuda":
+            mx, mr = max(max(nnzs), 1), max(max(rows), 1)
+            pad_col = torch.empty((world, mx), dtype=torch.int32, device=dev)
+            pad_val = torch.empty((world, mx), dtype=torch.float64, device=dev)
+            pad_ptr = torch.empty((world, mr), dtype=torch.int64, device=dev)
+            pad_col[rank, :nnzs[rank]] = local_col
+            pad_val[rank, :nnzs[rank]] = local_val
+            pad_ptr[rank, :rows[rank]] = local_ptr[1:] + n0
+            for pad in (pad_col, pad_val, pad_ptr):
+                works.append(dist.all_gather_into_tensor(pad.view(-1), pad[rank], group=group, async_op=True))
+
+            def compact(rows=rows, nnzs=nnzs, row_off=row_off, nnz_off=nnz_off, pads=(pad_ptr, pad_col, pad_val)):
+                pp, pc, pv = pads
+                for r in range(world):
+                    if r == rank:
+                        continue
+                    rs, ns = int(row_off[r]), int(nnz_off[r])
+                    g_ptr[rs + 1:rs + 1 + rows[r]] = pp[r, :rows[r]]
+                    g_col[ns:ns + nnzs[r]] = pc[r, :nnzs[r]]
+                    g_val[ns:ns + nnzs[r]] = pv[r, :nnzs[r]]
+            after.append(compact)
+        else:
+            ops = []
+            my_ptr = g_ptr[r0 + 1:r0 + 1 + rows[rank]]
+            my_col = g_col[n0:n0 + nnzs[rank]]
+            my_val = g_val[n0:n0 + nnzs[rank]]
+            for r in range(world):
+                if r == rank:
+                    continue
+                peer = dist.get_global_rank(group, r) if group else r
+                rs, ns = int(row_off[r]), int(nnz_off[r])
+                if rows[rank]:
+                    ops.append(dist.P2POp(dist.isend, my_ptr, peer, group))
+                if rows[r]:
+                    ops.append(dist.P2POp(dist.irecv, g_ptr[rs + 1:rs + 1 + rows[r]], peer, group))
+                if nnzs[rank]:
+                    ops.append(dist.P2POp(dist.isend, my_col, peer, group))
+                    ops.append(dist.P2POp(dist.isend, my_val, peer, group))
+                if nnzs[r]:
+                    ops.append(dist.P2POp(dist.irecv, g_col[ns:ns + nnzs[r]], peer, group))
+                    ops.append(dist.P2POp(dist.irecv, g_val[ns:ns + nnzs[r]], peer, group))
+            if ops:
+                works = dist.batch_isend_irecv(ops)
+        self.pending.append((works, after, keepalive))
+        self.rows_done = int(row_off[-1])
+        self.nnz_done = int(nnz_off[-1])
+
+    def finish(self):
+        """Waits for every wave; returns (row_ptr, col, val) of the whole C (views of the reused buffers)."""
+        for works, after, _keep in self.pending:
+            for w in works:
+                w.wait()
+            for fn in after:
+                fn()
+        self.pending = []
+        return self.g_ptr[:self.rows_done + 1], self.g_col[:self.nnz_done], self.g_val[:self.nnz_done]

@@ -233,7 +233,8 @@ def test_fiber_store_layouts(spada, oracle, monkeypatch, pad):
         for ka, lb, n in [(3, 4, 900), (16, 16, 1 << 18), (40, 50, 5000), (300, 40, 5000), (300, 230, 5000)]:
             a = random_csr(150, 700, row_nnz=ka, seed=ka + 40)
             b = random_csr(700, n, row_nnz=rng.integers(0, 2 * lb, size=700), seed=lb + 41)
-            run(e, oracle, a, b, exact=False)
+            # resident operands: B's fiber store is built on its first use (the host-level call skips it)
+            check(e.spgemm_dev(e.upload(a), e.upload(b)), oracle.spgemm(a, b, threads=oracle.max_threads()), False)
         a = random_csr(400, 400, density=0.03, seed=42)     # A x A: one operand on both sides
         da = e.upload(a)
         check(e.spgemm_dev(da, da), oracle.spgemm(a, a, threads=oracle.max_threads()), True)
@@ -317,6 +318,10 @@ def test_row_shards_concatenate(engine, oracle):
 def test_configs_scaled(engine, oracle, spada, name, scale, exact):
     a, b = spada.workloads.build(name, scale)
     run(engine, oracle, a, b, exact=exact)
+    # the same product with device-resident operands (what bench.py times): B gathered through its fiber store
+    da = engine.upload(a)
+    db = da if b is a else engine.upload(b)
+    check(engine.spgemm_dev(da, db), oracle.spgemm(a, b, threads=oracle.max_threads()), exact)
 
 
 # ---- full size: properties that need no CPU product ------------------------------------------------
@@ -343,7 +348,11 @@ def test_rect_full_size_properties(engine, spada):
     a, b = spada.workloads.build("rect")
     m, k, nnz_a, products, nnz_c = spada.workloads.KNOWN["rect"]
     assert a.nnz == nnz_a
-    r = engine.spgemm(a, b)
+    da = engine.upload(a)
+    db = engine.transpose(da)              # B = A^T built on the device, resident operands as in bench.py
+    tb = db.to_scipy()
+    assert np.array_equal(tb.indptr, b.indptr) and np.array_equal(tb.indices, b.indices) and np.array_equal(tb.data, b.data)
+    r = engine.spgemm_dev(da, db)
     st = r.stats()
     assert st["products"] == products and st["nnz_c"] == nnz_c
     ip, ix, dx = r.to_host()
