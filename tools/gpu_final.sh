@@ -14,7 +14,7 @@ echo "== ncu launch list (rect)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_rect.csv \
   python bench.py --workload rect --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_ll.log 2>&1
 echo "== ncu full: rect sort / heavy / copy kernels, ER fused, Poisson tiny"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_heavy_smem_numeric|k_esc_numeric_warp|k_bitonic_numeric_cta|k_copy_rows" -s 18 -c 9 -f -o gpurun_out/prof_rect_numeric \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_heavy_smem_numeric|k_esc_numeric_warp|k_bitonic_numeric_cta|k_copy_rows" -s 20 -c 10 -f -o gpurun_out/prof_rect_numeric \
   python bench.py --workload rect --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_a.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fused_light" -s 3 -c 1 -f -o gpurun_out/prof_er_fused \
   python bench.py --workload er --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_b.log 2>&1
