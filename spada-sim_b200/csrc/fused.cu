@@ -26,7 +26,11 @@
 
 namespace spada {
 
-constexpr int FUSED_WARPS = 8;  // warps per tile of the tiny-row kernel
+#ifndef SPADA_FUSED_WARPS
+#define SPADA_FUSED_WARPS 8
+#endif
+constexpr int FUSED_WARPS = SPADA_FUSED_WARPS;  // warps per tile of the tiny-row kernel (4 rows each; at most 8: one 32-row scan)
+static_assert(FUSED_WARPS <= 8, "the tile scan covers 32 rows");
 #ifndef SPADA_LIGHT_WARPS
 #define SPADA_LIGHT_WARPS 4
 #endif
@@ -298,14 +302,14 @@ __device__ __forceinline__ void tiny_tile_finish(uint32_t tile, int64_t m, uint3
                                                  unsigned long long* tile_state, int lane, int warp) {
     if (warp == 0) {
         // exclusive scan of the 32 row counts, then the look-back for the tile's base
-        const uint32_t n = s_nnz[lane];
+        const uint32_t n = lane < TINY_TILE ? s_nnz[lane] : 0u;
         uint32_t x = n;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t y = __shfl_up_sync(FULL, x, d);
             if (lane >= d) x += y;
         }
-        s_off[lane] = x - n;
+        if (lane < TINY_TILE) s_off[lane] = x - n;
         const unsigned long long tile_total = __shfl_sync(FULL, x, 31);
         unsigned long long excl = 0;
         if (tile == 0) {

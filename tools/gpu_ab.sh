@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for v in "" "$@"; do
   lib=$PWD/spada-sim_b200/lib/libspada_b200${v:+_$v}.so
-  for w in rect er; do
+  for w in ${AB_WORKLOADS:-rect er}; do
     SPADA_B200_LIB=$lib timeout 600 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 0 2>&1 | tail -1 > gpurun_out/ab.log
     python - <<PY
 import json
