@@ -363,7 +363,8 @@ void launch_heavy_bits(const DevCsr& a, const DevCsr& b, int64_t row_begin, cons
 void launch_heavy_rank(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, uint2* ws, const HeavyPlan& P,
                        uint32_t* row_nnz /* or NULL */, cudaStream_t s);
 void launch_heavy_emit(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, const uint2* ws,
-                       const HeavyPlan& P, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+                       const HeavyPlan& P, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                       const uint32_t* row_nnz = nullptr);
 void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
                         const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
                         uint32_t wave_hi, const uint2* ws, const HeavyPlan& P, const int64_t* c_ptr, double* c_val,

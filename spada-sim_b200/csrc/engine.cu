@@ -67,6 +67,8 @@ struct spada_b200 {
                                    // only), 0 no fiber store, 1 descriptors only, 16 always pad
     int64_t heavy_smem_cols = 1ll << 20;  // widest B whose heavy rows use the shared-memory bitmap (one column-range pass
                                    // per 2^20 columns; SPADA_B200_HEAVY_SMEM_COLS); wider: the item path of the huge bin
+    bool huge_oneshot = false;     // SPADA_B200_HUGE_ONESHOT=1: the same for the huge bin (experimental: pays only when the
+                                   // bitmaps need several waves; needs 12 B of scratch per product of those rows)
     bool heavy_oneshot = true;     // heavy bin in scratch mode: bitmap + ranks + values in ONE kernel into a scratch row
     spada_b200_opts opts{};
     PlanCounters* d_ctr = nullptr;
@@ -338,6 +340,7 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         if (const char* e = getenv("SPADA_B200_FIBER_PAD")) h->fiber_pad = atoi(e);
         if (const char* e = getenv("SPADA_B200_HEAVY_SMEM_COLS")) h->heavy_smem_cols = atoll(e);
+        if (const char* e = getenv("SPADA_B200_HUGE_ONESHOT")) h->huge_oneshot = atoi(e) != 0;
         if (const char* e = getenv("SPADA_B200_HEAVY_ONESHOT")) h->heavy_oneshot = atoi(e) != 0;
         if (const char* e = getenv("SPADA_B200_STREAMS")) {
             int v = atoi(e);
@@ -976,13 +979,25 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     for (int bnum = 1; bnum <= 8; ++bnum) sorted_products += pc.bin_products[bnum];
     // heavy bin (shared-memory bitmap, B at most 2^20 columns wide): one kernel per row into a scratch row instead of
     // a symbolic and a numeric kernel around the scan -- one expansion less, 0.39 ms of 8 on the rect config
-    const bool heavy_oneshot = !fused && h->two_phase_mode == 2 && h->heavy_oneshot &&
-                               B.cols <= h->heavy_smem_cols && pc.bin_rows[BIN_HEAVY] > 0;
+    const bool heavy_joins_huge = B.cols > h->heavy_smem_cols;   // wide B: heavy rows take the item path of the huge bin
+    const bool heavy_oneshot = !fused && h->two_phase_mode == 2 && h->heavy_oneshot && !heavy_joins_huge &&
+                               pc.bin_rows[BIN_HEAVY] > 0;
     if (heavy_oneshot) sorted_products += pc.bin_products[BIN_HEAVY];
-    const uint32_t scratch_limit = heavy_oneshot ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS;
+    // huge bin (item path, bitmaps in HBM), opt-in: the same one-shot idea -- bits, ranks, column ids and values of a
+    // wave of rows go into scratch rows in one sweep, instead of a symbolic sweep and a numeric sweep that has to
+    // rebuild the bitmaps of every wave (R-MAT: 263 ms of 830).  Costs 12 B of scratch per product of those rows
+    // (R-MAT: 64 GB, which did not fit beside C in the first trial) and a CTA-per-row copy; with a single wave
+    // (rect) nothing is rebuilt anyway and the copy makes it slower (7.47 -> 7.83 ms), hence off by default.
+    const uint64_t huge_rows0 = pc.bin_rows[BIN_HUGE] + (heavy_joins_huge ? pc.bin_rows[BIN_HEAVY] : 0);
+    const uint64_t huge_products0 = pc.bin_products[BIN_HUGE] + (heavy_joins_huge ? pc.bin_products[BIN_HEAVY] : 0);
+    const bool huge_oneshot_fits = !fused && h->two_phase_mode == 2 && h->huge_oneshot && huge_rows0 > 0 &&
+                                   (double)(sorted_products + huge_products0) * 12.0 <= 0.40 * (double)h->dev_total_mem;
+    if (huge_oneshot_fits) sorted_products += huge_products0;
+    const uint32_t scratch_limit = huge_oneshot_fits ? 0xffffffffu : (heavy_oneshot ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS);
     const bool scratch = !fused && h->two_phase_mode == 2 && sorted_products > 0 &&
-                         (double)sorted_products * 12.0 <= 0.30 * (double)h->dev_total_mem;
+                         (double)sorted_products * 12.0 <= (huge_oneshot_fits ? 0.40 : 0.30) * (double)h->dev_total_mem;
     const bool heavy_in_scratch = scratch && heavy_oneshot;
+    const bool huge_in_scratch = scratch && huge_oneshot_fits;
     if (!fused && !scratch && h->two_phase_mode >= 1) {
         uint64_t sorted_rows = 0;
         for (int bnum = 1; bnum <= 8; ++bnum) {
@@ -1010,7 +1025,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         TRY(dalloc(h, &d_tcol, (size_t)sorted_products));
         TRY(dalloc(h, &d_tval, (size_t)sorted_products));
         begin_rec("scratch_ptr", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
-        launch_mask_sorted(d_flops, m, heavy_in_scratch ? scratch_limit : ESC_MAX_PRODUCTS, d_masked, s);
+        launch_mask_sorted(d_flops, m, scratch_limit, d_masked, s);
         launch_scan_u32_i64(d_masked, m, d_prod_ptr, d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
         kernels += 2;
@@ -1020,8 +1035,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     // huge rows: cut into items, bitmaps for one wave of rows at a time
     // The shared-memory bitmap of the heavy bin covers 2^20 columns per pass; for wider B the heavy rows
     // join the huge rows on the item path (measured on R-MAT, n = 2^21: two passes per row lose to it).
-    const bool heavy_in_smem = B.cols <= h->heavy_smem_cols;
-    if (!heavy_in_smem && !heavy_in_scratch) {   // bins 9 and 10 are adjacent in perm[]: one combined list
+    if (heavy_joins_huge) {   // bins 9 and 10 are adjacent in perm[]: one combined list
         pc.bin_rows[BIN_HUGE] += pc.bin_rows[BIN_HEAVY];
         pc.bin_products[BIN_HUGE] += pc.bin_products[BIN_HEAVY];
         perm_of_bin[BIN_HUGE] = perm_of_bin[BIN_HEAVY];
@@ -1078,6 +1092,16 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
                 if (detail) begin_rec("sym_huge_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum], sb);
                 launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, sb);
                 kernels += 2;
+                if (huge_in_scratch) {   // one shot: the wave's column ids and values go to its scratch rows right away
+                    if (detail) end_rec();
+                    if (detail) begin_rec("num_huge_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum], sb);
+                    launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, d_prod_ptr, d_tcol, d_tval, sb, d_nnz);
+                    if (detail) end_rec();
+                    if (detail) begin_rec("num_huge_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum], sb);
+                    launch_heavy_accum(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
+                                       d_prod_ptr, d_tval, h->sm_count, sb);
+                    kernels += 2;
+                }
             }
         } else if (scratch) {
             snprintf(name, sizeof(name), "sort_pass<%s>", bin_name(bnum));
@@ -1141,6 +1165,11 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
                                   R->col, R->val, s);
             kernels += 1;
         }
+        if (huge_in_scratch) {
+            launch_copy_rows_list(perm_of_bin[BIN_HUGE], pc.bin_rows[BIN_HUGE], d_prod_ptr, d_tcol, d_tval, R->ptr,
+                                  R->col, R->val, s);
+            kernels += 1;
+        }
         CUT(cudaGetLastError());
         kernels += 1;
         end_rec();
@@ -1148,7 +1177,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
         uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
-        if (scratch && (bnum <= 8 || (bnum == BIN_HEAVY && heavy_in_scratch))) continue;
+        if (scratch && (bnum <= 8 || (bnum == BIN_HEAVY && heavy_in_scratch) || (bnum == BIN_HUGE && huge_in_scratch))) continue;
         char name[32];
         snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
         cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);

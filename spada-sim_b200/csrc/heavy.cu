@@ -192,11 +192,13 @@ k_heavy_rank(const uint32_t* __restrict__ rows_list, uint32_t wave_lo, uint2* ws
 // ---- emit: column ids of the row from the bitmap, values zeroed for the accumulation -----------
 __global__ void __launch_bounds__(HEAVY_THREADS)
 k_heavy_emit(const uint32_t* __restrict__ rows_list, uint32_t wave_lo, const uint2* ws, uint32_t words,
-             const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+             const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col, double* __restrict__ c_val,
+             const uint32_t* __restrict__ row_nnz) {
     const uint32_t hrow = wave_lo + blockIdx.x;
     const uint32_t r = rows_list ? rows_list[hrow] : hrow;
     const uint2* w = ws + (size_t)blockIdx.x * words;
-    const int64_t cbase = c_ptr[r], z = c_ptr[r + 1] - cbase;
+    // row_nnz given: c_ptr addresses scratch rows of capacity >= nnz (one-shot mode), only nnz slots are used
+    const int64_t cbase = c_ptr[r], z = row_nnz ? (int64_t)row_nnz[r] : c_ptr[r + 1] - cbase;
     for (int64_t i = threadIdx.x; i < z; i += HEAVY_THREADS) c_val[cbase + i] = 0.0;
     for (uint32_t i = threadIdx.x; i < words; i += HEAVY_THREADS) {
         uint2 e = __ldcg(&w[i]);
@@ -307,8 +309,9 @@ void launch_heavy_rank(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wav
     k_heavy_rank<<<wave_hi - wave_lo, HEAVY_THREADS, 0, s>>>(rows_list, wave_lo, ws, P.words, row_nnz);
 }
 void launch_heavy_emit(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, const uint2* ws,
-                       const HeavyPlan& P, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
-    k_heavy_emit<<<wave_hi - wave_lo, HEAVY_THREADS, 0, s>>>(rows_list, wave_lo, ws, P.words, c_ptr, c_col, c_val);
+                       const HeavyPlan& P, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
+                       const uint32_t* row_nnz) {
+    k_heavy_emit<<<wave_hi - wave_lo, HEAVY_THREADS, 0, s>>>(rows_list, wave_lo, ws, P.words, c_ptr, c_col, c_val, row_nnz);
 }
 void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
                         const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
