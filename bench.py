@@ -403,6 +403,7 @@ def main():
     # SPADA_B200_FLAG_SERIAL over the same device arrays, 3 warm-up + 5 recorded steps, CUDA events on its stream.
     timing_note = "launch times from the timed region"
     if world == 1:
+        eng.trim()          # hand the first handle's cached blocks back: the second handle needs the same footprint
         ser = pkg.Engine(device=local_rank, validate=False, stream=stream.cuda_stream, two_phase=args.two_phase,
                          single_pass=args.single_pass, serial=True)
         sa = ser.wrap_device(da.shape[0], da.shape[1], da.nnz, *da.device_ptrs(), keepalive=da)

@@ -67,8 +67,7 @@ struct spada_b200 {
                                    // only), 0 no fiber store, 1 descriptors only, 16 always pad
     int64_t heavy_smem_cols = 1ll << 20;  // widest B whose heavy rows use the shared-memory bitmap (one column-range pass
                                    // per 2^20 columns; SPADA_B200_HEAVY_SMEM_COLS); wider: the item path of the huge bin
-    bool huge_oneshot = false;     // SPADA_B200_HUGE_ONESHOT=1: the same for the huge bin (experimental: pays only when the
-                                   // bitmaps need several waves; needs 12 B of scratch per product of those rows)
+    bool huge_oneshot = true;      // the same for the huge bin when its bitmaps need several waves (SPADA_B200_HUGE_ONESHOT=0|1)
     bool heavy_oneshot = true;     // heavy bin in scratch mode: bitmap + ranks + values in ONE kernel into a scratch row
     spada_b200_opts opts{};
     PlanCounters* d_ctr = nullptr;
@@ -156,8 +155,12 @@ int pool_alloc(spada_b200* h, void** p, size_t bytes) {
     if (e != cudaSuccess) {
         cudaGetLastError();
         *p = nullptr;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? SPADA_B200_OOM : SPADA_B200_CUDA_ERROR,
-                    "cudaMalloc(%zu bytes) failed: %s", cap, cudaGetErrorString(e));
+                    "cudaMalloc(%zu bytes) failed: %s (device: %zu MiB free of %zu, this handle holds %zu MiB)", cap,
+                    cudaGetErrorString(e), free_b >> 20, total_b >> 20, h->pool_bytes >> 20);
     }
     h->pool_live[*p] = cap;
     h->pool_bytes += cap;
@@ -983,14 +986,16 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     const bool heavy_oneshot = !fused && h->two_phase_mode == 2 && h->heavy_oneshot && !heavy_joins_huge &&
                                pc.bin_rows[BIN_HEAVY] > 0;
     if (heavy_oneshot) sorted_products += pc.bin_products[BIN_HEAVY];
-    // huge bin (item path, bitmaps in HBM), opt-in: the same one-shot idea -- bits, ranks, column ids and values of a
-    // wave of rows go into scratch rows in one sweep, instead of a symbolic sweep and a numeric sweep that has to
-    // rebuild the bitmaps of every wave (R-MAT: 263 ms of 830).  Costs 12 B of scratch per product of those rows
-    // (R-MAT: 64 GB, which did not fit beside C in the first trial) and a CTA-per-row copy; with a single wave
-    // (rect) nothing is rebuilt anyway and the copy makes it slower (7.47 -> 7.83 ms), hence off by default.
+    // huge bin (item path, bitmaps in HBM) when the bitmaps of its rows need more than one wave of workspace: the same
+    // one-shot idea -- bits, ranks, column ids and values of a wave go into scratch rows in one sweep, instead of a
+    // symbolic sweep and a numeric sweep that has to rebuild the bitmaps of every wave (R-MAT: 830 -> 581 ms).
+    // Costs 12 B of scratch per product of those rows (R-MAT: 64 GB) and a CTA-per-row copy; with a single wave
+    // (rect) nothing is rebuilt and the extra copy only costs (7.47 -> 7.83 ms), so single-wave cases keep two sweeps.
     const uint64_t huge_rows0 = pc.bin_rows[BIN_HUGE] + (heavy_joins_huge ? pc.bin_rows[BIN_HEAVY] : 0);
     const uint64_t huge_products0 = pc.bin_products[BIN_HUGE] + (heavy_joins_huge ? pc.bin_products[BIN_HEAVY] : 0);
-    const bool huge_oneshot_fits = !fused && h->two_phase_mode == 2 && h->huge_oneshot && huge_rows0 > 0 &&
+    const bool huge_multi_wave =
+        huge_rows0 > 0 && heavy_plan_sizes((uint32_t)huge_rows0, huge_products0, B.cols, h->heavy_ws_budget).n_waves > 1;
+    const bool huge_oneshot_fits = !fused && h->two_phase_mode == 2 && h->huge_oneshot && huge_multi_wave &&
                                    (double)(sorted_products + huge_products0) * 12.0 <= 0.40 * (double)h->dev_total_mem;
     if (huge_oneshot_fits) sorted_products += huge_products0;
     const uint32_t scratch_limit = huge_oneshot_fits ? 0xffffffffu : (heavy_oneshot ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS);
@@ -1065,6 +1070,7 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
         if (!rows) continue;
         char name[32];
         snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
+        if (bnum == BIN_HUGE && huge_in_scratch) snprintf(name, sizeof(name), "oneshot<%s>", bin_name(bnum));
         cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);   // the stream of this bin
         if (bnum == BIN_HEAVY && heavy_in_scratch) {
             snprintf(name, sizeof(name), "oneshot<%s>", bin_name(bnum));

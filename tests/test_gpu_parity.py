@@ -275,6 +275,26 @@ def test_transposed_operand_feeds_the_hot_path(engine, oracle, cari, spada):
     check(engine.spgemm_dev(da, db), oracle.spgemm(g.a, g.b, threads=oracle.max_threads()), False)
 
 
+def test_huge_bin_in_waves(spada, oracle, monkeypatch):
+    # a 1 MiB bitmap workspace forces the huge bin through a dozen waves: one-shot sweeps into scratch rows
+    # (default) and the two-sweep path (symbolic, then numeric rebuilding every wave's bitmaps) must agree
+    if spada.device_count() == 0:
+        pytest.skip("no CUDA device")
+    a = random_csr(257, 600, row_nnz=300, seed=61)
+    b = random_csr(600, 200000, row_nnz=230, seed=62)
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    monkeypatch.setenv("SPADA_B200_HEAVY_WS_MB", "1")
+    for oneshot in ("1", "0"):
+        monkeypatch.setenv("SPADA_B200_HUGE_ONESHOT", oneshot)
+        e = spada.Engine(two_phase=True)
+        try:
+            r = e.spgemm(a, b)
+            assert list(r.stats()["bins"]) == ["huge"]
+            check(r, ref, False)
+        finally:
+            e.close()
+
+
 def test_usize_layout_matches(engine, oracle):
     a = random_csr(300, 200, density=0.05, seed=16)
     b = random_csr(200, 250, density=0.05, seed=17)
