@@ -115,6 +115,15 @@ __device__ __forceinline__ ItemRange item_range(const DevCsr& a, int64_t row_beg
     return R;
 }
 
+// A entries one warp takes per turn inside an item: the whole batch of 32 when the item is long enough to keep all
+// eight warps busy, fewer otherwise.  Items are cut by product count, so an item whose B rows are long (R-MAT hubs,
+// cari) has only 32 A entries: with 32 per warp seven warps of eight sat idle (ncu on R-MAT: warps active 9-15 %,
+// issue active 3 %); the products of a few entries are still dealt over all 32 lanes.
+__device__ __forceinline__ int item_sub_batch(const ItemRange& R) {
+    const int64_t per_warp = (R.a1 - R.a0 + HEAVY_WARPS - 1) / HEAVY_WARPS;
+    return per_warp >= 32 ? 32 : (per_warp < 1 ? 1 : (int)per_warp);
+}
+
 // ---- bits: every product sets its column's bit in the row's bitmap ------------------------------
 __global__ void __launch_bounds__(HEAVY_THREADS)
 k_heavy_bits(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list,
@@ -135,14 +144,16 @@ k_heavy_bits(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__
         // Test the word with a plain load first: the load brings the sector into L2 with full
         // memory-level parallelism (an atomic that misses L2 is served far more slowly), and bits
         // that are already set need no atomic at all (the OR is idempotent).
-        for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
+        const int sub = item_sub_batch(R);
+        for (int64_t pb = R.a0 + (int64_t)warp * sub; pb < R.a1; pb += (int64_t)HEAVY_WARPS * sub) {
+            const int64_t pe = pb + sub < R.a1 ? pb + sub : R.a1;   // this warp's entries of the turn
             int bt;
             auto set_bit = [&](uint32_t c) {
                 uint32_t bit = 1u << (c & 31);
                 if (!(__ldcg(&w[c >> 5].x) & bit)) atomicOr(&w[c >> 5].x, bit);
             };
             expand_batch_long<false, true, true>(
-                a, b, pb + lane, R.a1, lane, 0, bt, long_len, [&](int, uint32_t c, double, double) { set_bit(c); },
+                a, b, pb + lane, pe, lane, 0, bt, long_len, [&](int, uint32_t c, double, double) { set_bit(c); },
                 [&](int64_t bsj, int lj, double) {
                     if (tma_ok)
                         stream_row_tma<false>(b, bsj, lj, lane, s_col[warp], nullptr, &s_bar[warp], phase,
@@ -237,7 +248,9 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
         double pend_v = 0.0;
         uint32_t pend_pos = 0;
         bool pend = false;
-        for (int64_t pb = R.a0 + warp * 32; pb < R.a1; pb += HEAVY_THREADS) {
+        const int sub = item_sub_batch(R);
+        for (int64_t pb = R.a0 + (int64_t)warp * sub; pb < R.a1; pb += (int64_t)HEAVY_WARPS * sub) {
+            const int64_t pe = pb + sub < R.a1 ? pb + sub : R.a1;   // this warp's entries of the turn
             int bt;
             auto add = [&](uint32_t c, double prod) {
                 uint2 e = __ldcg(&w[c >> 5]);
@@ -249,7 +262,7 @@ k_heavy_accum(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict_
                 pend_v = prod;
             };
             expand_batch_long<true, true, true>(
-                a, b, pb + lane, R.a1, lane, 0, bt, long_len,
+                a, b, pb + lane, pe, lane, 0, bt, long_len,
                 [&](int, uint32_t c, double av, double bv) { add(c, __dmul_rn(av, bv)); },
                 [&](int64_t bsj, int lj, double aj) {
                     if (tma_ok)
