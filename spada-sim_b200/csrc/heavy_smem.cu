@@ -63,9 +63,15 @@ __device__ __forceinline__ uint32_t hs_block_excl_scan(uint32_t v, uint32_t* s_w
 template <bool NUMERIC, typename F>
 __device__ __forceinline__ void hs_stream(const DevCsr& a, const DevCsr& b, int64_t a_begin, int64_t a_end, F&& f) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    for (int64_t pb = a_begin + warp * 32; pb < a_end; pb += HS_THREADS) {
+    // A entries one warp takes per turn: 32 when the row keeps all 32 warps busy that way, fewer otherwise -- a row of
+    // 60 entries with long B rows (R-MAT) would occupy two warps of the CTA's 32; the products of a few entries are
+    // still dealt over all lanes
+    const int64_t per_warp = (a_end - a_begin + HS_WARPS - 1) / HS_WARPS;
+    const int sub = per_warp >= 32 ? 32 : (per_warp < 1 ? 1 : (int)per_warp);
+    for (int64_t pb = a_begin + (int64_t)warp * sub; pb < a_end; pb += (int64_t)HS_WARPS * sub) {
+        const int64_t pe = pb + sub < a_end ? pb + sub : a_end;
         int bt;
-        expand_batch<NUMERIC, true>(a, b, pb + lane, a_end, lane, 0, bt,
+        expand_batch<NUMERIC, true>(a, b, pb + lane, pe, lane, 0, bt,
                                     [&](int, uint32_t c, double av, double bv) { f(c, av, bv); });
     }
 }
