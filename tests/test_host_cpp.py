@@ -158,3 +158,58 @@ def test_cpp_cli_cari_transcript(binary, tmp_path, oracle, cari, spada, acc, ext
         assert [int(x) for x in m.group(2).split(", ")] == cj[cp[r]:cp[r] + 5].tolist()
         vals = np.array([float(x) for x in m.group(3).split(", ")])
         assert np.allclose(vals, cx[cp[r]:cp[r] + 5], rtol=1e-12, atol=0)
+
+
+SINK_DRIVER = r"""
+#include "spada_host.hpp"
+#include <cstdio>
+#include <cstdlib>
+using namespace spada_host;
+// argv: out.mtx n_cols  ; stdin: rows, then per row: n, then n x (col value-bits-as-u64)
+int main(int argc, char** argv) {
+    size_t n_rows;
+    if (std::scanf("%zu", &n_rows) != 1) return 3;
+    std::vector<CsrRow> rows(n_rows);
+    for (size_t r = 0; r < n_rows; ++r) {
+        size_t n;
+        if (std::scanf("%zu", &n) != 1) return 3;
+        rows[r].rowptr = r;
+        for (size_t j = 0; j < n; ++j) {
+            unsigned long long c, bits;
+            if (std::scanf("%llu %llu", &c, &bits) != 2) return 3;
+            double v;
+            std::memcpy(&v, &bits, 8);
+            rows[r].indptr.push_back(c);
+            rows[r].data.push_back(v);
+        }
+    }
+    std::printf("%s\n", dump_result(argv[1], rows, std::strtoull(argv[2], nullptr, 10)).c_str());
+    return 0;
+}
+"""
+
+
+def test_cpp_result_sink_matches_python(tmp_path, spada):
+    # SPADA_B200_DUMP_C in the compiled host: same file (every f64 round-trips) and same digest line as main.py
+    main = __import__("importlib").import_module("spada-sim_b200.main")
+    (tmp_path / "drv.cpp").write_text(SINK_DRIVER)
+    exe = tmp_path / "drv"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", HOST, "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                           str(tmp_path / "drv.cpp"), "-L", os.path.join(ROOT, "spada-sim_b200", "lib"), "-lspada_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "spada-sim_b200", "lib")])
+    rng = np.random.default_rng(5)
+    c = sp.random(41, 29, density=0.25, format="csr", random_state=rng); c.sort_indices()
+    c.data = rng.uniform(-1, 1, c.nnz) * 10.0 ** rng.integers(-200, 200, c.nnz)
+    text = [str(c.shape[0])]
+    for r in range(c.shape[0]):
+        s0, s1 = c.indptr[r], c.indptr[r + 1]
+        text.append(str(s1 - s0))
+        text += [f"{int(j)} {int(b)}" for j, b in zip(c.indices[s0:s1], c.data[s0:s1].view(np.uint64))]
+    p = subprocess.run([str(exe), str(tmp_path / "c_cpp.mtx"), str(c.shape[1])], input="\n".join(text), text=True,
+                       capture_output=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    line_py = main.dump_result(str(tmp_path / "c_py.mtx"), c.indptr, c.indices, c.data, c.shape[1])
+    assert p.stdout.strip() == line_py
+    a = scipy.io.mmread(str(tmp_path / "c_cpp.mtx")).tocsr(); a.sort_indices()
+    assert a.shape == c.shape and np.array_equal(a.indptr, c.indptr) and np.array_equal(a.indices, c.indices)
+    assert np.array_equal(a.data.view(np.uint64), c.data.view(np.uint64))
