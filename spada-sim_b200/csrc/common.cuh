@@ -13,10 +13,11 @@ constexpr unsigned FULL = 0xffffffffu;
 // choice restated for a GPU, rowwise_perf_adjust.rs:121-252 / scheduler.rs:729-753: R rows
 // share a window of L lanes; here a bin fixes how many lanes cooperate on one row).
 //   bin 0          p == 0                 nothing to do, nnz = 0
-//   bin 1          p <= 32                one warp per row, products sorted in registers
+//   bin 1          p <= 32                four rows per warp (8 lanes x 4 keys each), products sorted in registers
 //   bin 2..5       p <= 64,128,256,512    one warp per row, E = N/32 keys per lane
 //   bin 6..8       p <= 1024,2048,4096    one CTA per row, register chunk sorts merged in shared memory
-//   bin 9          p <= 65536             one CTA (1024 threads) per row, bitmap + ranks in shared memory
+//   bin 9          p <= 65536             one CTA (1024 threads) per row, bitmap + ranks in shared memory (B up to 2^21
+//                                         columns wide; wider: joins bin 10)
 //   bin 10         p  > 65536             items of ~8192 products over the grid, bitmap + ranks in HBM/L2
 constexpr int NUM_BINS = 11;
 constexpr int BIN_EMPTY = 0;

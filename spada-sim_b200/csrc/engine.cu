@@ -1,13 +1,17 @@
 // engine.cu -- host side of the engine and the C ABI of include/spada_b200.h.
 //
-// One handle owns a device, a stream and a caching device-memory pool (freed blocks are kept and
-// handed out again by size, so steady-state calls never reach the driver allocator; all work is
-// ordered on the one stream, which makes immediate reuse safe).  A call to
-// spada_b200_spgemm_dev runs the four stages of the path on that stream:
-//   1. flop count + binning      (plan.cu)   -- one host read-back of ~200 bytes of counters
-//   2. symbolic, one launch/bin  (esc.cu, heavy.cu)
-//   4. exclusive scan -> row_ptr (plan.cu)   -- one host read-back of nnz(C) to size C
-//   3. numeric, one launch/bin   (esc.cu, heavy.cu)
+// One handle owns a device, a stream (plus two side streams that are always joined back into it) and a
+// caching device-memory pool (freed blocks are kept and handed out again by size, so steady-state calls
+// never reach the driver allocator; everything is ordered on the one stream by the time a block is freed,
+// which makes immediate reuse safe).  A call to spada_b200_spgemm_dev runs the stages of the path:
+//   1. flop count + binning        (plan.cu)   -- one host read-back of ~200 bytes of counters
+//   then, picked per operand ("Engine modes"):
+//   single pass   rows <= 512 products expanded, sorted, reduced and placed by a look-back scan in ONE kernel
+//                 (fused.cu); heavier rows: symbolic kernels before it, numeric kernels after it
+//   two phase     2. one pass per bin into a scratch CSR sized by product count (esc.cu, esc_cta_bitonic.cu,
+//                    heavy_smem.cu; the huge bin's bitmap sweeps in heavy.cu)
+//                 4. exclusive scan -> row_ptr (plan.cu)   -- one host read-back of nnz(C) to size C
+//                 3. copy of the scratch rows into C; numeric kernels of whatever was only counted in 2.
 // There is no CPU compute path here: if no CUDA device is present every entry point fails with
 // SPADA_B200_NO_DEVICE.
 #include <cuda_runtime.h>
