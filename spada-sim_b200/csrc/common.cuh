@@ -280,6 +280,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 #endif
 
+// cudaFuncSetAttribute is per device: every launcher that needs more than 48 KB of dynamic shared memory raises the
+// limit the first time it runs on a device (one handle per device, but several devices per process are allowed)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // ---- launchers (implemented in the .cu files, called by engine.cu) ------------------------
 // stage 1
 void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t b_rows, uint32_t* b_len, int64_t row_begin, int64_t m,

@@ -115,10 +115,9 @@ template <typename K, int N>
 static void keep_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm, uint32_t rows,
                         uint32_t* row_nnz, const int64_t* prod_ptr, void* kstore, cudaStream_t s) {
     size_t smem = sizeof(K) * N;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(k_bitonic_symbolic_keep_cta<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
     }
     k_bitonic_symbolic_keep_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(a, b, row_begin, perm, rows, row_nnz, prod_ptr,
                                                                       reinterpret_cast<K*>(kstore));
@@ -128,11 +127,10 @@ static void presorted_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin
                              const int64_t* c_ptr, int32_t* c_col, double* c_val, const int64_t* prod_ptr,
                              const void* kstore, cudaStream_t s) {
     size_t smem = (sizeof(K) + sizeof(double)) * N;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(k_bitonic_numeric_presorted_cta<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
-        attr = true;
     }
     k_bitonic_numeric_presorted_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(
         a, b, row_begin, perm, rows, c_ptr, c_col, c_val, prod_ptr, reinterpret_cast<const K*>(kstore));
@@ -170,10 +168,9 @@ static void bitonic_numeric_launch(const DevCsr& a, const DevCsr& b, int64_t row
                                    uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
                                    uint32_t* nnz_out) {
     size_t smem = (sizeof(K) + sizeof(double)) * N;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(k_bitonic_numeric_cta<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
     }
     k_bitonic_numeric_cta<K, N><<<rows, ESC_CTA_THREADS, smem, s>>>(a, b, row_begin, perm, rows, c_ptr, c_col, c_val,
                                                                     nnz_out);

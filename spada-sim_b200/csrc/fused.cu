@@ -575,10 +575,9 @@ static void fused_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, in
     constexpr int RPW = fused_rpw(NMAX);
     constexpr int TILE_ROWS = LIGHT_WARPS * RPW;
     size_t smem = (sizeof(K) + sizeof(double)) * NMAX * TILE_ROWS;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(k_fused_light<K, NMAX, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
     }
     size_t tiles = (size_t)((m + TILE_ROWS - 1) / TILE_ROWS);
     cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);

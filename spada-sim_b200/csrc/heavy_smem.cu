@@ -194,11 +194,10 @@ k_heavy_smem_numeric(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __re
 void launch_heavy_smem_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
                                 uint32_t n_rows, uint32_t* row_nnz, cudaStream_t s) {
     if (n_rows == 0) return;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(k_heavy_smem_symbolic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM);
         cudaFuncSetAttribute(k_heavy_smem_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM);
-        attr = true;
     }
     k_heavy_smem_symbolic<<<n_rows, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, rows_list, n_rows, row_nnz);
 }
@@ -207,11 +206,10 @@ void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_beg
                                uint32_t n_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
                                uint32_t* row_nnz_out) {
     if (n_rows == 0) return;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(k_heavy_smem_symbolic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM);
         cudaFuncSetAttribute(k_heavy_smem_numeric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM);
-        attr = true;
     }
     k_heavy_smem_numeric<<<n_rows, HS_THREADS, HS_SMEM, s>>>(a, b, row_begin, rows_list, n_rows, c_ptr, c_col, c_val,
                                                              row_nnz_out);
