@@ -62,11 +62,15 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size"]
 out = [f"# {TAG} -- `ncu --set full --clock-control none --import-source on` summaries\n"]
-for rep, wl in (("prof_rect_heavy", "rect"), ("prof_rect_numeric", "rect"), ("prof_er_fused", "er"), ("prof_poisson_tiny", "poisson")):  # noqa
+NOTES = {"prof_rmat_huge": "captured BEFORE the sub-batch change of heavy.cu (`item_sub_batch`): the evidence for it -- "
+                           "one warp of eight busy per item, 9-15 % active warps, 3 % issue slots"}
+for rep, wl in (("prof_rect_heavy", "rect"), ("prof_rect_numeric", "rect"), ("prof_er_fused", "er"), ("prof_poisson_tiny", "poisson"),
+                ("prof_rmat_huge", "rmat_before_sub_batch")):  # noqa
     p = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(p): continue
     recs, units = ncu_raw(p)
     out.append(f"## {rep}.ncu-rep ({wl})\n")
+    if rep in NOTES: out.append(NOTES[rep] + "\n")
     out.append("| kernel | " + " | ".join(w.split(".")[0].replace("__", " ") for w in want) + " |")
     out.append("|---|" + "---|" * len(want))
     for r in recs:
