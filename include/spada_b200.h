@@ -44,9 +44,9 @@ extern "C" {
 #define SPADA_B200_API
 #endif
 
-#define SPADA_B200_ABI_VERSION 1
-#define SPADA_B200_MAX_BINS 16
-#define SPADA_B200_MAX_LAUNCHES 48
+#define SPADA_B200_ABI_VERSION 2
+#define SPADA_B200_MAX_BINS 32
+#define SPADA_B200_MAX_LAUNCHES 64
 
 typedef enum spada_b200_status {
     SPADA_B200_OK = 0,

@@ -12,8 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPADA_B200_LIB lets a tuning run load an alternative build of the same library (never a different backend)
 LIB_PATH = os.environ.get("SPADA_B200_LIB") or os.path.join(_HERE, "lib", "libspada_b200.so")
 
-MAX_BINS = 16
-MAX_LAUNCHES = 48
+MAX_BINS = 32
+MAX_LAUNCHES = 64
+ABI_VERSION = 2
 
 STATUS = {0: "OK", 1: "INVALID_ARG", 2: "UNSORTED_INPUT", 3: "DIM_MISMATCH", 4: "CUDA_ERROR",
           5: "NCCL_ERROR", 6: "OOM", 7: "NO_DEVICE", 8: "TOO_LARGE"}

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
+
 namespace spada {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -16,15 +18,15 @@ constexpr unsigned FULL = 0xffffffffu;
 //   bin 1          p <= 32                four rows per warp (8 lanes x 4 keys each), products sorted in registers
 //   bin 2..5       p <= 64,128,256,512    one warp per row, E = N/32 keys per lane
 //   bin 6..8       p <= 1024,2048,4096    one CTA per row, register chunk sorts merged in shared memory
-//   bin 9          p <= 65536             one CTA (1024 threads) per row, bitmap + ranks in shared memory (B up to 2^21
-//                                         columns wide; wider: joins bin 10)
-//   bin 10         p  > 65536             items of ~8192 products over the grid, bitmap + ranks in HBM/L2
-constexpr int NUM_BINS = 11;
+//   bin 8+L        p <= 4096 * 2^L        LONG rows (L = 1..20): K-tiled into chunks of 4096 products, every chunk sorted
+//                                         by one CTA, the chunks merged pairwise in L levels (longrow.cu) -- the
+//                                         reference's partial rows + merge tree (scheduler.rs:381-480, 820-920)
+constexpr int NUM_BINS = 29;
 constexpr int BIN_EMPTY = 0;
-constexpr int BIN_HEAVY = 9;
-constexpr int BIN_HUGE = 10;
+constexpr int BIN_LONG0 = 9;            // first long bin (two chunks, one merge level)
 constexpr uint32_t ESC_MAX_PRODUCTS = 4096;
-constexpr uint32_t HEAVY_MAX_PRODUCTS = 65536;
+constexpr int LONG_UNIT_LOG = 12;
+constexpr int LONG_UNIT = 1 << LONG_UNIT_LOG;   // products per chunk of a long row = outputs per merge tile
 
 __host__ __device__ inline int bin_of(uint32_t p) {
     if (p == 0) return 0;
@@ -36,10 +38,18 @@ __host__ __device__ inline int bin_of(uint32_t p) {
     if (p <= 1024) return 6;
     if (p <= 2048) return 7;
     if (p <= 4096) return 8;
-    if (p <= 65536) return 9;
-    return 10;
+    // L = ceil(log2(ceil(p / 4096))) merge levels
+    uint32_t x = (p - 1) >> LONG_UNIT_LOG;   // >= 1
+#ifdef __CUDA_ARCH__
+    return 8 + (32 - __clz((int)x));
+#else
+    int L = 0;
+    while (x) { ++L; x >>= 1; }
+    return 8 + L;
+#endif
 }
-__host__ __device__ inline uint32_t bin_capacity(int b) { return b == 0 ? 0u : (b >= BIN_HEAVY ? 0u : (32u << (b - 1))); }
+__host__ __device__ inline int long_levels(uint32_t p) { return bin_of(p) - 8; }
+__host__ __device__ inline uint64_t bin_capacity(int b) { return b == 0 ? 0ull : (32ull << (b - 1)); }
 
 struct BinTable {
     uint32_t offset[NUM_BINS + 1];  // start of each bin inside perm[]
@@ -54,7 +64,7 @@ struct PlanCounters {
     uint32_t long_rows;      // rows deferred to the CTA-per-row flop counter
     uint32_t invalid_rows;   // validation failures
     uint32_t scan_ticket;    // dynamic tile id of the look-back scan
-    uint32_t pad;
+    uint32_t max_flops;      // largest per-row product count (saturates at 2^32-1)
 };
 
 // ---- device-side CSR view ------------------------------------------------------------
@@ -299,11 +309,22 @@ void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t b_rows, uint32_
                   uint32_t* flops, uint32_t* long_list, PlanCounters* ctr, cudaStream_t s);
 void launch_bin_scatter(const uint32_t* flops, int64_t m, const BinTable& tbl, uint32_t* perm,
                         PlanCounters* ctr, cudaStream_t s);
-void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t limit, uint32_t* out, cudaStream_t s);
-void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const int64_t* t_ptr, const int32_t* t_col,
-                      const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+// scratch CSR of the first pass: rows with lo < products <= hi get `products` slots, the others none
+void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t lo, uint32_t hi, uint32_t* out, cudaStream_t s);
+// Scratch rows -> their final place.  dst[0..n_dst) are the C buffers of every GPU that holds a copy of C (this one
+// first; peers are written through NVLink peer mappings: the all-gather of C fused into the store), dst_off = where
+// this shard's first entry goes inside them.
+struct CopyDst {
+    int32_t* col[8];
+    double* val[8];
+    int n;
+    int64_t off;
+};
+void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t lo, uint32_t hi, const int64_t* t_ptr,
+                      const int32_t* t_col, const double* t_val, const int64_t* c_ptr, const CopyDst& dst,
+                      cudaStream_t s);
 void launch_copy_rows_list(const uint32_t* rows_list, uint32_t n_rows, const int64_t* t_ptr, const int32_t* t_col,
-                           const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s);
+                           const double* t_val, const int64_t* c_ptr, const CopyDst& dst, cudaStream_t s);
 // fiber store of a B operand (see DevCsr::desc): padded row lengths -> (scan) -> starts -> descriptors + aligned copy
 void launch_fiber_lengths(const int64_t* ptr, int64_t rows, uint32_t pad, uint32_t* padded_len, PlanCounters* ctr,
                           cudaStream_t s);
@@ -329,71 +350,59 @@ void launch_widen_i32(const int32_t* src_ptr, int64_t n_ptr, int64_t* dst_ptr, c
 void launch_narrow_result(const int64_t* ptr, int64_t n_ptr, uint64_t* out_ptr, const int32_t* idx,
                           int64_t nnz, uint64_t* out_idx, cudaStream_t s);
 void launch_validate(const DevCsr& a, PlanCounters* ctr, cudaStream_t s);
-// stage 2 / 3, ESC bins (1..8)
+// stages 2+3 in one pass per row, sort bins (1..8): the finished row goes to c_ptr[row] (a scratch row of capacity >=
+// nnz, or the row's final place) and its nnz is recorded in row_nnz_out (nullable)
 int esc_grid(int bin, uint32_t rows);
-void launch_esc_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                         uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
-// row_nnz_out (nullable): the kernel also records every row's nnz (first pass of the scratch mode)
 void launch_esc_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                         uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
                         uint32_t* row_nnz_out = nullptr);
-// two-phase mode with kept keys: symbolic stores each row's sorted (column, arrival) keys at
-// kstore + prod_ptr[row]; numeric reloads them instead of sorting again (bins 1..8)
-void launch_esc_symbolic_keep(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
-                              const uint32_t* perm, uint32_t rows, uint32_t* row_nnz, const int64_t* prod_ptr,
-                              void* kstore, cudaStream_t s);
-void launch_esc_numeric_presorted(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
-                                  const uint32_t* perm, uint32_t rows, const int64_t* c_ptr, int32_t* c_col,
-                                  double* c_val, const int64_t* prod_ptr, const void* kstore, cudaStream_t s);
-void launch_cta_symbolic_keep(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
-                              const uint32_t* perm, uint32_t rows, uint32_t* row_nnz, const int64_t* prod_ptr,
-                              void* kstore, cudaStream_t s);
-void launch_cta_numeric_presorted(int bin, bool wide, const DevCsr& a, const DevCsr& b, int64_t row_begin,
-                                  const uint32_t* perm, uint32_t rows, const int64_t* c_ptr, int32_t* c_col,
-                                  double* c_val, const int64_t* prod_ptr, const void* kstore, cudaStream_t s);
-bool esc_needs_wide_keys(int bin, int64_t b_cols);
-// stage 2 / 3, heavy bin (9): one CTA per row, bitmap in shared memory (heavy_smem.cu)
-void launch_heavy_smem_symbolic(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
-                                uint32_t n_rows, uint32_t* row_nnz, cudaStream_t s);
-// row_nnz_out (nullable): one-shot mode -- c_ptr addresses scratch rows of capacity >= nnz, nnz is recorded
-void launch_heavy_smem_numeric(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
-                               uint32_t n_rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
-                               uint32_t* row_nnz_out = nullptr);
-// stage 2 / 3, huge bin (10): rows are cut into items (~8192 products) spread over the grid (heavy.cu)
-struct HeavyPlan {
-    uint32_t words;      // bitmap words per row = ceil(B.cols / 32)
-    uint32_t wave_rows;  // heavy rows whose bitmaps fit the workspace at once
-    uint32_t n_waves;
-    uint64_t max_items;  // capacity of the item list
-    size_t ws_words;     // uint2 words of workspace
-};
-HeavyPlan heavy_plan_sizes(uint32_t n_rows, uint64_t products, int64_t b_cols, size_t ws_budget_bytes);
-void launch_heavy_items(const DevCsr& a, int64_t row_begin, const uint32_t* rows_list, uint32_t n_rows,
-                        const uint32_t* flops, uint32_t* items_per_row, int64_t* item_off, uint32_t* item_row,
-                        uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s);
-void launch_heavy_bits(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
-                       const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
-                       uint32_t wave_hi, uint2* ws, const HeavyPlan& P, int sm_count, cudaStream_t s);
-void launch_heavy_rank(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, uint2* ws, const HeavyPlan& P,
-                       uint32_t* row_nnz /* or NULL */, cudaStream_t s);
-void launch_heavy_emit(const uint32_t* rows_list, uint32_t wave_lo, uint32_t wave_hi, const uint2* ws,
-                       const HeavyPlan& P, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
-                       const uint32_t* row_nnz = nullptr);
-void launch_heavy_accum(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list,
-                        const uint32_t* flops, const int64_t* item_off, const uint32_t* item_row, uint32_t wave_lo,
-                        uint32_t wave_hi, const uint2* ws, const HeavyPlan& P, const int64_t* c_ptr, double* c_val,
-                        int sm_count, cudaStream_t s);
-// bitonic variant of the CTA-per-row bins 6..8 (esc_cta_bitonic.cu)
-void launch_bitonic_cta_symbolic(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
-                                 uint32_t rows, uint32_t* row_nnz, cudaStream_t s);
+// CTA-per-row bins 6..8 (esc_cta_bitonic.cu)
 void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* perm,
                                 uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
                                 uint32_t* row_nnz_out = nullptr);
+// long rows (bins >= BIN_LONG0), longrow.cu: K-tiled chunk sorts + merge levels + left-to-right sums, all in the
+// oracle's ascending-k order (no atomics).  One WAVE = a contiguous slice of the long-row list whose products fit
+// the two ping-pong buffers.
+struct LongWave {
+    const uint32_t* rows_list;   // the wave's slice of perm[] (long rows, ascending merge-level count)
+    uint32_t n_rows;
+    uint32_t level_lo[24];       // first list index (inside the wave) that takes part in merge level l (1-based)
+    uint32_t level_grid[24];     // upper bound of the merge tiles of level l
+    int max_level;
+    uint64_t unit_bound;         // upper bound of the wave's chunks
+    // workspace (device)
+    uint32_t* p;                 // [n_rows]   products per row
+    uint32_t* u;                 // [n_rows]   chunks per row
+    int64_t* prod_off;           // [n_rows+1] start of the row inside the ping-pong buffers
+    int64_t* unit_off;           // [n_rows+1] first chunk of the row
+    uint32_t* unit_heads;        // [unit_bound] distinct columns that start inside the chunk
+    int64_t* unit_hoff;          // [unit_bound+1]
+    int32_t* col[2];             // ping-pong buffers, one entry per product of the wave
+    double* val[2];
+    uint64_t* tile_state;        // look-back state of the wave's scans
+};
+// aseq[e] (one u32 per nonzero of A, written for long rows only) = arrival number of the first product of entry e
+void launch_long_prefix(const DevCsr& a, int64_t row_begin, const uint32_t* rows_list, uint32_t n_rows,
+                        const uint32_t* b_len, uint32_t* aseq, cudaStream_t s);
+// t_ptr/t_col/t_val: scratch CSR the finished rows are written to; row_nnz: their nnz.  stages (nullable): called
+// around the sort, the merge levels and the sums so the engine can time them.  Returns the kernels launched.
+struct LongStages {
+    std::function<void(const char*, uint32_t)> on;
+    std::function<void()> off;
+};
+uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
+                          const uint32_t* aseq, const LongWave& w, const int64_t* t_ptr, int32_t* t_col, double* t_val,
+                          uint32_t* row_nnz, PlanCounters* ctr, cudaStream_t s, const LongStages* stages = nullptr);
+// shard row pointers shifted by the shard's global offset, written into every GPU's row_ptr (sharded runs)
+struct RowPtrDst {
+    int64_t* ptr[8];
+    int n;
+};
+void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const RowPtrDst& dst, int64_t row_off, cudaStream_t s);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
 void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
                         const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,
                         uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s);
-void setup_kernel_attributes();
 
 }  // namespace spada

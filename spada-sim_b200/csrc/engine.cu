@@ -1,17 +1,17 @@
 // engine.cu -- host side of the engine and the C ABI of include/spada_b200.h.
 //
-// One handle owns a device, a stream (plus two side streams that are always joined back into it) and a
+// One handle owns a device, a stream (plus a side stream that is always joined back into it) and a
 // caching device-memory pool (freed blocks are kept and handed out again by size, so steady-state calls
 // never reach the driver allocator; everything is ordered on the one stream by the time a block is freed,
 // which makes immediate reuse safe).  A call to spada_b200_spgemm_dev runs the stages of the path:
-//   1. flop count + binning        (plan.cu)   -- one host read-back of ~200 bytes of counters
+//   1. flop count + binning        (plan.cu)   -- one host read-back of ~300 bytes of counters
 //   then, picked per operand ("Engine modes"):
 //   single pass   rows <= 512 products expanded, sorted, reduced and placed by a look-back scan in ONE kernel
-//                 (fused.cu); heavier rows: symbolic kernels before it, numeric kernels after it
-//   two phase     2. one pass per bin into a scratch CSR sized by product count (esc.cu, esc_cta_bitonic.cu,
-//                    heavy_smem.cu; the huge bin's bitmap sweeps in heavy.cu)
+//                 (fused.cu); heavier rows: first pass into scratch rows before it, copied into place after it
+//   two phase     2. one pass per bin into a scratch CSR sized by product count (esc.cu, esc_cta_bitonic.cu;
+//                    long rows: chunk sorts + merge levels, longrow.cu)
 //                 4. exclusive scan -> row_ptr (plan.cu)   -- one host read-back of nnz(C) to size C
-//                 3. copy of the scratch rows into C; numeric kernels of whatever was only counted in 2.
+//                 3. copy of the scratch rows into C (and, for sharded runs, into every peer's C)
 // There is no CPU compute path here: if no CUDA device is present every entry point fails with
 // SPADA_B200_NO_DEVICE.
 #include <cuda_runtime.h>
@@ -59,23 +59,17 @@ struct spada_b200 {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // Side streams: the heavy / huge bins (latency bound: one 1024-thread CTA per SM, atomics) are independent of the
-    // sort bins until the row_ptr scan and run beside them on a second stream, joined back into `stream` by events
-    // (rect config: 7.96 -> 7.47 ms per step).  SPADA_B200_STREAMS=3 also moves the CTA-per-row sort bins aside (no
-    // gain measured); SPADA_B200_FLAG_SERIAL / SPADA_B200_STREAMS=1 serialise everything, which is what the
-    // per-launch event times of the stats are meaningful for.
-    cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    int n_streams = 2;
+    // Side stream: the long rows (chunk sorts + merge levels, many small launches) are independent of the sort bins
+    // until the row_ptr scan and run beside them, joined back into `stream` by an event.  SPADA_B200_FLAG_SERIAL puts
+    // everything on the one stream, which is what the per-launch event times of the stats are meaningful for.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int fiber_pad = -1;            // SPADA_B200_FIBER_PAD: -1 auto (16 when rows average >= 6 nonzeros, else descriptors
                                    // only), 0 no fiber store, 1 descriptors only, 16 always pad
-    int64_t heavy_smem_cols = 1ll << 21;  // widest B whose heavy rows use the shared-memory bitmap (one column-range pass per
-                                   // 2^20 columns; SPADA_B200_HEAVY_SMEM_COLS); wider: the item path of the huge bin.
-                                   // Two passes measured on R-MAT (n = 2^21): heavy bin 324 ms against ~400 on the item path
-    bool huge_oneshot = true;      // the same for the huge bin when its bitmaps need several waves (SPADA_B200_HUGE_ONESHOT=0|1)
-    bool heavy_oneshot = true;     // heavy bin in scratch mode: bitmap + ranks + values in ONE kernel into a scratch row
+    size_t long_ws_budget = (size_t)24 << 30;   // ping-pong buffers of one wave of long rows (SPADA_B200_LONG_WS_MB)
     spada_b200_opts opts{};
     PlanCounters* d_ctr = nullptr;
+    PlanCounters* d_ctr_side = nullptr;   // scan tickets of the side stream
     PlanCounters* h_ctr = nullptr;  // pinned
     int64_t* h_scalar = nullptr;    // pinned
     std::vector<cudaEvent_t> events;
@@ -85,8 +79,6 @@ struct spada_b200 {
     std::unordered_map<void*, size_t> pool_live;
     size_t pool_bytes = 0;
     size_t dev_total_mem = 0;
-    int two_phase_mode = 2;   // sort bins in two-phase mode: 0 sort twice, 1 keep the sorted keys, 2 scratch rows + copy
-    size_t heavy_ws_budget = (size_t)2 << 30;  // bitmap workspace for the heavy bin (SPADA_B200_HEAVY_WS_MB)
 };
 
 struct spada_b200_csr {
@@ -198,19 +190,6 @@ cudaEvent_t next_event(spada_b200* h, cudaStream_t on = nullptr) {
     return e;
 }
 
-struct LaunchRec {
-    char name[32];
-    cudaEvent_t e0, e1;
-    uint32_t grid;
-    uint64_t rows, products, nnz;
-    int stage;  // 1 flops, 2 symbolic, 3 numeric, 4 scan
-};
-
-const char* bin_name(int b) {
-    static const char* names[NUM_BINS] = {"empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy", "huge"};
-    return names[b];
-}
-
 int check_csr_args(uint64_t rows, uint64_t cols, uint64_t nnz, const void* indptr, const void* indices,
                    const void* data) {
     if (!indptr) return fail(SPADA_B200_INVALID_ARG, "indptr is NULL");
@@ -241,11 +220,17 @@ int validate_device_csr(spada_b200* h, const DevCsr& d) {
 int make_csr(spada_b200* h, uint64_t rows, uint64_t cols, uint64_t nnz, spada_b200_csr** out, int64_t** ptr,
              int32_t** col, double** val) {
     int rc;
-    if ((rc = dalloc(h, ptr, rows + 1))) return rc;
-    if ((rc = dalloc(h, col, nnz))) return rc;
-    if ((rc = dalloc(h, val, nnz))) return rc;
-    spada_b200_csr* m = new (std::nothrow) spada_b200_csr;
-    if (!m) return fail(SPADA_B200_OOM, "host allocation failed");
+    *ptr = nullptr;
+    *col = nullptr;
+    *val = nullptr;
+    spada_b200_csr* m = nullptr;
+    if ((rc = dalloc(h, ptr, rows + 1)) || (rc = dalloc(h, col, nnz)) || (rc = dalloc(h, val, nnz)) ||
+        !(m = new (std::nothrow) spada_b200_csr)) {
+        dfree(h, *ptr);
+        dfree(h, *col);
+        dfree(h, *val);
+        return rc ? rc : fail(SPADA_B200_OOM, "host allocation failed");
+    }
     m->h = h;
     m->d = DevCsr{*ptr, *col, *val, (int64_t)rows, (int64_t)cols, (int64_t)nnz};
     m->owned = true;
@@ -282,6 +267,27 @@ extern "C" int spada_b200_host_free(void* ptr) {
 }
 
 // ---- handle -------------------------------------------------------------------------------
+static void destroy_handle(spada_b200* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->side) cudaStreamSynchronize(h->side);
+    for (auto& kv : h->pool_free) cudaFree(kv.second);
+    h->pool_free.clear();
+    for (auto& kv : h->pool_live) cudaFree(kv.first);  // objects the caller never freed
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->d_ctr) cudaFree(h->d_ctr);
+    if (h->d_ctr_side) cudaFree(h->d_ctr_side);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->h_scalar) cudaFreeHost(h->h_scalar);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
 extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out) {
     if (!out) return fail(SPADA_B200_INVALID_ARG, "out is NULL");
     *out = nullptr;
@@ -294,6 +300,11 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
     }
     spada_b200* h = new (std::nothrow) spada_b200;
     if (!h) return fail(SPADA_B200_OOM, "host allocation failed");
+    // every early return below releases what has been acquired so far
+    struct Guard {
+        spada_b200* h;
+        ~Guard() { destroy_handle(h); }
+    } guard{h};
     if (opts) h->opts = *opts;
     else {
         h->opts.device = -1;
@@ -314,22 +325,15 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
     if (h->opts.device < 0) {
         CU(cudaGetDevice(&h->device));
     } else {
-        if (h->opts.device >= n) {
-            int bad = h->opts.device;
-            delete h;
-            return fail(SPADA_B200_INVALID_ARG, "device %d out of range (count %d)", bad, n);
-        }
+        if (h->opts.device >= n) return fail(SPADA_B200_INVALID_ARG, "device %d out of range (count %d)", h->opts.device, n);
         h->device = h->opts.device;
     }
     DeviceGuard g(h->device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, h->device));
-    if (prop.major < 10) {
-        int dev = h->device;
-        delete h;
-        return fail(SPADA_B200_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a only", dev, prop.major,
+    if (prop.major < 10)
+        return fail(SPADA_B200_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a only", h->device, prop.major,
                     prop.minor);
-    }
     h->sm_count = prop.multiProcessorCount;
     h->dev_total_mem = prop.totalGlobalMem;
     if (h->opts.stream) {
@@ -341,56 +345,26 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
     {
         int lo_prio = 0, hi_prio = 0;
         cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
-        for (int i = 0; i < 2; ++i) {
-            CU(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, hi_prio));
-            CU(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
-        }
+        CU(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_prio));
+        CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         if (const char* e = getenv("SPADA_B200_FIBER_PAD")) h->fiber_pad = atoi(e);
-        if (const char* e = getenv("SPADA_B200_HEAVY_SMEM_COLS")) h->heavy_smem_cols = atoll(e);
-        if (const char* e = getenv("SPADA_B200_HUGE_ONESHOT")) h->huge_oneshot = atoi(e) != 0;
-        if (const char* e = getenv("SPADA_B200_HEAVY_ONESHOT")) h->heavy_oneshot = atoi(e) != 0;
-        if (const char* e = getenv("SPADA_B200_STREAMS")) {
-            int v = atoi(e);
-            if (v >= 1 && v <= 3) h->n_streams = v;
+        if (const char* e = getenv("SPADA_B200_LONG_WS_MB")) {
+            long mb = atol(e);
+            if (mb > 0) h->long_ws_budget = (size_t)mb << 20;
         }
-        if (h->opts.flags & SPADA_B200_FLAG_SERIAL) h->n_streams = 1;
     }
     CU(cudaMalloc((void**)&h->d_ctr, sizeof(PlanCounters)));
+    CU(cudaMalloc((void**)&h->d_ctr_side, sizeof(PlanCounters)));
+    CU(cudaMemset(h->d_ctr_side, 0, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_ctr, sizeof(PlanCounters)));
     CU(cudaMallocHost((void**)&h->h_scalar, 64));
-    setup_kernel_attributes();
-    if (const char* e = getenv("SPADA_B200_TWO_PHASE_MODE"))
-        h->two_phase_mode = !strcmp(e, "plain") ? 0 : (!strcmp(e, "keys") ? 1 : 2);
-    if (const char* e = getenv("SPADA_B200_HEAVY_WS_MB")) {
-        long mb = atol(e);
-        if (mb > 0) h->heavy_ws_budget = (size_t)mb << 20;
-    }
+    guard.h = nullptr;
     *out = h;
     return 0;
 }
 
-extern "C" void spada_b200_destroy(spada_b200_t* h) {
-    if (!h) return;
-    DeviceGuard g(h->device);
-    cudaStreamSynchronize(h->stream);
-    pool_release_cached(h);
-    for (auto& kv : h->pool_live) cudaFree(kv.first);  // objects the caller never freed
-    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) {
-        if (h->side[i]) {
-            cudaStreamSynchronize(h->side[i]);
-            cudaStreamDestroy(h->side[i]);
-        }
-        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
-    }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    cudaFree(h->d_ctr);
-    cudaFreeHost(h->h_ctr);
-    cudaFreeHost(h->h_scalar);
-    if (h->own_stream) cudaStreamDestroy(h->stream);
-    delete h;
-}
+extern "C" void spada_b200_destroy(spada_b200_t* h) { destroy_handle(h); }
 
 extern "C" int spada_b200_set_stream(spada_b200_t* h, void* cuda_stream) {
     if (!h) return fail(SPADA_B200_INVALID_ARG, "handle is NULL");
@@ -438,30 +412,35 @@ extern "C" int spada_b200_upload(spada_b200_t* h, const spada_csr_view* m, spada
     double* val;
     spada_b200_csr* c;
     if ((rc = make_csr(h, m->rows, m->cols, m->nnz, &c, &ptr, &col, &val))) return rc;
-    // usize row pointers are bit-identical to i64 below 2^63; column ids are narrowed on the device
-    CU(cudaMemcpyAsync(ptr, m->indptr, (m->rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    if (m->nnz) {
-        uint64_t* tmp;
-        if ((rc = dalloc(h, &tmp, m->nnz))) return rc;
-        CU(cudaMemcpyAsync(tmp, m->indices, m->nnz * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-        launch_widen_u64(nullptr, 0, nullptr, tmp, (int64_t)m->nnz, col, h->stream);
-        CU(cudaGetLastError());
-        dfree(h, tmp);
-        CU(cudaMemcpyAsync(val, m->data, m->nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    }
-    CU(cudaStreamSynchronize(h->stream));
-    if (h->opts.flags & SPADA_B200_FLAG_VALIDATE) {
-        // a u64 column id >= 2^31 would alias after narrowing: check on the host side of the copy
-        for (uint64_t i = 0; i < m->nnz; ++i)
-            if (m->indices[i] >= m->cols) {
-                spada_b200_csr_free(c);
-                return fail(SPADA_B200_UNSORTED_INPUT, "column id %llu out of range at position %llu",
-                            (unsigned long long)m->indices[i], (unsigned long long)i);
-            }
-        if ((rc = validate_device_csr(h, c->d))) {
-            spada_b200_csr_free(c);
-            return rc;
+    // every failure below releases the operand (and the temporary) again
+    uint64_t* tmp = nullptr;
+    auto body = [&]() -> int {
+        // usize row pointers are bit-identical to i64 below 2^63; column ids are narrowed on the device
+        CU(cudaMemcpyAsync(ptr, m->indptr, (m->rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        if (m->nnz) {
+            int rc2;
+            if ((rc2 = dalloc(h, &tmp, m->nnz))) return rc2;
+            CU(cudaMemcpyAsync(tmp, m->indices, m->nnz * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+            launch_widen_u64(nullptr, 0, nullptr, tmp, (int64_t)m->nnz, col, h->stream);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(val, m->data, m->nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         }
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->opts.flags & SPADA_B200_FLAG_VALIDATE) {
+            // a u64 column id >= 2^31 would alias after narrowing: check on the host side of the copy
+            for (uint64_t i = 0; i < m->nnz; ++i)
+                if (m->indices[i] >= m->cols)
+                    return fail(SPADA_B200_UNSORTED_INPUT, "column id %llu out of range at position %llu",
+                                (unsigned long long)m->indices[i], (unsigned long long)i);
+            return validate_device_csr(h, c->d);
+        }
+        return 0;
+    };
+    rc = body();
+    dfree(h, tmp);
+    if (rc) {
+        spada_b200_csr_free(c);
+        return rc;
     }
     *out = c;
     return 0;
@@ -482,22 +461,26 @@ extern "C" int spada_b200_upload32(spada_b200_t* h, const spada_csr_view32* m, s
     double* val;
     spada_b200_csr* c;
     if ((rc = make_csr(h, m->rows, m->cols, m->nnz, &c, &ptr, &col, &val))) return rc;
-    int32_t* tmp;
-    if ((rc = dalloc(h, &tmp, m->rows + 1))) return rc;
-    CU(cudaMemcpyAsync(tmp, m->indptr, (m->rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    launch_widen_i32(tmp, (int64_t)m->rows + 1, ptr, h->stream);
-    CU(cudaGetLastError());
-    dfree(h, tmp);
-    if (m->nnz) {
-        CU(cudaMemcpyAsync(col, m->indices, m->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(val, m->data, m->nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    }
-    CU(cudaStreamSynchronize(h->stream));
-    if (h->opts.flags & SPADA_B200_FLAG_VALIDATE) {
-        if ((rc = validate_device_csr(h, c->d))) {
-            spada_b200_csr_free(c);
-            return rc;
+    int32_t* tmp = nullptr;
+    auto body = [&]() -> int {
+        int rc2;
+        if ((rc2 = dalloc(h, &tmp, m->rows + 1))) return rc2;
+        CU(cudaMemcpyAsync(tmp, m->indptr, (m->rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        launch_widen_i32(tmp, (int64_t)m->rows + 1, ptr, h->stream);
+        CU(cudaGetLastError());
+        if (m->nnz) {
+            CU(cudaMemcpyAsync(col, m->indices, m->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(val, m->data, m->nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         }
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->opts.flags & SPADA_B200_FLAG_VALIDATE) return validate_device_csr(h, c->d);
+        return 0;
+    };
+    rc = body();
+    dfree(h, tmp);
+    if (rc) {
+        spada_b200_csr_free(c);
+        return rc;
     }
     *out = c;
     return 0;
@@ -733,19 +716,24 @@ extern "C" int spada_b200_flops(spada_b200_t* h, const spada_b200_csr_t* a, cons
                     (long long)a->d.cols, (long long)b->d.rows);
     DeviceGuard g(h->device);
     int64_t m = a->d.rows;
-    uint32_t *d_flops, *d_long;
-    int rc;
-    if ((rc = dalloc(h, &d_flops, (size_t)m))) return rc;
-    if ((rc = dalloc(h, &d_long, (size_t)(a->d.nnz / 256 + 2)))) return rc;
-    if ((rc = run_flops(h, a->d, b->d, 0, m, d_flops, d_long))) return rc;
+    uint32_t *d_flops = nullptr, *d_long = nullptr;
     std::vector<uint32_t> tmp;
-    if (host_flops && m) {
-        tmp.resize((size_t)m);
-        CU(cudaMemcpyAsync(tmp.data(), d_flops, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
-    }
-    CU(cudaStreamSynchronize(h->stream));
+    auto body = [&]() -> int {
+        int rc;
+        if ((rc = dalloc(h, &d_flops, (size_t)std::max<int64_t>(m, 1)))) return rc;
+        if ((rc = dalloc(h, &d_long, (size_t)(a->d.nnz / 256 + 2)))) return rc;
+        if ((rc = run_flops(h, a->d, b->d, 0, m, d_flops, d_long))) return rc;
+        if (host_flops && m) {
+            tmp.resize((size_t)m);
+            CU(cudaMemcpyAsync(tmp.data(), d_flops, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    };
+    const int rc = body();
     dfree(h, d_flops);
     dfree(h, d_long);
+    if (rc) return rc;
     if (total_products) *total_products = h->h_ctr->total_products;
     if (host_flops)
         for (int64_t i = 0; i < m; ++i) host_flops[i] = tmp[(size_t)i];
@@ -777,9 +765,219 @@ extern "C" int spada_b200_plan_shards(spada_b200_t* h, const spada_b200_csr_t* a
     return 0;
 }
 
+// ---- window report --------------------------------------------------------------------------
+// The shape [R, L/R] every bin runs with (scheduler.rs:729-753: R rows share the L lanes of a window): R = rows
+// that share one cooperative group (a warp or a CTA), lanes = lanes that cooperate on one row.
+static void window_report(const spada_b200* h, const PlanCounters& pc, spada_b200_stats& st) {
+    (void)h;
+    for (int bnum = 0; bnum < NUM_BINS; ++bnum) {
+        uint32_t R = 0, lanes = 0;
+        if (bnum == 1) { R = 4; lanes = 8; }
+        else if (bnum >= 2 && bnum <= 5) { R = 1; lanes = 32; }
+        else if (bnum >= 6) { R = 1; lanes = 256; }
+        st.bin_window_rows[bnum] = pc.bin_rows[bnum] ? R : 0;
+        st.bin_window_lanes[bnum] = pc.bin_rows[bnum] ? lanes : 0;
+    }
+}
+
 // ---- the hot path -------------------------------------------------------------------------
-extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
-                                     uint64_t row_begin, uint64_t row_end, spada_b200_result_t** out) {
+// A product runs in two halves (one ABI call does both; the sharded entry points expose them separately so that the
+// ranks of a multi-GPU run can exchange their nnz in between):
+//   begin   stage 1 (flop count, bins), then every row that is not computed in place goes through ONE pass into a
+//           scratch CSR laid out by product count: sort bins on the main stream, long rows (chunk sorts + merge
+//           levels, longrow.cu) on a side stream; the pass records every row's nnz; row_ptr scan.
+//   finish  C is sized, the scratch rows are copied to their final place -- into this GPU's C and, for a sharded
+//           run, into every peer's C at the shard's global offset (the all-gather fused into the store).
+// Single-pass mode (stencils, uniform graphs): rows <= 512 products are expanded, sorted, reduced and placed by a
+// look-back scan in one kernel (fused.cu) straight into C; only heavier rows take the scratch route.
+struct LaunchRec {
+    char name[32];
+    cudaEvent_t e0, e1;
+    uint32_t grid;
+    uint64_t rows, products, nnz;
+    int stage;  // 1 flops, 2 first pass, 3 placement, 4 scan
+};
+
+static const char* bin_name(int b) {
+    static char names[NUM_BINS][12];
+    static bool init = false;
+    if (!init) {
+        snprintf(names[0], sizeof(names[0]), "empty");
+        for (int i = 1; i < NUM_BINS; ++i) snprintf(names[i], sizeof(names[i]), "%llu", (unsigned long long)bin_capacity(i));
+        init = true;
+    }
+    return names[b];
+}
+
+struct spada_b200_shard {
+    spada_b200* h = nullptr;
+    spada_b200_result* R = nullptr;
+    DevCsr A{}, B{};
+    int64_t row_begin = 0, m = 0;
+    bool fused = false, scratch = false, forked = false, finished = false;
+    PlanCounters pc{};
+    BinTable tbl{};
+    bool identity = false;
+    uint32_t scratch_lo = 0;      // rows with more than this many products go through the scratch CSR
+    uint64_t scratch_products = 0;
+    uint32_t n_long = 0;
+    uint64_t long_products = 0;
+    int max_light_bin = 0;
+    uint64_t light_rows = 0;
+    int64_t nnz_c = 0;
+    // device blocks (pool)
+    uint32_t *d_flops = nullptr, *d_long = nullptr, *d_perm = nullptr, *d_nnz = nullptr, *d_masked = nullptr,
+             *d_blen = nullptr, *d_aseq = nullptr;
+    uint64_t *d_tiles = nullptr, *d_tiles_side = nullptr;
+    int64_t* d_prod_ptr = nullptr;
+    int32_t* d_tcol = nullptr;
+    double* d_tval = nullptr;
+    // long-row wave workspace
+    uint32_t *w_p = nullptr, *w_u = nullptr, *w_heads = nullptr;
+    int64_t *w_prod_off = nullptr, *w_unit_off = nullptr, *w_hoff = nullptr;
+    int32_t* w_col[2] = {nullptr, nullptr};
+    double* w_val[2] = {nullptr, nullptr};
+    std::vector<LaunchRec> recs;
+    cudaStream_t rec_stream = nullptr;
+    uint32_t kernels = 0;
+    cudaEvent_t e_end = nullptr;
+
+    const uint32_t* perm_of(int bin) const { return identity ? nullptr : d_perm + tbl.offset[bin]; }
+    void begin_rec(const char* name, int stage, uint32_t grid, uint64_t rows, uint64_t products, cudaStream_t on = nullptr) {
+        LaunchRec r{};
+        snprintf(r.name, sizeof(r.name), "%s", name);
+        r.stage = stage;
+        r.grid = grid;
+        r.rows = rows;
+        r.products = products;
+        rec_stream = on ? on : h->stream;
+        r.e0 = next_event(h, rec_stream);
+        recs.push_back(r);
+    }
+    void end_rec() { recs.back().e1 = next_event(h, rec_stream); }
+    void release_work() {
+        if (forked) cudaStreamSynchronize(h->side);
+        forked = false;
+        uint32_t** u32s[] = {&d_flops, &d_long, &d_perm, &d_nnz, &d_masked, &d_blen, &d_aseq, &w_p, &w_u, &w_heads};
+        for (auto pp : u32s) { dfree(h, *pp); *pp = nullptr; }
+        uint64_t** u64s[] = {&d_tiles, &d_tiles_side};
+        for (auto pp : u64s) { dfree(h, *pp); *pp = nullptr; }
+        int64_t** i64s[] = {&d_prod_ptr, &w_prod_off, &w_unit_off, &w_hoff};
+        for (auto pp : i64s) { dfree(h, *pp); *pp = nullptr; }
+        dfree(h, d_tcol); d_tcol = nullptr;
+        dfree(h, d_tval); d_tval = nullptr;
+        for (int i = 0; i < 2; ++i) {
+            dfree(h, w_col[i]); w_col[i] = nullptr;
+            dfree(h, w_val[i]); w_val[i] = nullptr;
+        }
+    }
+};
+
+namespace {
+
+// waves of long rows: contiguous slices of the long-row list (ascending merge-level count) whose products fit the
+// ping-pong buffers.  The host knows rows and products per level bin (stage-1 counters), and inside a bin only the
+// bound 4096 * 2^L per row, which is what a bin that has to be cut is planned with.
+struct WavePlan {
+    uint32_t lo, hi;                 // slice of the long list
+    uint64_t products_bound;
+    uint64_t unit_bound;
+    uint32_t level_lo[24];
+    uint32_t level_grid[24];
+    int max_level;
+};
+std::vector<WavePlan> plan_waves(const PlanCounters& pc, uint64_t budget_products) {
+    struct Piece { int level; uint32_t lo, hi; uint64_t pbound, ubound; };
+    std::vector<std::vector<Piece>> waves;
+    std::vector<Piece> cur;
+    uint64_t cur_p = 0;
+    uint32_t idx = 0;
+    auto flush = [&]() {
+        if (!cur.empty()) waves.push_back(cur);
+        cur.clear();
+        cur_p = 0;
+    };
+    for (int bnum = BIN_LONG0; bnum < NUM_BINS; ++bnum) {
+        const uint32_t rows = pc.bin_rows[bnum];
+        if (!rows) continue;
+        const int L = bnum - 8;
+        const uint64_t cap = (uint64_t)LONG_UNIT << L;          // most products a row of this bin can have
+        const uint64_t prods = pc.bin_products[bnum];
+        if (cur_p + prods <= budget_products) {                   // the whole bin joins the open wave (exact count)
+            cur.push_back({L, idx, idx + rows, prods, prods / LONG_UNIT + rows});
+            cur_p += prods;
+        } else if (prods <= budget_products) {                    // the whole bin opens a new wave
+            flush();
+            cur.push_back({L, idx, idx + rows, prods, prods / LONG_UNIT + rows});
+            cur_p = prods;
+        } else {                                                  // the bin is cut by its per-row bound
+            flush();
+            const uint64_t per = std::max<uint64_t>(1, budget_products / cap);
+            for (uint32_t lo = 0; lo < rows; lo += (uint32_t)std::min<uint64_t>(per, rows)) {
+                const uint32_t hi = (uint32_t)std::min<uint64_t>(rows, (uint64_t)lo + per);
+                const uint64_t pb = std::min<uint64_t>(prods, (uint64_t)(hi - lo) * cap);
+                cur.push_back({L, idx + lo, idx + hi, pb, pb / LONG_UNIT + (hi - lo)});
+                cur_p = pb;
+                if (hi < rows) flush();
+            }
+        }
+        idx += rows;
+    }
+    flush();
+    std::vector<WavePlan> out;
+    for (auto& w : waves) {
+        WavePlan P{};
+        P.lo = w.front().lo;
+        P.hi = w.back().hi;
+        P.max_level = w.back().level;
+        for (auto& pc_ : w) {
+            P.products_bound += pc_.pbound;
+            P.unit_bound += pc_.ubound;
+        }
+        for (int l = 1; l <= P.max_level && l < 24; ++l) {
+            uint32_t first = P.hi;
+            uint64_t grid = 0;
+            for (auto& pc_ : w)
+                if (pc_.level >= l) {
+                    first = std::min(first, pc_.lo);
+                    grid += pc_.ubound;
+                }
+            P.level_lo[l] = first - P.lo;
+            P.level_grid[l] = (uint32_t)grid;
+        }
+        out.push_back(P);
+    }
+    return out;
+}
+
+void shard_free(spada_b200_shard* S) {
+    if (!S) return;
+    DeviceGuard g(S->h->device);
+    S->release_work();
+    if (S->R) spada_b200_result_free(S->R);
+    delete S;
+}
+
+#define TRY(x)                \
+    do {                      \
+        if ((rc = (x))) {     \
+            shard_free(S);    \
+            return rc;        \
+        }                     \
+    } while (0)
+#define CUT(expr)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            shard_free(S);                                                                        \
+            return fail(e__ == cudaErrorMemoryAllocation ? SPADA_B200_OOM : SPADA_B200_CUDA_ERROR, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                         \
+    } while (0)
+
+// first half: everything up to the local row_ptr.  force_scratch: sharded runs place every row in the second half.
+int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b, uint64_t row_begin,
+                uint64_t row_end, bool force_scratch, spada_b200_shard** out) {
     if (!h || !a || !b || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
     *out = nullptr;
     if (a->d.cols != b->d.rows)
@@ -794,22 +992,32 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     int rc;
     // owned operands get their fiber store the first time they are used as B (wrapped ones: spada_b200_csr_prepare)
     if (b->owned && !b->fib_ready && (rc = build_fibers(h, const_cast<spada_b200_csr*>(b)))) return rc;
-    const DevCsr& A = a->d;
-    DevCsr Bv = b->d;
+    spada_b200_shard* S = new (std::nothrow) spada_b200_shard;
+    if (!S) return fail(SPADA_B200_OOM, "host allocation failed");
+    S->h = h;
+    S->A = a->d;
+    S->B = b->d;
     if (b->desc) {
-        Bv.desc = b->desc;
+        S->B.desc = b->desc;
         if (b->gcol) {
-            Bv.col = b->gcol;
-            Bv.val = b->gval;
-            Bv.nnz = b->fib_extent;   // extent of the arrays the kernels index (bulk-copy bounds, heavy.cu)
+            S->B.col = b->gcol;
+            S->B.val = b->gval;
+            S->B.nnz = b->fib_extent;
         }
     }
-    const DevCsr& B = Bv;
+    const DevCsr& A = S->A;
+    const DevCsr& B = S->B;
     const int64_t m = (int64_t)(row_end - row_begin);
+    S->m = m;
+    S->row_begin = (int64_t)row_begin;
 
     spada_b200_result* R = new (std::nothrow) spada_b200_result;
-    if (!R) return fail(SPADA_B200_OOM, "host allocation failed");
+    if (!R) {
+        delete S;
+        return fail(SPADA_B200_OOM, "host allocation failed");
+    }
     memset(R, 0, sizeof(*R));
+    S->R = R;
     R->h = h;
     R->rows = (uint64_t)m;
     R->cols = (uint64_t)B.cols;
@@ -817,437 +1025,300 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     st.rows = (uint64_t)m;
     st.cols = (uint64_t)B.cols;
     st.nnz_b = (uint64_t)b->d.nnz;
-    if ((rc = dalloc(h, &R->ptr, (size_t)m + 1))) { delete R; return rc; }
-
+    if (row_begin == 0 && row_end == (uint64_t)A.rows) st.nnz_a = (uint64_t)A.nnz;
+    TRY(dalloc(h, &R->ptr, (size_t)m + 1));
     h->ev_used = 0;
-    std::vector<LaunchRec> recs;
-    cudaStream_t rec_stream = s;
-    auto begin_rec = [&](const char* name, int stage, uint32_t grid, uint64_t rows, uint64_t products,
-                         cudaStream_t on = nullptr) {
-        LaunchRec r{};
-        snprintf(r.name, sizeof(r.name), "%s", name);
-        r.stage = stage;
-        r.grid = grid;
-        r.rows = rows;
-        r.products = products;
-        rec_stream = on ? on : s;
-        r.e0 = next_event(h, rec_stream);
-        recs.push_back(r);
-    };
-    auto end_rec = [&]() { recs.back().e1 = next_event(h, rec_stream); };
-    // side streams: sc = CTA-per-row sort bins, sh = heavy + huge bins (both = s when serialised)
-    cudaStream_t sc = h->n_streams >= 3 ? h->side[0] : s;
-    cudaStream_t sh = h->n_streams >= 2 ? h->side[1] : s;
-    bool forked = false;
-    auto fork = [&]() -> cudaError_t {   // side streams wait for everything enqueued on s so far
-        cudaError_t e = cudaEventRecord(h->ev_fork, s);
-        if (e == cudaSuccess && sc != s) e = cudaStreamWaitEvent(sc, h->ev_fork, 0);
-        if (e == cudaSuccess && sh != s) e = cudaStreamWaitEvent(sh, h->ev_fork, 0);
-        forked = true;
-        return e;
-    };
-    auto join = [&]() -> cudaError_t {   // s waits for both side streams
-        cudaError_t e = cudaSuccess;
-        cudaStream_t sides[2] = {sc, sh};
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-            if (sides[i] == s) continue;
-            e = cudaEventRecord(h->ev_join[i], sides[i]);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, h->ev_join[i], 0);
-        }
-        return e;
-    };
-
-    uint32_t *d_flops = nullptr, *d_long = nullptr, *d_perm = nullptr, *d_nnz = nullptr;
-    uint64_t* d_tiles = nullptr;
-    uint2* d_heavy_ws = nullptr;
-    uint32_t *d_items_per_row = nullptr, *d_item_row = nullptr;
-    int64_t *d_item_off = nullptr, *d_prod_ptr = nullptr;
-    void* d_kstore = nullptr;
-    uint32_t* d_masked = nullptr;
-    int32_t* d_tcol = nullptr;
-    double* d_tval = nullptr;
-    uint32_t kernels = 0;
-    auto cleanup = [&]() {
-        if (forked) {   // error paths: nothing may still run on a side stream when blocks go back to the pool
-            if (sc != s) cudaStreamSynchronize(sc);
-            if (sh != s) cudaStreamSynchronize(sh);
-        }
-        dfree(h, d_flops);
-        dfree(h, d_long);
-        dfree(h, d_perm);
-        dfree(h, d_nnz);
-        dfree(h, d_tiles);
-        dfree(h, d_heavy_ws);
-        dfree(h, d_items_per_row);
-        dfree(h, d_item_row);
-        dfree(h, d_item_off);
-        dfree(h, d_prod_ptr);
-        dfree(h, (char*)d_kstore);
-        dfree(h, d_masked);
-        dfree(h, d_tcol);
-        dfree(h, d_tval);
-    };
-#define TRY(x)                    \
-    do {                          \
-        if ((rc = (x))) {         \
-            cleanup();            \
-            spada_b200_result_free(R); \
-            return rc;            \
-        }                         \
-    } while (0)
-#define CUT(expr)                                                                                 \
-    do {                                                                                          \
-        cudaError_t e__ = (expr);                                                                 \
-        if (e__ != cudaSuccess) {                                                                 \
-            cleanup();                                                                            \
-            spada_b200_result_free(R);                                                            \
-            return fail(e__ == cudaErrorMemoryAllocation ? SPADA_B200_OOM : SPADA_B200_CUDA_ERROR, \
-                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-        }                                                                                         \
-    } while (0)
-
     if (m == 0) {
         CUT(cudaMemsetAsync(R->ptr, 0, sizeof(int64_t), s));
-        TRY(dalloc(h, &R->col, 1));
-        TRY(dalloc(h, &R->val, 1));
-        CUT(cudaStreamSynchronize(s));
-        *out = R;
+        *out = S;
         return 0;
     }
+    PlanCounters& pc = S->pc;
 
     // ---- stage 1: flop count, bins (the window choice) --------------------------------------
-    int64_t a_nnz_shard_bound = A.nnz;  // long-row list capacity: rows longer than 256 nonzeros
-    TRY(dalloc(h, &d_flops, (size_t)m));
-    TRY(dalloc(h, &d_long, (size_t)(a_nnz_shard_bound / 256 + 2)));
-    TRY(dalloc(h, &d_perm, (size_t)m));
-    TRY(dalloc(h, &d_nnz, (size_t)m));
-    TRY(dalloc(h, &d_tiles, std::max(scan_tile_state_words(m), fused_tile_state_words(m))));
-    begin_rec("flop_count", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
-    TRY(run_flops(h, A, B, (int64_t)row_begin, m, d_flops, d_long));
-    kernels += 3;
-    end_rec();
-    CUT(cudaMemsetAsync(d_nnz, 0, (size_t)m * sizeof(uint32_t), s));
+    TRY(dalloc(h, &S->d_flops, (size_t)m));
+    TRY(dalloc(h, &S->d_long, (size_t)(A.nnz / 256 + 2)));
+    TRY(dalloc(h, &S->d_perm, (size_t)m));
+    TRY(dalloc(h, &S->d_nnz, (size_t)m));
+    TRY(dalloc(h, &S->d_blen, (size_t)std::max<int64_t>(B.rows, 1)));
+    TRY(dalloc(h, &S->d_tiles, std::max(scan_tile_state_words(m), fused_tile_state_words(m))));
+    S->begin_rec("flop_count", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
+    CUT(cudaMemsetAsync(h->d_ctr, 0, sizeof(PlanCounters), s));
+    launch_flops(A, B.ptr, B.rows, S->d_blen, (int64_t)row_begin, m, S->d_flops, S->d_long, h->d_ctr, s);
+    CUT(cudaGetLastError());
+    CUT(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(PlanCounters), cudaMemcpyDeviceToHost, s));
+    S->kernels += 3;
+    S->end_rec();
+    CUT(cudaMemsetAsync(S->d_nnz, 0, (size_t)m * sizeof(uint32_t), s));
     CUT(cudaStreamSynchronize(s));  // host read-back #1: bin sizes
-    PlanCounters pc = *h->h_ctr;
+    pc = *h->h_ctr;
     st.products = pc.total_products;
-    recs[0].products = pc.total_products;
-    BinTable tbl;
+    S->recs[0].products = pc.total_products;
+    if (pc.max_flops == 0xffffffffu) {
+        shard_free(S);
+        return fail(SPADA_B200_TOO_LARGE, "a row of C has 2^32 or more intermediate products");
+    }
+    BinTable& tbl = S->tbl;
     uint32_t off = 0;
+    uint64_t non_empty = 0, dominant = 0;
     for (int bnum = 0; bnum < NUM_BINS; ++bnum) {
         tbl.offset[bnum] = off;
         if (bnum != BIN_EMPTY) off += pc.bin_rows[bnum];
         st.bin_rows[bnum] = pc.bin_rows[bnum];
         st.bin_products[bnum] = pc.bin_products[bnum];
-        st.bin_window_rows[bnum] = (bnum >= 1 && bnum <= 5) ? 4u : (bnum == 0 ? 0u : 1u);
-        st.bin_window_lanes[bnum] = (bnum >= 1 && bnum <= 5) ? 32u : (bnum == 0 ? 0u : (bnum == BIN_HEAVY ? 1024u : 256u));
+        if (bnum >= 1) non_empty += pc.bin_rows[bnum];
+        if (bnum >= 1 && bnum <= 5) {
+            dominant = std::max<uint64_t>(dominant, pc.bin_rows[bnum]);
+            if (pc.bin_rows[bnum]) {
+                S->max_light_bin = bnum;
+                S->light_rows += pc.bin_rows[bnum];
+            }
+        }
+        if (bnum >= BIN_LONG0) {
+            S->n_long += pc.bin_rows[bnum];
+            S->long_products += pc.bin_products[bnum];
+        }
+        // one sort bin holds every row: no permutation (the long-row path always works from a list)
+        if (pc.bin_rows[bnum] == (uint64_t)m && bnum >= 1 && bnum < BIN_LONG0) S->identity = true;
     }
     tbl.offset[NUM_BINS] = off;
-    // a single non-empty bin holding every row needs no permutation
-    const uint32_t* perm_of_bin[NUM_BINS];
-    bool identity = false;
-    for (int bnum = 1; bnum < NUM_BINS; ++bnum)
-        if (pc.bin_rows[bnum] == (uint64_t)m) identity = true;
-    if (!identity && off > 0) {
-        begin_rec("bin_scatter", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
-        launch_bin_scatter(d_flops, m, tbl, d_perm, h->d_ctr, s);
+    window_report(h, pc, st);
+    if (!S->identity && off > 0) {
+        S->begin_rec("bin_scatter", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
+        launch_bin_scatter(S->d_flops, m, tbl, S->d_perm, h->d_ctr, s);
         CUT(cudaGetLastError());
-        kernels += 1;
-        end_rec();
+        S->kernels += 1;
+        S->end_rec();
     }
-    for (int bnum = 0; bnum < NUM_BINS; ++bnum) perm_of_bin[bnum] = identity ? nullptr : d_perm + tbl.offset[bnum];
 
-    // Single-pass mode: rows of the warp-per-row bins are computed once and placed by a look-back
-    // scan inside the same kernel; C then has to be sized by its upper bound (the product count).
-    int max_light_bin = 0;
-    uint64_t light_rows = 0;
-    for (int bnum = 1; bnum <= 5; ++bnum)
-        if (pc.bin_rows[bnum]) {
-            max_light_bin = bnum;
-            light_rows += pc.bin_rows[bnum];
-        }
-    // The look-back places rows in row order, so a tile finishes with its slowest row: the single pass
-    // pays off when the rows look alike (one bin holds >= 80 % of the non-empty rows, e.g. stencils and
-    // uniform random graphs: measured 1.3x-1.6x), not on heavy-tailed row lengths (0.9x) -- see DESIGN.md.
-    uint64_t dominant = 0, non_empty = 0;
-    for (int bnum = 1; bnum < NUM_BINS; ++bnum) {
-        non_empty += pc.bin_rows[bnum];
-        if (bnum <= 5) dominant = std::max<uint64_t>(dominant, pc.bin_rows[bnum]);
-    }
-    bool fused = !(h->opts.flags & SPADA_B200_FLAG_TWO_PHASE) && light_rows > 0 &&
+    // Engine mode.  The look-back of the single pass places rows in row order, so a tile finishes with its slowest
+    // row: it pays off when the rows look alike (one bin holds >= 80 % of the non-empty rows, e.g. stencils and
+    // uniform random graphs: measured 1.3x-1.6x), not on heavy-tailed row lengths (0.9x) -- DESIGN.md section 4.
+    bool fused = !force_scratch && !(h->opts.flags & SPADA_B200_FLAG_TWO_PHASE) && S->light_rows > 0 &&
                  (double)pc.total_products * 12.0 <= 0.45 * (double)h->dev_total_mem;
     if (fused && !(h->opts.flags & SPADA_B200_FLAG_SINGLE_PASS) && dominant * 10 < non_empty * 8) fused = false;
-    const int first_sym_bin = fused ? 6 : 1;
+    S->fused = fused;
+    S->scratch_lo = fused ? 512u : 0u;
+    for (int bnum = fused ? 6 : 1; bnum < NUM_BINS; ++bnum) S->scratch_products += pc.bin_products[bnum];
+    S->scratch = S->scratch_products > 0;
 
-    // Two-phase mode: the symbolic kernels of the sort bins (1..8) leave each row's sorted keys in HBM
-    // at kstore + prod_ptr[row]; the numeric kernels reload them instead of sorting the row again.
-    bool keep_keys = false, wide_keys = false;
-    // Mode 2 (default): the first pass computes the finished rows of the sort bins into a scratch CSR
-    // laid out by product count; after the scan they are copied to their place -- one expansion, one sort.
-    uint64_t sorted_products = 0;
-    for (int bnum = 1; bnum <= 8; ++bnum) sorted_products += pc.bin_products[bnum];
-    // heavy bin (shared-memory bitmap, B at most 2^20 columns wide): one kernel per row into a scratch row instead of
-    // a symbolic and a numeric kernel around the scan -- one expansion less, 0.39 ms of 8 on the rect config
-    const bool heavy_joins_huge = B.cols > h->heavy_smem_cols;   // wide B: heavy rows take the item path of the huge bin
-    const bool heavy_oneshot = !fused && h->two_phase_mode == 2 && h->heavy_oneshot && !heavy_joins_huge &&
-                               pc.bin_rows[BIN_HEAVY] > 0;
-    if (heavy_oneshot) sorted_products += pc.bin_products[BIN_HEAVY];
-    // huge bin (item path, bitmaps in HBM) when the bitmaps of its rows need more than one wave of workspace: the same
-    // one-shot idea -- bits, ranks, column ids and values of a wave go into scratch rows in one sweep, instead of a
-    // symbolic sweep and a numeric sweep that has to rebuild the bitmaps of every wave (R-MAT: 830 -> 581 ms).
-    // Costs 12 B of scratch per product of those rows (R-MAT: 64 GB) and a CTA-per-row copy; with a single wave
-    // (rect) nothing is rebuilt and the extra copy only costs (7.47 -> 7.83 ms), so single-wave cases keep two sweeps.
-    const uint64_t huge_rows0 = pc.bin_rows[BIN_HUGE] + (heavy_joins_huge ? pc.bin_rows[BIN_HEAVY] : 0);
-    const uint64_t huge_products0 = pc.bin_products[BIN_HUGE] + (heavy_joins_huge ? pc.bin_products[BIN_HEAVY] : 0);
-    const bool huge_multi_wave =
-        huge_rows0 > 0 && heavy_plan_sizes((uint32_t)huge_rows0, huge_products0, B.cols, h->heavy_ws_budget).n_waves > 1;
-    const bool huge_oneshot_fits = !fused && h->two_phase_mode == 2 && h->huge_oneshot && huge_multi_wave &&
-                                   (double)(sorted_products + huge_products0) * 12.0 <= 0.40 * (double)h->dev_total_mem;
-    if (huge_oneshot_fits) sorted_products += huge_products0;
-    const uint32_t scratch_limit = huge_oneshot_fits ? 0xffffffffu : (heavy_oneshot ? HEAVY_MAX_PRODUCTS : ESC_MAX_PRODUCTS);
-    const bool scratch = !fused && h->two_phase_mode == 2 && sorted_products > 0 &&
-                         (double)sorted_products * 12.0 <= (huge_oneshot_fits ? 0.40 : 0.30) * (double)h->dev_total_mem;
-    const bool heavy_in_scratch = scratch && heavy_oneshot;
-    const bool huge_in_scratch = scratch && huge_oneshot_fits;
-    if (!fused && !scratch && h->two_phase_mode >= 1) {
-        uint64_t sorted_rows = 0;
-        for (int bnum = 1; bnum <= 8; ++bnum) {
-            sorted_rows += pc.bin_rows[bnum];
-            if (pc.bin_rows[bnum] && esc_needs_wide_keys(bnum, B.cols)) wide_keys = true;
+    // long rows: wave plan + workspace
+    std::vector<WavePlan> waves;
+    uint64_t wave_products = 0, wave_units = 0, wave_rows = 0;
+    if (S->n_long) {
+        waves = plan_waves(pc, std::max<uint64_t>(h->long_ws_budget / 24, (uint64_t)LONG_UNIT));
+        for (auto& w : waves) {
+            wave_products = std::max(wave_products, w.products_bound);
+            wave_units = std::max(wave_units, w.unit_bound);
+            wave_rows = std::max<uint64_t>(wave_rows, w.hi - w.lo);
         }
-        const double kbytes = (double)pc.total_products * (wide_keys ? 8.0 : 4.0);
-        keep_keys = sorted_rows > 0 && kbytes <= 0.15 * (double)h->dev_total_mem;
     }
-    if (keep_keys) {
-        TRY(dalloc(h, &d_prod_ptr, (size_t)m + 1));
-        char* ks = nullptr;
-        TRY(dalloc(h, &ks, (size_t)pc.total_products * (wide_keys ? 8 : 4)));
-        d_kstore = ks;
-        begin_rec("product_scan", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
-        launch_scan_u32_i64(d_flops, m, d_prod_ptr, d_tiles, h->d_ctr, s);
+    {
+        const double need = (double)S->scratch_products * 12.0 + (double)wave_products * 24.0 +
+                            (fused ? (double)pc.total_products * 12.0 : 0.0);
+        if (need > 0.92 * (double)h->dev_total_mem) {
+            shard_free(S);
+            return fail(SPADA_B200_OOM,
+                        "the first pass needs %.1f GB of scratch rows for %llu intermediate products (device: %.1f GB); "
+                        "compute C in row panels with spada_b200_spgemm_stream",
+                        need / 1e9, (unsigned long long)pc.total_products, (double)h->dev_total_mem / 1e9);
+        }
+    }
+    if (S->scratch) {
+        TRY(dalloc(h, &S->d_masked, (size_t)m));
+        TRY(dalloc(h, &S->d_prod_ptr, (size_t)m + 1));
+        TRY(dalloc(h, &S->d_tcol, (size_t)S->scratch_products));
+        TRY(dalloc(h, &S->d_tval, (size_t)S->scratch_products));
+        S->begin_rec("scratch_ptr", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
+        launch_mask_sorted(S->d_flops, m, S->scratch_lo, 0xffffffffu, S->d_masked, s);
+        launch_scan_u32_i64(S->d_masked, m, S->d_prod_ptr, S->d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
-        kernels += 1;
-        end_rec();
+        S->kernels += 2;
+        S->end_rec();
+    }
+    if (S->n_long) {
+        TRY(dalloc(h, &S->d_aseq, (size_t)std::max<int64_t>(A.nnz, 1)));
+        TRY(dalloc(h, &S->w_p, (size_t)wave_rows));
+        TRY(dalloc(h, &S->w_u, (size_t)wave_rows));
+        TRY(dalloc(h, &S->w_prod_off, (size_t)wave_rows + 1));
+        TRY(dalloc(h, &S->w_unit_off, (size_t)wave_rows + 1));
+        TRY(dalloc(h, &S->w_heads, (size_t)wave_units));
+        TRY(dalloc(h, &S->w_hoff, (size_t)wave_units + 1));
+        TRY(dalloc(h, &S->d_tiles_side, scan_tile_state_words((int64_t)std::max<uint64_t>(wave_units, wave_rows))));
+        for (int i = 0; i < 2; ++i) {
+            TRY(dalloc(h, &S->w_col[i], (size_t)wave_products));
+            TRY(dalloc(h, &S->w_val[i], (size_t)wave_products));
+        }
     }
 
-    if (scratch) {
-        TRY(dalloc(h, &d_masked, (size_t)m));
-        TRY(dalloc(h, &d_prod_ptr, (size_t)m + 1));
-        TRY(dalloc(h, &d_tcol, (size_t)sorted_products));
-        TRY(dalloc(h, &d_tval, (size_t)sorted_products));
-        begin_rec("scratch_ptr", 1, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
-        launch_mask_sorted(d_flops, m, scratch_limit, d_masked, s);
-        launch_scan_u32_i64(d_masked, m, d_prod_ptr, d_tiles, h->d_ctr, s);
+    // ---- first pass: every scratch row is expanded, sorted and summed exactly once ---------------------------
+    cudaStream_t sh = (h->opts.flags & SPADA_B200_FLAG_SERIAL) ? s : h->side;
+    if (sh != s) {
+        CUT(cudaEventRecord(h->ev_fork, s));
+        CUT(cudaStreamWaitEvent(sh, h->ev_fork, 0));
+        S->forked = true;
+    }
+    if (S->n_long) {
+        const uint32_t* long_list = S->perm_of(BIN_LONG0);   // bins >= BIN_LONG0 are adjacent in perm[]
+        S->begin_rec("long_prefix", 2, S->n_long, S->n_long, S->long_products, sh);
+        launch_long_prefix(A, (int64_t)row_begin, long_list, S->n_long, S->d_blen, S->d_aseq, sh);
         CUT(cudaGetLastError());
-        kernels += 2;
-        end_rec();
+        S->kernels += 1;
+        S->end_rec();
+        int wi = 0;
+        for (auto& w : waves) {
+            LongWave W{};
+            W.rows_list = long_list + w.lo;
+            W.n_rows = w.hi - w.lo;
+            memcpy(W.level_lo, w.level_lo, sizeof(W.level_lo));
+            memcpy(W.level_grid, w.level_grid, sizeof(W.level_grid));
+            W.max_level = w.max_level;
+            W.unit_bound = w.unit_bound;
+            W.p = S->w_p;
+            W.u = S->w_u;
+            W.prod_off = S->w_prod_off;
+            W.unit_off = S->w_unit_off;
+            W.unit_heads = S->w_heads;
+            W.unit_hoff = S->w_hoff;
+            for (int i = 0; i < 2; ++i) {
+                W.col[i] = S->w_col[i];
+                W.val[i] = S->w_val[i];
+            }
+            W.tile_state = S->d_tiles_side;
+            LongStages stages;
+            stages.on = [&](const char* what, uint32_t grid) {
+                char name[32];
+                if (waves.size() > 1) snprintf(name, sizeof(name), "%s#%d", what, wi);
+                else snprintf(name, sizeof(name), "%s", what);
+                if (waves.size() <= 4) S->begin_rec(name, 2, grid, W.n_rows, w.products_bound, sh);
+            };
+            stages.off = [&]() {
+                if (waves.size() <= 4) S->end_rec();
+            };
+            if (waves.size() > 4 && wi == 0) S->begin_rec("long_waves", 2, (uint32_t)w.unit_bound, S->n_long, S->long_products, sh);
+            S->kernels += launch_long_wave(A, B, (int64_t)row_begin, S->d_flops, S->d_aseq, W, S->d_prod_ptr, S->d_tcol,
+                                           S->d_tval, S->d_nnz, h->d_ctr_side, sh, &stages);
+            CUT(cudaGetLastError());
+            ++wi;
+        }
+        if (waves.size() > 4) S->end_rec();
     }
-
-    // huge rows: cut into items, bitmaps for one wave of rows at a time
-    // The shared-memory bitmap of the heavy bin covers 2^20 columns per pass; for wider B the heavy rows
-    // join the huge rows on the item path (measured on R-MAT, n = 2^21: two passes per row lose to it).
-    if (heavy_joins_huge) {   // bins 9 and 10 are adjacent in perm[]: one combined list
-        pc.bin_rows[BIN_HUGE] += pc.bin_rows[BIN_HEAVY];
-        pc.bin_products[BIN_HUGE] += pc.bin_products[BIN_HEAVY];
-        perm_of_bin[BIN_HUGE] = perm_of_bin[BIN_HEAVY];
-        pc.bin_rows[BIN_HEAVY] = 0;
-        pc.bin_products[BIN_HEAVY] = 0;
-    }
-    HeavyPlan HP{};
-    const uint32_t n_heavy = pc.bin_rows[BIN_HUGE];
-    if (n_heavy) {
-        HP = heavy_plan_sizes(n_heavy, pc.bin_products[BIN_HUGE], B.cols, h->heavy_ws_budget);
-        TRY(dalloc(h, &d_items_per_row, (size_t)n_heavy));
-        TRY(dalloc(h, &d_item_off, (size_t)n_heavy + 1));
-        TRY(dalloc(h, &d_item_row, (size_t)HP.max_items));
-        TRY(dalloc(h, &d_heavy_ws, HP.ws_words));
-        begin_rec("huge_items", 1, (n_heavy + 255) / 256, n_heavy, pc.bin_products[BIN_HUGE]);
-        launch_heavy_items(A, (int64_t)row_begin, perm_of_bin[BIN_HUGE], n_heavy, d_flops, d_items_per_row,
-                           d_item_off, d_item_row, d_tiles, h->d_ctr, s);
-        CUT(cudaGetLastError());
-        kernels += 3;
-        end_rec();
-    }
-
-    // ---- stage 2: symbolic ------------------------------------------------------------------
-    CUT(fork());
-    for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
-        uint32_t rows = pc.bin_rows[bnum];
+    for (int bnum = fused ? 6 : 1; bnum <= 8; ++bnum) {
+        const uint32_t rows = pc.bin_rows[bnum];
         if (!rows) continue;
         char name[32];
-        snprintf(name, sizeof(name), "symbolic<%s>", bin_name(bnum));
-        if (bnum == BIN_HUGE && huge_in_scratch) snprintf(name, sizeof(name), "oneshot<%s>", bin_name(bnum));
-        cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);   // the stream of this bin
-        if (bnum == BIN_HEAVY && heavy_in_scratch) {
-            snprintf(name, sizeof(name), "oneshot<%s>", bin_name(bnum));
-            begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
-            launch_heavy_smem_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_prod_ptr, d_tcol, d_tval, sb,
-                                      d_nnz);
-            kernels += 1;
-        } else if (bnum == BIN_HEAVY) {
-            begin_rec(name, 2, rows, rows, pc.bin_products[bnum], sb);
-            launch_heavy_smem_symbolic(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, sb);
-            kernels += 1;
-        } else if (bnum == BIN_HUGE) {
-            const uint32_t* hl = perm_of_bin[bnum];
-            const bool detail = HP.n_waves == 1;  // per-kernel records for a single wave, one record otherwise
-            if (!detail) begin_rec(name, 2, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum], sb);
-            for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
-                uint32_t hi = std::min(rows, lo + HP.wave_rows);
-                if (detail) begin_rec("sym_huge_clear", 2, 0, hi - lo, 0, sb);
-                CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), sb));
-                if (detail) end_rec();
-                if (detail) begin_rec("sym_huge_bits", 2, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum], sb);
-                launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
-                                  h->sm_count, sb);
-                if (detail) end_rec();
-                if (detail) begin_rec("sym_huge_rank", 2, hi - lo, hi - lo, pc.bin_products[bnum], sb);
-                launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, d_nnz, sb);
-                kernels += 2;
-                if (huge_in_scratch) {   // one shot: the wave's column ids and values go to its scratch rows right away
-                    if (detail) end_rec();
-                    if (detail) begin_rec("num_huge_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum], sb);
-                    launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, d_prod_ptr, d_tcol, d_tval, sb, d_nnz);
-                    if (detail) end_rec();
-                    if (detail) begin_rec("num_huge_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum], sb);
-                    launch_heavy_accum(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
-                                       d_prod_ptr, d_tval, h->sm_count, sb);
-                    kernels += 2;
-                }
-            }
-        } else if (scratch) {
-            snprintf(name, sizeof(name), "sort_pass<%s>", bin_name(bnum));
-            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum], sb);
-            launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_prod_ptr, d_tcol, d_tval, sb,
-                               d_nnz);
-            kernels += 1;
-        } else {
-            begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum], sb);
-            if (keep_keys && bnum <= 5)
-                launch_esc_symbolic_keep(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz,
-                                         d_prod_ptr, d_kstore, sb);
-            else if (keep_keys && bnum <= 8)
-                launch_cta_symbolic_keep(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz,
-                                         d_prod_ptr, d_kstore, sb);
-            else
-                launch_esc_symbolic(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, d_nnz, sb);
-            kernels += 1;
-        }
+        snprintf(name, sizeof(name), "sort_pass<%s>", bin_name(bnum));
+        S->begin_rec(name, 2, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum], s);
+        launch_esc_numeric(bnum, A, B, (int64_t)row_begin, S->perm_of(bnum), rows, S->d_prod_ptr, S->d_tcol, S->d_tval, s,
+                           S->d_nnz);
         CUT(cudaGetLastError());
-        end_rec();
+        S->kernels += 1;
+        S->end_rec();
     }
-    CUT(join());
-    int64_t nnz_c = 0;
+    if (S->forked) {
+        CUT(cudaEventRecord(h->ev_join, sh));
+        CUT(cudaStreamWaitEvent(s, h->ev_join, 0));
+        S->forked = false;
+    }
     if (!fused) {
         // ---- stage 4: row_ptr ---------------------------------------------------------------
-        begin_rec("row_ptr_scan", 4, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
-        launch_scan_u32_i64(d_nnz, m, R->ptr, d_tiles, h->d_ctr, s);
+        S->begin_rec("row_ptr_scan", 4, (uint32_t)((m + 4095) / 4096), (uint64_t)m, 0);
+        launch_scan_u32_i64(S->d_nnz, m, R->ptr, S->d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
-        kernels += 1;
-        end_rec();
+        S->kernels += 1;
+        S->end_rec();
         CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         CUT(cudaStreamSynchronize(s));  // host read-back #2: nnz(C) sizes the output
-        nnz_c = h->h_scalar[0];
-        TRY(dalloc(h, &R->col, (size_t)nnz_c));
-        TRY(dalloc(h, &R->val, (size_t)nnz_c));
+        S->nnz_c = h->h_scalar[0];
+    }
+    *out = S;
+    return 0;
+}
+
+// second half.  dst == nullptr: C is allocated here (exact size, or the product bound in single-pass mode) and is
+// the only destination.  Otherwise dst lists the C buffers of every GPU (this GPU's first) and the shard's rows go to
+// dst->off + local offset in all of them; row_ptr_dst[d] (nullable) get the shard's row pointers shifted by dst->off
+// at row offset row_off.
+int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_ptr_dst, int64_t row_off,
+                 spada_b200_result_t** out) {
+    spada_b200* h = S->h;
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    spada_b200_result* R = S->R;
+    spada_b200_stats& st = R->stats;
+    const PlanCounters& pc = S->pc;
+    const int64_t m = S->m;
+    int rc;
+    if (m == 0) {
+        if (!dst) {
+            TRY(dalloc(h, &R->col, 1));
+            TRY(dalloc(h, &R->val, 1));
+        }
+        CUT(cudaStreamSynchronize(s));
+        if (out) {
+            *out = R;
+            S->R = nullptr;
+        }
+        shard_free(S);
+        return 0;
+    }
+    CopyDst D{};
+    if (dst) {
+        D = *dst;
     } else {
-        // ---- stages 2+3+4 fused for the warp-per-row bins ----------------------------------------
-        TRY(dalloc(h, &R->col, (size_t)pc.total_products));
-        TRY(dalloc(h, &R->val, (size_t)pc.total_products));
+        const size_t cap = (size_t)(S->fused ? pc.total_products : (uint64_t)S->nnz_c);
+        TRY(dalloc(h, &R->col, cap));
+        TRY(dalloc(h, &R->val, cap));
+        D.col[0] = R->col;
+        D.val[0] = R->val;
+        D.n = 1;
+        D.off = 0;
+    }
+    if (S->fused) {
+        // ---- stages 2+3+4 fused for the warp-per-row bins: straight into C ----------------------------------
         char name[32];
-        snprintf(name, sizeof(name), "fused<%s>", bin_name(max_light_bin));
+        snprintf(name, sizeof(name), "fused<%s>", bin_name(S->max_light_bin));
         uint64_t light_products = 0;
         for (int bnum = 1; bnum <= 5; ++bnum) light_products += pc.bin_products[bnum];
-        begin_rec(name, 3, (uint32_t)((m + 7) / 8), light_rows, light_products);
-        launch_fused_light(max_light_bin, A, B, (int64_t)row_begin, m, d_flops, d_nnz, R->ptr, R->col, R->val, d_tiles,
-                           h->d_ctr, s);
+        S->begin_rec(name, 3, (uint32_t)((m + 7) / 8), S->light_rows, light_products);
+        launch_fused_light(S->max_light_bin, S->A, S->B, S->row_begin, m, S->d_flops, S->d_nnz, R->ptr, R->col, R->val,
+                           S->d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
-        kernels += 1;
-        end_rec();
+        S->kernels += 1;
+        S->end_rec();
         CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     }
-
-    // ---- stage 3: numeric -------------------------------------------------------------------
-    CUT(fork());
-    if (scratch) {
-        begin_rec("copy_rows", 3, (uint32_t)((m + 7) / 8), (uint64_t)m, sorted_products);
-        launch_copy_rows(d_flops, m, ESC_MAX_PRODUCTS, d_prod_ptr, d_tcol, d_tval, R->ptr, R->col, R->val, s);
-        if (heavy_in_scratch) {   // the heavy bin's scratch rows: one CTA per row
-            launch_copy_rows_list(perm_of_bin[BIN_HEAVY], pc.bin_rows[BIN_HEAVY], d_prod_ptr, d_tcol, d_tval, R->ptr,
-                                  R->col, R->val, s);
-            kernels += 1;
-        }
-        if (huge_in_scratch) {
-            launch_copy_rows_list(perm_of_bin[BIN_HUGE], pc.bin_rows[BIN_HUGE], d_prod_ptr, d_tcol, d_tval, R->ptr,
-                                  R->col, R->val, s);
-            kernels += 1;
+    // ---- placement: scratch rows -> C (and the peers' C) --------------------------------------------------
+    if (S->scratch) {
+        S->begin_rec(D.n > 1 ? "copy_gather" : "copy_rows", 3, (uint32_t)((m + 7) / 8), (uint64_t)m, S->scratch_products);
+        launch_copy_rows(S->d_flops, m, S->scratch_lo, ESC_MAX_PRODUCTS, S->d_prod_ptr, S->d_tcol, S->d_tval, R->ptr, D, s);
+        S->kernels += 1;
+        if (S->n_long) {   // long rows: one CTA per row
+            launch_copy_rows_list(S->perm_of(BIN_LONG0), S->n_long, S->d_prod_ptr, S->d_tcol, S->d_tval, R->ptr, D, s);
+            S->kernels += 1;
         }
         CUT(cudaGetLastError());
-        kernels += 1;
-        end_rec();
+        S->end_rec();
     }
-    for (int bnum = first_sym_bin; bnum < NUM_BINS; ++bnum) {
-        uint32_t rows = pc.bin_rows[bnum];
-        if (!rows) continue;
-        if (scratch && (bnum <= 8 || (bnum == BIN_HEAVY && heavy_in_scratch) || (bnum == BIN_HUGE && huge_in_scratch))) continue;
-        char name[32];
-        snprintf(name, sizeof(name), "numeric<%s>", bin_name(bnum));
-        cudaStream_t sb = bnum >= BIN_HEAVY ? sh : (bnum >= 6 ? sc : s);
-        if (bnum == BIN_HEAVY) {
-            begin_rec(name, 3, rows, rows, pc.bin_products[bnum], sb);
-            launch_heavy_smem_numeric(A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, sb);
-            kernels += 1;
-        } else if (bnum == BIN_HUGE) {
-            const uint32_t* hl = perm_of_bin[bnum];
-            const bool ws_valid = HP.n_waves == 1;  // bitmaps + ranks of the symbolic stage are still resident
-            if (!ws_valid) begin_rec(name, 3, (uint32_t)h->sm_count * 8, rows, pc.bin_products[bnum], sb);
-            for (uint32_t lo = 0; lo < rows; lo += HP.wave_rows) {
-                uint32_t hi = std::min(rows, lo + HP.wave_rows);
-                if (!ws_valid) {
-                    CUT(cudaMemsetAsync(d_heavy_ws, 0, (size_t)(hi - lo) * HP.words * sizeof(uint2), sb));
-                    launch_heavy_bits(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws,
-                                      HP, h->sm_count, sb);
-                    launch_heavy_rank(hl, lo, hi, d_heavy_ws, HP, nullptr, sb);
-                    kernels += 2;
-                }
-                if (ws_valid) begin_rec("num_huge_emit", 3, hi - lo, hi - lo, pc.bin_products[bnum], sb);
-                launch_heavy_emit(hl, lo, hi, d_heavy_ws, HP, R->ptr, R->col, R->val, sb);
-                if (ws_valid) end_rec();
-                if (ws_valid) begin_rec("num_huge_accum", 3, (uint32_t)h->sm_count * 8, hi - lo, pc.bin_products[bnum], sb);
-                launch_heavy_accum(A, B, (int64_t)row_begin, hl, d_flops, d_item_off, d_item_row, lo, hi, d_heavy_ws, HP,
-                                   R->ptr, R->val, h->sm_count, sb);
-                kernels += 2;
-            }
-        } else {
-            begin_rec(name, 3, (uint32_t)esc_grid(bnum, rows), rows, pc.bin_products[bnum], sb);
-            if (keep_keys && bnum <= 5)
-                launch_esc_numeric_presorted(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr,
-                                             R->col, R->val, d_prod_ptr, d_kstore, sb);
-            else if (keep_keys && bnum <= 8)
-                launch_cta_numeric_presorted(bnum, wide_keys, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr,
-                                             R->col, R->val, d_prod_ptr, d_kstore, sb);
-            else
-                launch_esc_numeric(bnum, A, B, (int64_t)row_begin, perm_of_bin[bnum], rows, R->ptr, R->col, R->val, sb);
-            kernels += 1;
-        }
+    if (dst && row_ptr_dst) {
+        S->begin_rec("row_ptr_gather", 3, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
+        launch_shift_row_ptr(R->ptr, m, D.off, *row_ptr_dst, row_off, s);
         CUT(cudaGetLastError());
-        end_rec();
+        S->kernels += 1;
+        S->end_rec();
     }
-    CUT(join());
-    forked = false;
-    cudaEvent_t e_end = next_event(h, s);
-    cleanup();
+    S->e_end = next_event(h, s);
+    S->release_work();
     CUT(cudaStreamSynchronize(s));
     CUT(cudaGetLastError());
-    if (fused) nnz_c = h->h_scalar[0];
-    R->nnz = (uint64_t)nnz_c;
-    st.nnz_c = (uint64_t)nnz_c;
+    if (S->fused) S->nnz_c = h->h_scalar[0];
+    R->nnz = (uint64_t)S->nnz_c;
+    st.nnz_c = (uint64_t)S->nnz_c;
 
     // ---- stats ------------------------------------------------------------------------------
-    st.nnz_a = 0;  // filled by the caller-facing wrappers when the whole of A is used
-    if (row_begin == 0 && row_end == (uint64_t)A.rows) st.nnz_a = (uint64_t)A.nnz;
-    st.n_launches = kernels;
+    st.n_launches = S->kernels;
     st.n_recorded = 0;
-    for (const LaunchRec& r : recs) {
+    for (const LaunchRec& r : S->recs) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.e0, r.e1);
         if (r.stage == 1) st.ms_flops += ms;
@@ -1264,11 +1335,28 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
             L.nnz = 0;
         }
     }
-    if (!recs.empty()) cudaEventElapsedTime(&st.ms_total, recs.front().e0, e_end);
+    if (!S->recs.empty()) cudaEventElapsedTime(&st.ms_total, S->recs.front().e0, S->e_end);
+    if (out) {
+        *out = R;
+        S->R = nullptr;
+    }
+    S->finished = true;
+    shard_free(S);
+    return 0;
+}
 #undef TRY
 #undef CUT
-    *out = R;
-    return 0;
+
+}  // namespace
+
+extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
+                                     uint64_t row_begin, uint64_t row_end, spada_b200_result_t** out) {
+    if (!out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    spada_b200_shard* S = nullptr;
+    int rc = shard_begin(h, a, b, row_begin, row_end, false, &S);
+    if (rc) return rc;
+    return shard_finish(S, nullptr, nullptr, 0, out);
 }
 
 namespace {
@@ -1286,7 +1374,11 @@ int spgemm_host(spada_b200_t* h, const View* a, const View* b, spada_b200_result
     cudaEventRecord(e0, h->stream);
     spada_b200_csr_t *da = nullptr, *db = nullptr;
     int rc = upload(h, a, &da);
-    if (rc) return rc;
+    if (rc) {
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return rc;
+    }
     // the reference clones A into B for square workloads (gemm.rs:42-43); the same host arrays
     // uploaded once are enough
     bool alias = (const void*)a == (const void*)b ||
@@ -1295,6 +1387,8 @@ int spgemm_host(spada_b200_t* h, const View* a, const View* b, spada_b200_result
     if (alias) db = da;
     else if ((rc = upload(h, b, &db))) {
         spada_b200_csr_free(da);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
         return rc;
     }
     cudaEventRecord(e1, h->stream);
@@ -1340,16 +1434,20 @@ extern "C" int spada_b200_result_copy32(const spada_b200_result_t* r, int64_t* i
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    cudaEventRecord(e0, h->stream);
-    if (indptr) CU(cudaMemcpyAsync(indptr, r->ptr, (r->rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    if (indices && r->nnz) CU(cudaMemcpyAsync(indices, r->col, r->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    if (data && r->nnz) CU(cudaMemcpyAsync(data, r->val, r->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    cudaEventRecord(e1, h->stream);
-    CU(cudaStreamSynchronize(h->stream));
-    cudaEventElapsedTime(&const_cast<spada_b200_result_t*>(r)->stats.ms_d2h, e0, e1);
+    auto body = [&]() -> int {
+        cudaEventRecord(e0, h->stream);
+        if (indptr) CU(cudaMemcpyAsync(indptr, r->ptr, (r->rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        if (indices && r->nnz) CU(cudaMemcpyAsync(indices, r->col, r->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (data && r->nnz) CU(cudaMemcpyAsync(data, r->val, r->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        cudaEventRecord(e1, h->stream);
+        CU(cudaStreamSynchronize(h->stream));
+        cudaEventElapsedTime(&const_cast<spada_b200_result_t*>(r)->stats.ms_d2h, e0, e1);
+        return 0;
+    };
+    const int rc = body();
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    return 0;
+    return rc;
 }
 
 extern "C" int spada_b200_result_copy(const spada_b200_result_t* r, uint64_t* indptr, uint64_t* indices, double* data) {

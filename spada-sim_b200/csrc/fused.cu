@@ -4,13 +4,12 @@
 // expanded, sorted and reduced once; the reduced row waits in the warp's shared memory while the
 // CTA learns where it goes: eight consecutive rows form a tile, the tile's nnz total is
 // published and the exclusive prefix over all earlier tiles is obtained by decoupled look-back
-// (the same single-pass scan as plan.cu, one tile per CTA; tile id = blockIdx.x -- a global
-// ticket counter would serialise half a million same-address atomics on the Poisson config).
+// (the same single-pass scan as plan.cu, one tile per CTA; tile id = a ticket drawn at CTA start).
 // Then row_ptr is written and the rows are copied to their final place with coalesced stores.
 //
-// Rows of the CTA-per-row and bitmap bins (> 512 products) are counted beforehand by their own
-// symbolic kernels; the tile sums simply include their counts, and their numeric kernels run
-// afterwards against the finished row_ptr.
+// Rows with more than 512 products (CTA-per-row sort bins, long rows) are computed beforehand into
+// scratch rows by their own kernels, which also record their nnz; the tile sums simply include those
+// counts, and the scratch rows are copied to their place afterwards against the finished row_ptr.
 //
 // C is allocated with capacity = number of intermediate products (an upper bound on nnz(C))
 // because nnz(C) is only known when this kernel ends; the engine falls back to the two-phase
@@ -101,19 +100,23 @@ template <typename K, int NMAX, int RPW>
 __global__ void __launch_bounds__(LIGHT_WARPS * 32)
 k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
               const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
-              double* __restrict__ c_val, unsigned long long* tile_state) {
+              double* __restrict__ c_val, unsigned long long* tile_state, uint32_t* ticket) {
     constexpr int SBK = Log2<NMAX>::v;
     constexpr int TILE_ROWS = LIGHT_WARPS * RPW;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ uint32_t s_nnz[TILE_ROWS];
     __shared__ unsigned long long s_excl;
+    __shared__ uint32_t s_tile;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     K* keys_w = reinterpret_cast<K*>(s_raw) + (size_t)warp * RPW * NMAX;
     double* vals_w = reinterpret_cast<double*>(s_raw + sizeof(K) * NMAX * TILE_ROWS) + (size_t)warp * RPW * NMAX;
 
-    // Tile id = blockIdx.x: CTAs of a 1-D grid are dispatched in index order, so every tile this one
-    // looks back at is already resident or finished (the usual decoupled look-back assumption).
-    const uint32_t tile = blockIdx.x;
+    // Tile id = a ticket drawn when the CTA starts: every tile this one looks back at is held by a CTA that is
+    // already running (or done), whatever order the hardware dispatches the grid in and whatever else shares the
+    // GPU (side streams, NCCL kernels) -- the look-back can always make progress.
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
     const int64_t r0 = (int64_t)tile * TILE_ROWS + warp * RPW;
 
     int nnz[RPW];
@@ -369,17 +372,21 @@ template <typename K>
 __global__ void __launch_bounds__(FUSED_WARPS * 32)
 k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
              const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
-             double* __restrict__ c_val, unsigned long long* tile_state) {
+             double* __restrict__ c_val, unsigned long long* tile_state, uint32_t* ticket) {
     __shared__ uint32_t s_col[TINY_TILE][TINY_LD];
     __shared__ double s_val[TINY_TILE][TINY_LD];
     __shared__ uint32_t s_nnz[TINY_TILE];   // nnz of every row of the tile
     __shared__ uint32_t s_off[TINY_TILE];   // exclusive offsets inside the tile
     __shared__ uint32_t s_light;            // bit rt set <=> row rt was computed here
     __shared__ unsigned long long s_excl;
+    __shared__ uint32_t s_tile;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x;
-    if (threadIdx.x == 0) s_light = 0u;
+    if (threadIdx.x == 0) {
+        s_light = 0u;
+        s_tile = atomicAdd(ticket, 1u);   // tile id = start order (see k_fused_light)
+    }
     __syncthreads();
+    const uint32_t tile = s_tile;
 
 #pragma unroll 1
     for (int q = 0; q < TINY_RPW; ++q) {
@@ -392,7 +399,7 @@ k_fused_tiny(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* _
                 nnz = tiny_row_warp<K>(a, b, row_begin, r, s_col[rt], s_val[rt], lane);
                 if (lane == 0) atomicOr(&s_light, 1u << rt);
             } else if (pf > 32u) {
-                nnz = (int)pre_nnz[r];   // counted by its own symbolic kernel
+                nnz = (int)pre_nnz[r];   // computed into a scratch row beforehand
             }
         }
         if (lane == 0) s_nnz[rt] = (uint32_t)nnz;
@@ -423,7 +430,7 @@ template <typename K>
 __global__ void __launch_bounds__(FUSED_WARPS * 32)
 k_fused_tiny4(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
               const uint32_t* __restrict__ pre_nnz, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
-              double* __restrict__ c_val, unsigned long long* tile_state) {
+              double* __restrict__ c_val, unsigned long long* tile_state, uint32_t* ticket) {
     __shared__ uint32_t s_col[TINY_TILE][TINY_LD];   // finished rows (compacted), staged for the coalesced store
     __shared__ double s_val[TINY_TILE][TINY_LD];     // first the products by arrival index, then the finished rows
     __shared__ uint32_t t_col[TINY_TILE][TINY_LD];   // the sorted row, read by the run sums
@@ -432,11 +439,15 @@ k_fused_tiny4(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
     __shared__ uint32_t s_off[TINY_TILE];
     __shared__ uint32_t s_light;
     __shared__ unsigned long long s_excl;
+    __shared__ uint32_t s_tile;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int g = lane >> 3, sub = lane & 7;
-    const uint32_t tile = blockIdx.x;
-    if (threadIdx.x == 0) s_light = 0u;
+    if (threadIdx.x == 0) {
+        s_light = 0u;
+        s_tile = atomicAdd(ticket, 1u);   // tile id = start order (see k_fused_light)
+    }
     __syncthreads();
+    const uint32_t tile = s_tile;
 
     {
         const int rt = warp * TINY_RPW + g;
@@ -571,7 +582,7 @@ constexpr int fused_rpw(int nmax) { return nmax <= 32 ? 4 : (nmax <= 64 ? 2 : 1)
 template <typename K, int NMAX>
 static void fused_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m, const uint32_t* flops,
                          const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val, uint64_t* tile_state,
-                         cudaStream_t s) {
+                         uint32_t* ticket, cudaStream_t s) {
     constexpr int RPW = fused_rpw(NMAX);
     constexpr int TILE_ROWS = LIGHT_WARPS * RPW;
     size_t smem = (sizeof(K) + sizeof(double)) * NMAX * TILE_ROWS;
@@ -581,8 +592,9 @@ static void fused_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, in
     }
     size_t tiles = (size_t)((m + TILE_ROWS - 1) / TILE_ROWS);
     cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
+    cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s);
     k_fused_light<K, NMAX, RPW><<<(unsigned)tiles, LIGHT_WARPS * 32, smem, s>>>(
-        a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+        a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state, ticket);
 }
 
 size_t fused_tile_state_words(int64_t m) { return (size_t)((m + LIGHT_WARPS - 1) / LIGHT_WARPS) + 1; }
@@ -590,13 +602,13 @@ size_t fused_tile_state_words(int64_t m) { return (size_t)((m + LIGHT_WARPS - 1)
 template <typename K>
 static void fused_dispatch(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
                            const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,
-                           uint64_t* tile_state, cudaStream_t s) {
+                           uint64_t* tile_state, uint32_t* ticket, cudaStream_t s) {
     switch (max_bin) {
-        case 1: fused_launch<K, 32>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
-        case 2: fused_launch<K, 64>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
-        case 3: fused_launch<K, 128>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
-        case 4: fused_launch<K, 256>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
-        default: fused_launch<K, 512>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s); break;
+        case 1: fused_launch<K, 32>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, ticket, s); break;
+        case 2: fused_launch<K, 64>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, ticket, s); break;
+        case 3: fused_launch<K, 128>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, ticket, s); break;
+        case 4: fused_launch<K, 256>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, ticket, s); break;
+        default: fused_launch<K, 512>(a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, ticket, s); break;
     }
 }
 
@@ -607,10 +619,11 @@ void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t r
     if (m <= 0) return;
     if (max_bin < 1) max_bin = 1;
     if (max_bin > 5) max_bin = 5;
-    (void)ctr;
+    uint32_t* ticket = &ctr->scan_ticket;
     if (max_bin == 1) {
         size_t tiles = (size_t)((m + TINY_TILE - 1) / TINY_TILE);
         cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
+        cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s);
         static int quad = -1;   // SPADA_B200_TINY=warp keeps the one-row-per-warp kernel (A/B measurements)
         if (quad < 0) {
             const char* e = getenv("SPADA_B200_TINY");
@@ -620,24 +633,24 @@ void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t r
         if (quad) {
             if (narrow)
                 k_fused_tiny4<uint32_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
-                    a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+                    a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state, ticket);
             else
                 k_fused_tiny4<uint64_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
-                    a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+                    a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state, ticket);
         } else if (narrow)
             k_fused_tiny<uint32_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
-                a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+                a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state, ticket);
         else
             k_fused_tiny<uint64_t><<<(unsigned)tiles, FUSED_WARPS * 32, 0, s>>>(
-                a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state);
+                a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, (unsigned long long*)tile_state, ticket);
         return;
     }
     int sbk = 4 + max_bin;
     bool narrow = (uint64_t)b.cols < (1ull << (32 - sbk));  // strict: a valid key is never the all-ones sentinel
     if (narrow)
-        fused_dispatch<uint32_t>(max_bin, a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s);
+        fused_dispatch<uint32_t>(max_bin, a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, ticket, s);
     else
-        fused_dispatch<uint64_t>(max_bin, a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, s);
+        fused_dispatch<uint64_t>(max_bin, a, b, row_begin, m, flops, pre_nnz, c_ptr, c_col, c_val, tile_state, ticket, s);
 }
 
 }  // namespace spada

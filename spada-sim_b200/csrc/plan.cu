@@ -29,10 +29,12 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
         uint32_t* __restrict__ flops, uint32_t* __restrict__ long_list, PlanCounters* ctr) {
     __shared__ uint32_t s_rows[NUM_BINS];
     __shared__ unsigned long long s_prod[NUM_BINS];
+    __shared__ uint32_t s_max;
     if (threadIdx.x < NUM_BINS) {
         s_rows[threadIdx.x] = 0;
         s_prod[threadIdx.x] = 0;
     }
+    if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * FLOPS_THREADS + threadIdx.x;
     int b = -1;   // bin of this thread's row, -1: nothing to count here
@@ -47,6 +49,7 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
             uint32_t f32 = f > 0xffffffffull ? 0xffffffffu : (uint32_t)f;
             flops[i] = f32;
             b = bin_of(f32);
+            if (f32 > ESC_MAX_PRODUCTS) atomicMax(&s_max, f32);
             if (f >> 32) {   // cannot happen below 2^32 products per row; counted directly
                 atomicAdd(&s_rows[b], 1u);
                 atomicAdd(&s_prod[b], f);
@@ -72,6 +75,7 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
         atomicAdd(&ctr->bin_products[threadIdx.x], s_prod[threadIdx.x]);
         atomicAdd(&ctr->total_products, s_prod[threadIdx.x]);
     }
+    if (threadIdx.x == 0 && s_max) atomicMax(&ctr->max_flops, s_max);
 }
 
 // K1b: long A rows, one CTA of 1024 threads per row (persistent over the deferred list); four
@@ -110,6 +114,7 @@ k_flops_long(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin,
             atomicAdd(&ctr->bin_rows[b], 1u);
             atomicAdd(&ctr->bin_products[b], t);
             atomicAdd(&ctr->total_products, t);
+            atomicMax(&ctr->max_flops, f32);
         }
         __syncthreads();
     }
@@ -267,62 +272,104 @@ void launch_scan_u32_i64(const uint32_t* in, int64_t n, int64_t* out, uint64_t* 
 }
 
 // ---------------------------------------------------------------------------------------
-// Two-phase mode, sort bins: the first pass writes finished rows to a scratch CSR laid out by
-// product count (an upper bound of every row's nnz); after the row_ptr scan they are copied to
-// their final place.  k_mask_sorted yields the per-row scratch sizes, k_copy_rows moves the rows.
-__global__ void k_mask_sorted(const uint32_t* __restrict__ flops, int64_t m, uint32_t limit, uint32_t* __restrict__ out) {
+// The first pass writes finished rows to a scratch CSR laid out by product count (an upper bound of every
+// row's nnz); after the row_ptr scan they are copied to their final place.  k_mask_sorted yields the
+// per-row scratch sizes, k_copy_rows moves the rows.
+__global__ void k_mask_sorted(const uint32_t* __restrict__ flops, int64_t m, uint32_t lo, uint32_t hi,
+                              uint32_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) {
         uint32_t f = flops[i];
-        out[i] = (f <= limit) ? f : 0u;
+        out[i] = (f > lo && f <= hi) ? f : 0u;
     }
 }
-// limit: rows with at most that many products go through the scratch CSR
-void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t limit, uint32_t* out, cudaStream_t s) {
-    if (m > 0) k_mask_sorted<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(flops, m, limit, out);
+// rows with lo < products <= hi go through the scratch CSR
+void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t lo, uint32_t hi, uint32_t* out, cudaStream_t s) {
+    if (m > 0) k_mask_sorted<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(flops, m, lo, hi, out);
 }
 
+// The copy out of the scratch CSR is also where the C shards of a multi-GPU run are exchanged: dst.col[d] / dst.val[d]
+// are the C buffers of every GPU (this one first, the peers through NVLink peer mappings), so one read of the scratch
+// row feeds the local store and the stores into every peer -- the all-gather of C fused into the kernel that writes C
+// (SURVEY.md 8e "fusion candidate").  With a single destination it is a plain copy.
 constexpr int COPY_WARPS = 8;
+template <int ND>
 __global__ void __launch_bounds__(COPY_WARPS * 32)
-k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, uint32_t limit, const int64_t* __restrict__ t_ptr,
+k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, uint32_t lo, uint32_t hi, const int64_t* __restrict__ t_ptr,
             const int32_t* __restrict__ t_col, const double* __restrict__ t_val, const int64_t* __restrict__ c_ptr,
-            int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+            CopyDst dst) {
     const int lane = lane_id();
     const int64_t r = (int64_t)blockIdx.x * COPY_WARPS + (threadIdx.x >> 5);
     if (r >= m) return;
     const uint32_t f = flops[r];
-    if (f == 0 || f > limit) return;  // empty rows have nothing; rows above the limit are written by their own kernels
-    const int64_t src = t_ptr[r], dst = c_ptr[r];
-    const int n = (int)(c_ptr[r + 1] - dst);
+    if (f <= lo || f > hi) return;  // rows outside (lo, hi] are written by their own kernels
+    const int64_t src = t_ptr[r], d0 = c_ptr[r];
+    const int n = (int)(c_ptr[r + 1] - d0);
+    const int64_t o = d0 + dst.off;
     for (int j = lane; j < n; j += 32) {
-        st_out(c_col + dst + j, t_col[src + j]);
-        st_out(c_val + dst + j, t_val[src + j]);
+        const int32_t c = t_col[src + j];
+        const double v = t_val[src + j];
+        if (ND == 1) {
+            st_out(dst.col[0] + o + j, c);
+            st_out(dst.val[0] + o + j, v);
+        } else {
+            for (int d = 0; d < dst.n; ++d) {
+                st_out(dst.col[d] + o + j, c);
+                st_out(dst.val[d] + o + j, v);
+            }
+        }
     }
 }
-void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t limit, const int64_t* t_ptr, const int32_t* t_col,
-                      const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
-    if (m > 0)
-        k_copy_rows<<<(unsigned)((m + COPY_WARPS - 1) / COPY_WARPS), COPY_WARPS * 32, 0, s>>>(flops, m, limit, t_ptr, t_col,
-                                                                                          t_val, c_ptr, c_col, c_val);
+void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t lo, uint32_t hi, const int64_t* t_ptr,
+                      const int32_t* t_col, const double* t_val, const int64_t* c_ptr, const CopyDst& dst,
+                      cudaStream_t s) {
+    if (m <= 0) return;
+    const unsigned grid = (unsigned)((m + COPY_WARPS - 1) / COPY_WARPS);
+    if (dst.n == 1) k_copy_rows<1><<<grid, COPY_WARPS * 32, 0, s>>>(flops, m, lo, hi, t_ptr, t_col, t_val, c_ptr, dst);
+    else k_copy_rows<8><<<grid, COPY_WARPS * 32, 0, s>>>(flops, m, lo, hi, t_ptr, t_col, t_val, c_ptr, dst);
 }
 
-// long scratch rows (the heavy bin in one-shot mode): one CTA per row of the list, a warp per row would leave
-// a tail of 300-iteration warps behind the rest of the copy
+// long scratch rows: one CTA per row of the list, a warp per row would leave a tail of 300-iteration warps behind
+// the rest of the copy
+template <int ND>
 __global__ void __launch_bounds__(256)
 k_copy_rows_list(const uint32_t* __restrict__ rows_list, const int64_t* __restrict__ t_ptr,
                  const int32_t* __restrict__ t_col, const double* __restrict__ t_val, const int64_t* __restrict__ c_ptr,
-                 int32_t* __restrict__ c_col, double* __restrict__ c_val) {
+                 CopyDst dst) {
     const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
-    const int64_t src = t_ptr[r], dst = c_ptr[r];
-    const int64_t n = c_ptr[r + 1] - dst;
+    const int64_t src = t_ptr[r], d0 = c_ptr[r];
+    const int64_t n = c_ptr[r + 1] - d0;
+    const int64_t o = d0 + dst.off;
     for (int64_t j = threadIdx.x; j < n; j += 256) {
-        st_out(c_col + dst + j, t_col[src + j]);
-        st_out(c_val + dst + j, t_val[src + j]);
+        const int32_t c = t_col[src + j];
+        const double v = t_val[src + j];
+        if (ND == 1) {
+            st_out(dst.col[0] + o + j, c);
+            st_out(dst.val[0] + o + j, v);
+        } else {
+            for (int d = 0; d < dst.n; ++d) {
+                st_out(dst.col[d] + o + j, c);
+                st_out(dst.val[d] + o + j, v);
+            }
+        }
     }
 }
 void launch_copy_rows_list(const uint32_t* rows_list, uint32_t n_rows, const int64_t* t_ptr, const int32_t* t_col,
-                           const double* t_val, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s) {
-    if (n_rows > 0) k_copy_rows_list<<<n_rows, 256, 0, s>>>(rows_list, t_ptr, t_col, t_val, c_ptr, c_col, c_val);
+                           const double* t_val, const int64_t* c_ptr, const CopyDst& dst, cudaStream_t s) {
+    if (n_rows == 0) return;
+    if (dst.n == 1) k_copy_rows_list<1><<<n_rows, 256, 0, s>>>(rows_list, t_ptr, t_col, t_val, c_ptr, dst);
+    else k_copy_rows_list<8><<<n_rows, 256, 0, s>>>(rows_list, t_ptr, t_col, t_val, c_ptr, dst);
+}
+
+// row pointers of a shard, shifted by the shard's global nnz offset, into the row_ptr of every GPU
+__global__ void k_shift_row_ptr(const int64_t* __restrict__ ptr, int64_t m, int64_t off, RowPtrDst dst, int64_t row_off) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > m) return;
+    const int64_t v = ptr[r] + off;
+    for (int d = 0; d < dst.n; ++d) dst.ptr[d][row_off + r] = v;
+}
+void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const RowPtrDst& dst, int64_t row_off, cudaStream_t s) {
+    k_shift_row_ptr<<<(unsigned)((m + 1 + 255) / 256), 256, 0, s>>>(ptr, m, off, dst, row_off);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -15,7 +15,9 @@ from . import _abi
 from ._abi import check, lib
 
 U64_MAX = (1 << 64) - 1
-BIN_NAMES = ["empty", "32", "64", "128", "256", "512", "1024", "2048", "4096", "heavy", "huge"]
+# bin b holds rows with at most 32 * 2^(b-1) intermediate products; bins above 4096 are the LONG rows (chunk sorts + merge levels)
+BIN_NAMES = ["empty"] + [str(32 << (b - 1)) for b in range(1, 29)]
+LONG_BINS = BIN_NAMES[9:]
 
 
 def _ptr(a: np.ndarray, ct):

@@ -10,8 +10,8 @@ use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
 
 pub const SPADA_B200_OK: c_int = 0;
-pub const SPADA_B200_MAX_BINS: usize = 16;
-pub const SPADA_B200_MAX_LAUNCHES: usize = 48;
+pub const SPADA_B200_MAX_BINS: usize = 32;
+pub const SPADA_B200_MAX_LAUNCHES: usize = 64;
 pub const SPADA_B200_FLAG_VALIDATE: u32 = 1;
 pub const SPADA_B200_FLAG_TWO_PHASE: u32 = 2;
 pub const SPADA_B200_FLAG_SINGLE_PASS: u32 = 4;

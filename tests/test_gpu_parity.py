@@ -1,8 +1,10 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle -- needs a B200.
 
 Bar: row_ptr and col_idx bit-exact; values within relative 1e-12 per
-entry in f64 (TOL below).  The sort-based bins (<= 4096 intermediate products per row) fix the
-oracle's summation order, so there the values are checked bit-exact as well.
+entry in f64 (TOL below).  Every path of the engine sums the products of one C[i,j] in the
+oracle's order (ascending k, left to right) -- the sort bins through the arrival index in the sort
+key, the long rows (> 4096 products) through stable merges of unreduced chunks -- so values are
+checked BIT-EXACT everywhere, with signed (cancelling) operands.
 """
 import hashlib
 import json
@@ -49,15 +51,14 @@ def run(engine, oracle, a, b, exact=True, usize=False):
 # ---- every bin, forced individually ---------------------------------------------------------
 @pytest.mark.parametrize("ka,lb,expect_bin", [
     (1, 1, "32"), (4, 8, "32"), (5, 5, "32"), (8, 8, "64"), (10, 12, "128"), (16, 16, "256"),
-    (20, 25, "512"), (32, 32, "1024"), (40, 50, "2048"), (64, 64, "4096"), (70, 100, "heavy"), (128, 64, "heavy"),
-    (300, 40, "heavy"), (300, 230, "huge"),
+    (20, 25, "512"), (32, 32, "1024"), (40, 50, "2048"), (64, 64, "4096"), (70, 100, "8192"), (128, 64, "8192"),
+    (300, 40, "16384"), (300, 230, "131072"), (517, 300, "262144"),
 ])
 def test_each_bin(engine, oracle, ka, lb, expect_bin):
     m, k, n = 257, 600, 5000
-    vals = "uniform" if expect_bin in ("heavy", "huge") else "signed"   # heavy bin: order not fixed -> no cancellation
-    a = random_csr(m, k, row_nnz=ka, seed=ka * 7 + lb, values=vals)
-    b = random_csr(k, n, row_nnz=lb, seed=ka * 11 + lb, values=vals)
-    _, st = run(engine, oracle, a, b, exact=(expect_bin not in ("heavy", "huge")))
+    a = random_csr(m, k, row_nnz=ka, seed=ka * 7 + lb, values="signed")
+    b = random_csr(k, n, row_nnz=lb, seed=ka * 11 + lb, values="signed")
+    _, st = run(engine, oracle, a, b)
     assert list(st["bins"].keys()) == [expect_bin], st["bins"]
     assert st["bins"][expect_bin]["rows"] == m
 
@@ -68,25 +69,16 @@ def test_key_width_paths(engine, oracle, n_cols):
     for ka, lb in [(4, 6), (16, 16), (40, 50), (80, 90)]:
         a = random_csr(130, 300, row_nnz=ka, seed=3)
         b = random_csr(300, n_cols, row_nnz=lb, seed=4)
-        run(engine, oracle, a, b, exact=(ka * lb <= 4096))   # the heavy bin is checked at TOL
+        run(engine, oracle, a, b)
 
 
 def test_mixed_bins_and_permutation(engine, oracle):
     rng = np.random.default_rng(5)
     lens = rng.choice([0, 1, 3, 8, 20, 60, 150, 400], size=3000, p=[.1, .2, .2, .2, .15, .1, .04, .01])
-    a = random_csr(3000, 2000, row_nnz=lens, seed=6)
-    b = random_csr(2000, 4000, row_nnz=rng.choice([0, 2, 9, 30], size=2000), seed=7)
-    r = engine.spgemm(a, b)
-    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
-    st = r.stats()
-    ip, ix, dx = r.to_host()
-    assert np.array_equal(ip, ref[0]) and np.array_equal(ix, ref[1])
+    a = random_csr(3000, 2000, row_nnz=lens, seed=6, values="signed")
+    b = random_csr(2000, 4000, row_nnz=rng.choice([0, 2, 9, 30], size=2000), seed=7, values="signed")
+    _, st = run(engine, oracle, a, b)
     assert len(st["bins"]) >= 5
-    # rows handled by the sort-based bins are bit-exact; the heavy bin is within TOL
-    f = oracle.flops(a, b)
-    light = np.repeat(f <= 4096, np.diff(ref[0]))
-    assert np.array_equal(dx[light].view(np.uint64), ref[2][light].view(np.uint64))
-    assert (np.abs(dx[~light] - ref[2][~light]) <= TOL * np.abs(ref[2][~light])).all()
 
 
 # ---- the reference's own operand ------------------------------------------------------------
@@ -94,14 +86,16 @@ def test_cari_golden(engine, oracle, cari, spada):
     known = json.load(open(os.path.join(GOLDEN, "cari_known_answers.json")))
     g = spada.GEMM.from_mat("cari", cari)
     assert g.b.shape == (1200, 400)
-    r, st = run(engine, oracle, g.a, g.b, exact=False)  # 144k products per row -> heavy bin
+    r, st = run(engine, oracle, g.a, g.b)  # 144k products per row -> long rows, 6 merge levels; bit-exact
     ip, ix, dx = r.to_host()
     sha = lambda x: hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()
     assert sha(ip.astype("<i8")) == known["sha256_indptr_i64"]
     assert sha(ix.astype("<i8")) == known["sha256_indices_i64"]
     assert st["products"] == known["products"] and st["nnz_c"] == known["c_nnz"]
     assert abs(dx.sum() - known["c_data_sum"]) <= 1e-9
-    assert np.allclose(dx[:5], known["row0_vals"], rtol=TOL, atol=0)
+    assert dx[:5].tolist() == known["row0_vals"]
+    assert dx.sum() == known["c_data_sum"]
+    assert sha(dx.astype("<f8")) == known["sha256_data_f64"]
 
 
 # ---- edge cases of SURVEY.md 8a ---------------------------------------------------------------
@@ -167,7 +161,7 @@ def test_long_rows_and_first_last(engine, oracle):
     lens = np.full(64, 3); lens[0] = 1500; lens[-1] = 700; lens[10] = 0
     a = random_csr(64, 4000, row_nnz=lens, seed=8)
     b = random_csr(4000, 30000, row_nnz=np.random.default_rng(9).integers(0, 12, size=4000), seed=10)
-    run(engine, oracle, a, b, exact=False)
+    run(engine, oracle, a, b)
 
 
 def test_many_empty_b_rows_in_a_row(engine, oracle):
@@ -199,26 +193,19 @@ def test_skewed_columns(engine, oracle, ka, lb, width):
     # a handful of hot words in the heavy bin's bitmap
     a = random_csr(120, 400, row_nnz=ka, seed=ka + 1)
     b = _widen(random_csr(400, width, row_nnz=min(lb, width), seed=lb + 2), 1 << 20, shift=(1 << 19) + 77)
-    run(engine, oracle, a, b, exact=(ka * min(lb, width) <= 4096))
+    run(engine, oracle, a, b)
 
 
 def test_long_rows_mixed_lengths(engine, oracle):
     # rows of 513 .. ~40000 products side by side: CTA-per-row sort bins and the heavy bin in one call
     rng = np.random.default_rng(21)
     lens = rng.choice([0, 30, 70, 130, 260, 520, 900, 2500], size=400, p=[.05, .2, .2, .2, .15, .1, .07, .03])
-    a = random_csr(400, 6000, row_nnz=lens, seed=22)
-    b = random_csr(6000, 1 << 20, row_nnz=rng.integers(10, 26, size=6000), seed=23)
-    r = engine.spgemm(a, b)
-    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
-    ip, ix, dx = r.to_host()
-    assert np.array_equal(ip, ref[0]) and np.array_equal(ix, ref[1])
-    f = oracle.flops(a, b)
-    one_pass = np.repeat(f <= 4096, np.diff(ref[0]))
-    assert np.array_equal(dx[one_pass].view(np.uint64), ref[2][one_pass].view(np.uint64))
-    assert (np.abs(dx[~one_pass] - ref[2][~one_pass]) <= TOL * np.abs(ref[2][~one_pass])).all()
-    # tiny column space: every output column is hit hundreds of times
-    b2 = random_csr(6000, 48, row_nnz=rng.integers(8, 20, size=6000), seed=24)
-    run(engine, oracle, a, b2, exact=False)
+    a = random_csr(400, 6000, row_nnz=lens, seed=22, values="signed")
+    b = random_csr(6000, 1 << 20, row_nnz=rng.integers(10, 26, size=6000), seed=23, values="signed")
+    run(engine, oracle, a, b)
+    # tiny column space: every output column is hit hundreds of times (long runs of equal columns across chunks)
+    b2 = random_csr(6000, 48, row_nnz=rng.integers(8, 20, size=6000), seed=24, values="signed")
+    run(engine, oracle, a, b2)
 
 
 @pytest.mark.parametrize("pad", ["0", "1", "16"])
@@ -234,7 +221,7 @@ def test_fiber_store_layouts(spada, oracle, monkeypatch, pad):
             a = random_csr(150, 700, row_nnz=ka, seed=ka + 40)
             b = random_csr(700, n, row_nnz=rng.integers(0, 2 * lb, size=700), seed=lb + 41)
             # resident operands: B's fiber store is built on its first use (the host-level call skips it)
-            check(e.spgemm_dev(e.upload(a), e.upload(b)), oracle.spgemm(a, b, threads=oracle.max_threads()), False)
+            check(e.spgemm_dev(e.upload(a), e.upload(b)), oracle.spgemm(a, b, threads=oracle.max_threads()), True)
         a = random_csr(400, 400, density=0.03, seed=42)     # A x A: one operand on both sides
         da = e.upload(a)
         check(e.spgemm_dev(da, da), oracle.spgemm(a, a, threads=oracle.max_threads()), True)
@@ -272,27 +259,49 @@ def test_transposed_operand_feeds_the_hot_path(engine, oracle, cari, spada):
     g = spada.GEMM.from_mat("cari", cari)                 # host transpose, as the reference does it
     da = engine.upload(g.a)
     db = engine.transpose(da)                             # device transpose
-    check(engine.spgemm_dev(da, db), oracle.spgemm(g.a, g.b, threads=oracle.max_threads()), False)
+    check(engine.spgemm_dev(da, db), oracle.spgemm(g.a, g.b, threads=oracle.max_threads()), True)
 
 
-def test_huge_bin_in_waves(spada, oracle, monkeypatch):
-    # a 1 MiB bitmap workspace forces the huge bin through a dozen waves: one-shot sweeps into scratch rows
-    # (default) and the two-sweep path (symbolic, then numeric rebuilding every wave's bitmaps) must agree
+def test_long_rows_in_waves(spada, oracle, monkeypatch):
+    # a 1 MiB ping-pong budget forces the long rows through many waves (level bins cut by their per-row bound)
     if spada.device_count() == 0:
         pytest.skip("no CUDA device")
-    a = random_csr(257, 600, row_nnz=300, seed=61)
-    b = random_csr(600, 200000, row_nnz=230, seed=62)
+    rng = np.random.default_rng(60)
+    lens = rng.choice([10, 40, 90, 300, 600], size=300)
+    a = random_csr(300, 800, row_nnz=lens, seed=61, values="signed")
+    b = random_csr(800, 200000, row_nnz=rng.integers(100, 260, size=800), seed=62, values="signed")
     ref = oracle.spgemm(a, b, threads=oracle.max_threads())
-    monkeypatch.setenv("SPADA_B200_HEAVY_WS_MB", "1")
-    for oneshot in ("1", "0"):
-        monkeypatch.setenv("SPADA_B200_HUGE_ONESHOT", oneshot)
-        e = spada.Engine(two_phase=True)
-        try:
-            r = e.spgemm(a, b)
-            assert list(r.stats()["bins"]) == ["huge"]
-            check(r, ref, False)
-        finally:
-            e.close()
+    for mb in ("1", "64"):
+        monkeypatch.setenv("SPADA_B200_LONG_WS_MB", mb)
+        for serial in (False, True):
+            e = spada.Engine(two_phase=True, serial=serial)
+            try:
+                r = e.spgemm(a, b)
+                assert set(r.stats()["bins"]) <= set(spada.engine.LONG_BINS) | {"4096", "2048", "1024"}
+                check(r, ref, True)
+            finally:
+                e.close()
+
+
+def test_long_row_shapes(engine, oracle):
+    # the shapes a chunked row can take: one B row longer than several chunks, a row of exactly k * 4096 products,
+    # a row one product over, A entries that meet empty B rows between the chunks, and duplicate-heavy columns
+    k, n = 64, 50000
+    lb = np.zeros(k, dtype=np.int64)
+    lb[0] = 20000; lb[1] = 4096; lb[2] = 4096; lb[3] = 1; lb[5] = 8191; lb[7] = 3000; lb[9:20] = 700
+    b = random_csr(k, n, row_nnz=lb, seed=70, values="signed")
+    rows = [[0], [1, 2], [1, 2, 3], [0, 4, 5, 6, 7], list(range(64)), [4, 6, 8], [5, 8], list(range(9, 20)), [0, 5]]
+    ip = np.cumsum([0] + [len(r) for r in rows])
+    ix = np.concatenate([np.array(r) for r in rows])
+    a = sp.csr_matrix((np.random.default_rng(71).uniform(-1, 1, len(ix)), ix, ip), shape=(len(rows), k))
+    run(engine, oracle, a, b)
+    # few columns: every chunk carries every column, the runs of equal columns span all chunks
+    b2 = random_csr(k, 30, row_nnz=np.minimum(lb, 30), seed=72, values="signed")
+    a2 = random_csr(40, k, row_nnz=60, seed=73, values="signed")
+    b2 = sp.vstack([b2] * 1).tocsr()
+    a3 = sp.hstack([a2] * 6).tocsr(); a3.sort_indices()
+    b3 = sp.vstack([b2] * 6).tocsr(); b3.sort_indices()
+    run(engine, oracle, a3, b3)
 
 
 def test_usize_layout_matches(engine, oracle):
@@ -334,7 +343,7 @@ def test_row_shards_concatenate(engine, oracle):
 
 # ---- BASELINE configs, scaled down, against the oracle ------------------------------------------
 @pytest.mark.parametrize("name,scale,exact", [("poisson", 1 / 16, True), ("er", 1 / 64, True),
-                                              ("rmat", 1 / 128, False), ("rect", 1 / 64, False)])
+                                              ("rmat", 1 / 128, True), ("rect", 1 / 64, True)])
 def test_configs_scaled(engine, oracle, spada, name, scale, exact):
     a, b = spada.workloads.build(name, scale)
     run(engine, oracle, a, b, exact=exact)

@@ -10,13 +10,13 @@ rng = np.random.default_rng(7)
 for mode in ({"two_phase": True}, {"single_pass": True}):
     e = pkg.Engine(**mode)
     for ka, lb, n in [(3, 4, 300), (5, 5, 5000), (12, 2, 64), (8, 8, 5000), (16, 16, 5000), (20, 25, 5000), (32, 32, 5000),
-                      (64, 64, 5000), (70, 100, 5000), (300, 230, 3000)]:
-        a = random_csr(40, 600, row_nnz=rng.integers(max(ka - 2, 0), ka + 1, size=40), seed=ka)
-        b = random_csr(600, n, row_nnz=rng.integers(max(lb - 2, 0), lb + 1, size=600), seed=lb)
+                      (64, 64, 5000), (70, 100, 5000), (300, 230, 3000), (120, 300, 40)]:
+        a = random_csr(40, 600, row_nnz=rng.integers(max(ka - 2, 0), ka + 1, size=40), seed=ka, values="signed")
+        b = random_csr(600, n, row_nnz=np.minimum(rng.integers(max(lb - 2, 0), lb + 1, size=600), n), seed=lb, values="signed")
         r = e.spgemm(a, b)
         ip, ix, dx = r.to_host()
         ref = oracle.spgemm(a, b, threads=2)
-        ok = np.array_equal(ip, ref[0]) and np.array_equal(ix, ref[1]) and np.allclose(dx, ref[2], rtol=1e-12, atol=0)
+        ok = np.array_equal(ip, ref[0]) and np.array_equal(ix, ref[1]) and np.array_equal(dx.view(np.uint64), ref[2].view(np.uint64))
         print(mode, ka, lb, n, "ok" if ok else "MISMATCH", flush=True)
     a = random_csr(300, 900, row_nnz=rng.integers(0, 30, size=300), seed=99)
     t = e.transpose(e.upload(a)).to_scipy()
