@@ -200,17 +200,33 @@ def cpu_oracle_rate(a, b, target_seconds, threads=None):
     return 2.0 * prods / dt / 1e9, threads, f"rows [0,{r}) of A = {prods} of {total} products", dt
 
 
+def workload_config(pkg, args, a, b, products=None, nnz_c=None):
+    """The `config` object both arms print: same keys and values for the same workload."""
+    m, k, n = a.shape[0], a.shape[1], b.shape[1]
+    known = pkg.workloads.KNOWN.get(args.workload) if args.scale >= 1.0 else None
+    if known:
+        products = products if products is not None else known[3]
+        nnz_c = nnz_c if nnz_c is not None else known[4]
+    alg = pkg.workloads.algorithmic_bytes(a.nnz, m, b.nnz, k, nnz_c) if nnz_c else None
+    return {"workload": WORKLOAD_DESC[args.workload], "scale": args.scale, "m": m, "k": k, "n": n, "nnz_a": int(a.nnz),
+            "nnz_b": int(b.nnz), "products": products, "nnz_c": nnz_c,
+            "l2": ("inputs+output larger than L2 (no flush)" if alg and alg > 4 * 126e6 else "working set near L2 size")}
+
+
 def run_reference(args, pkg):
     """--impl reference: the reference's CPU implementation of the path.  The Rust simulator cannot
     be built in this image (no cargo, un-vendored crates), so this times the oracle port with every
-    host thread, one bounded sample per step."""
+    host core (set explicitly: torchrun exports OMP_NUM_THREADS=1), one bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     a, b = load_workload(pkg, args.workload, args.scale)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
-    threads = oracle.max_threads()
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     lens_b = np.diff(b.indptr).astype(np.int64)
     per_row = np.add.reduceat(np.append(lens_b[a.indices], 0), a.indptr[:-1].astype(np.int64))
     per_row[np.diff(a.indptr) == 0] = 0
@@ -232,12 +248,12 @@ def run_reference(args, pkg):
     dt = time.perf_counter() - t
     v = 2.0 * prods * args.steps / dt / 1e9
     sample = f"rows [0,{r}) of A = {prods} of {total} products per step"
+    cfg = workload_config(pkg, args, a, b, products=total if args.scale < 1.0 else None)
     print(json.dumps({
         "impl": "reference", "metric": "SpGEMM GFLOP/s (2 x intermediate products / time)", "value": v,
         "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload], "scale": args.scale},
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -254,6 +270,16 @@ def pinned_copy(pkg, arr):
     return v, p
 
 
+def add_launches(per_launch, stats):
+    for L in stats["launches"]:
+        d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": 0, "rows": L["rows"], "grid": L["grid"]})
+        d["ms"] += L["ms"]; d["n"] += 1; d["products"] += L["products"]
+
+
+NVLINK_PEAK_GBS = 770.0   # measured peer-copy bandwidth per direction, /opt/skills/guides/B200_PROFILING.md
+PLACEMENT_KERNELS = ("copy_rows", "copy_gather", "row_ptr_gather")   # move finished rows: no algorithmic work
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -264,12 +290,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="<1 shrinks the workload (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--two-phase", action="store_true", help="force separate symbolic/numeric passes (exact-size C)")
+    ap.add_argument("--two-phase", action="store_true", help="force the scratch-row pass for every row (exact-size C)")
     ap.add_argument("--single-pass", action="store_true", help="force the fused single pass for rows <= 512 products")
-    ap.add_argument("--gather-waves", type=int, default=1,
-                    help="N > 1: row waves per rank; with more than one, the all-gather of wave j overlaps the computation "
-                         "of wave j+1 (measured at N=2 on rect: 6.9 / 8.7 / 9.3 ms per step for 1 / 2 / 3 waves -- the NCCL "
-                         "copy kernels queue behind the SpGEMM kernels and every wave adds host round trips, so 1 is the default)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = the kernel that places C's rows stores them into every rank's buffers over NVLink "
+                         "(the product); 'nccl' = separate NCCL all-gather after the compute (the baseline it replaces)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -291,151 +316,206 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     D = importlib.import_module("spada-sim_b200.distributed")
 
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        t0, t1 = ev(), ev()
+        t0.record()
+        out = fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return out, t0.elapsed_time(t1)
+
     stream = torch.cuda.current_stream()
     eng = pkg.Engine(device=local_rank, validate=True, stream=stream.cuda_stream, two_phase=args.two_phase,
                      single_pass=args.single_pass)
 
-    # ---- operands resident in HBM (not timed) ---------------------------------------------------
+    # ---- operands resident in HBM (outside the timed steps; reported in `setup`) ------------------------------
     a = b = None
     if rank == 0:
         a, b = load_workload(pkg, args.workload, args.scale)
+    setup = {}
+    pg = None
     if world == 1:
         da = eng.upload(a)
         db = da if b is a else eng.upload(b)
+        setup["prepare_ms"] = db.prepare()                   # fiber store of B (first use as B would build it anyway)
         lo, hi = 0, a.shape[0]
         dims = (a.shape[0], a.shape[1], b.shape[1], a.nnz, b.nnz)
+        same_operand = b is a
     else:
-        da, _ka = D.broadcast_csr(eng, a, device)            # NCCL broadcast over NVLink
+        D.broadcast_csr(eng, a, device)                      # warm-up of the communicator
+        (da, _ka), bc_a = timed(lambda: D.broadcast_csr(eng, a, device))   # NCCL broadcast over NVLink
         same = [b is a] if rank == 0 else [None]
         dist.broadcast_object_list(same, src=0)
-        db, _kb = (da, _ka) if same[0] else D.broadcast_csr(eng, b, device)
-        db.prepare()                                         # fiber store of the replicated B (not timed, like the broadcast)
-        waves = max(1, args.gather_waves)
-        bounds = D.plan_bounds(eng, da, db, world * waves, device)   # shard j * world + r = wave j of rank r
-        lo, hi = 0, 0
+        same_operand = same[0]
+        bc_b = 0.0
+        if same_operand:
+            db, _kb = da, _ka
+        else:
+            (db, _kb), bc_b = timed(lambda: D.broadcast_csr(eng, b, device))
+        setup["broadcast_ms"] = {"A": bc_a, "B": bc_b,
+                                 "note": "host arrays of rank 0 -> its GPU -> ncclBroadcast to every rank (SURVEY 8e); once per operand"}
+        setup["prepare_ms"] = db.prepare()
+        bounds, setup["plan_ms"] = timed(lambda: D.plan_bounds(eng, da, db, world, device))
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         dims = (da.shape[0], da.shape[1], db.shape[1], da.nnz, db.nnz)
     m, k, n, nnz_a, nnz_b = dims
 
     # GEMM::from_mat's transpose (gemm.rs:41-53) on the device, timed once for the record (not part of a step:
     # the workload builder already holds B = A^T on the host, like the reference after its loader)
-    transpose_ms = None
-    if world == 1 and b is not a and a.shape[0] != a.shape[1]:
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world == 1 and not same_operand and a.shape[0] != a.shape[1]:
         eng.transpose(da).free()                             # warm-up (pool blocks)
-        t0.record()
-        dt = eng.transpose(da)
-        t1.record()
-        torch.cuda.synchronize()
+        dt, setup["device_transpose_ms"] = timed(lambda: eng.transpose(da))
         assert dt.shape == db.shape and dt.nnz == db.nnz
-        transpose_ms = t0.elapsed_time(t1)
         dt.free()
 
-    gathered = None
-    wave_gather = None
     if world > 1:
         cap = torch.zeros(1, dtype=torch.int64, device=device)
         if rank == 0:
             cap[0] = eng.flops(da, db)               # nnz(C) <= intermediate products
         dist.broadcast(cap, src=0)
-        wave_gather = D.WaveGather(m, int(cap[0]), device)
+        if args.gather == "peer":
+            pg = D.PeerGather(eng, m, n, int(cap[0]), device)
+        else:
+            nccl_out = (torch.empty(m + 1, dtype=torch.int64, device=device),
+                        torch.empty(int(cap[0]), dtype=torch.int32, device=device),
+                        torch.empty(int(cap[0]), dtype=torch.float64, device=device))
 
-    def step():
-        """One pass of the hot path; returns the stats of the engine calls it made."""
+    gathered = None
+
+    def step(compute_only=False):
+        """One pass of the hot path; returns the engine stats of this rank's part."""
         nonlocal gathered
         if world == 1:
-            return [eng.spgemm_dev(da, db, lo, hi).stats()]
-        wave_gather.reset()
-        stats = []
-        for j in range(waves):
-            s_ = j * world + rank
-            res = eng.spgemm_dev(da, db, int(bounds[s_]), int(bounds[s_ + 1]))
-            stats.append(res.stats())
+            return eng.spgemm_dev(da, db, lo, hi).stats()
+        if pg is not None:
+            return pg.step(da, db, lo, hi, compute_only=compute_only)
+        res = eng.spgemm_dev(da, db, lo, hi)
+        if not compute_only:
             lp, lc, lv = D.result_views(res, device)
-            wave_gather.add(lp, lc, lv, keepalive=res)       # asynchronous: wave j travels while wave j+1 is computed
-        gathered = wave_gather.finish()
-        return stats
+            gathered = D.allgather_csr(lp, lc, lv, out=nccl_out)
+            torch.cuda.current_stream().synchronize()   # the Result's pool blocks may be reused once it is freed
+        return res.stats()
 
     for _ in range(args.warmup):
-        sts = step()
-    tot = torch.tensor([sum(x["products"] for x in sts), sum(x["nnz_c"] for x in sts)], dtype=torch.int64, device=device)
-    if world > 1:
-        dist.all_reduce(tot)
-    products, nnz_c = int(tot[0]), int(tot[1])
-    st0 = {"products": sum(x["products"] for x in sts), "bins": sts[0]["bins"]}
+        st = step()
+    if world > 1 and pg is not None:
+        nnz_c = pg.own.nnz
+        products = int(cap[0])
+    elif world > 1:
+        nnz_c = int(gathered[0][-1])
+        products = int(cap[0])
+    else:
+        products, nnz_c = st["products"], st["nnz_c"]
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
     launches = 0
-    per_launch = {}
-    compute_ms = 0.0
     t_wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        for st in step():                     # host-side copies of event timings already taken by the engine
-            launches += st["n_launches"]
-            compute_ms += st["ms_total"]
-            for L in st["launches"]:
-                d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": 0, "rows": L["rows"], "grid": L["grid"]})
-                d["ms"] += L["ms"]; d["n"] += 1; d["products"] += L["products"]
+        launches += step()["n_launches"]
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
-    ms = torch.tensor([e0.elapsed_time(e1), compute_ms], dtype=torch.float64, device=device)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms, compute_ms = float(ms[0]), float(ms[1])
+    total_ms = float(ms[0])
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_per_step = total_ms / args.steps
     gflops = 2.0 * products / (ms_per_step * 1e-3) / 1e9
 
+    # ---- N > 1: the same steps without the exchange (compute only), NVLink bytes, and a check of the gathered C ----
+    multi = None
+    if world > 1:
+        for _ in range(2):
+            step(compute_only=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        c0, c1 = ev(), ev()
+        c0.record()
+        for _ in range(5):
+            step(compute_only=True)
+        c1.record()
+        torch.cuda.synchronize()
+        cms = torch.tensor([c0.elapsed_time(c1) / 5], dtype=torch.float64, device=device)
+        dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+        step()                                            # leave a complete C in the buffers
+        torch.cuda.synchronize()
+        dist.barrier()
+        if pg is not None:
+            g_ptr, g_col, g_val = pg.result()
+            sent = torch.tensor([pg.nvlink_bytes() + 8 * (hi - lo + 1) * (world - 1)], dtype=torch.float64, device=device)
+        else:
+            g_ptr, g_col, g_val = gathered[0], gathered[1][:nnz_c], gathered[2][:nnz_c]
+            sent = torch.tensor([0.0], dtype=torch.float64, device=device)
+        # every rank compares its gathered C with the C it computes alone on one GPU (bit for bit, on the device)
+        ref = eng.spgemm_dev(da, db)
+        rp, rc, rv = D.result_views(ref, device)
+        same_c = bool(torch.equal(rp, g_ptr[:m + 1]) and torch.equal(rc, g_col[:ref.nnz]) and
+                      torch.equal(rv.view(torch.int64), g_val[:ref.nnz].view(torch.int64)))
+        flag = torch.tensor([1 if same_c else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        mx = sent.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        ref = rp = rc = rv = None
+        multi = {"gather": args.gather, "compute_only_ms_per_step": float(cms[0]),
+                 "gathered_c_identical_to_one_gpu_on_every_rank": bool(int(flag[0])),
+                 "nvlink_bytes_sent_per_rank_per_step_max": float(mx[0]),
+                 "nvlink_floor_ms": float(mx[0]) / (NVLINK_PEAK_GBS * 1e9) * 1e3,
+                 "note": "value includes the exchange of C; compute_only = same steps storing only into the rank's own buffers"}
+
+    # ---- per-launch durations: the engine overlaps the long rows with the sort bins on a side stream, so the event
+    # times of the timed region overlap too.  For the roofline every kernel is timed alone: a second handle with
+    # SPADA_B200_FLAG_SERIAL over the same device arrays (this rank's rows), 3 warm-up + 5 recorded steps.
+    if pg is not None:
+        pg.close()
+        pg = None
+    if world > 1:
+        nccl_out = gathered = g_ptr = g_col = g_val = None
+    eng.trim()          # hand the first handle's cached blocks back: the second handle needs the same footprint
+    ser = pkg.Engine(device=local_rank, validate=False, stream=stream.cuda_stream, two_phase=args.two_phase or world > 1,
+                     single_pass=args.single_pass and world == 1, serial=True)
+    sa = ser.wrap_device(da.shape[0], da.shape[1], da.nnz, *da.device_ptrs(), keepalive=da)
+    sb = sa if db is da else ser.wrap_device(db.shape[0], db.shape[1], db.nnz, *db.device_ptrs(), keepalive=db)
+    sb.prepare()
+    per_launch = {}
+    local_products = 0
+    for it in range(8):
+        r_ = ser.spgemm_dev(sa, sb, lo, hi)
+        if it >= 3:
+            s_ = r_.stats()
+            local_products = s_["products"]
+            add_launches(per_launch, s_)
+        r_ = None
+    sa.free()
+    if sb is not sa:
+        sb.free()
+    ser.close()
+    timing_note = ("launch times from 5 serialised steps after the timed region (SPADA_B200_FLAG_SERIAL, rank 0's rows): the "
+                   "timed steps run the long rows on a side stream beside the sort bins")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- per-launch durations: the engine overlaps the heavy / huge bins with the sort bins on a side stream, so the
-    # event times of the timed region overlap too.  For the roofline every kernel is timed alone: a second handle with
-    # SPADA_B200_FLAG_SERIAL over the same device arrays, 3 warm-up + 5 recorded steps, CUDA events on its stream.
-    timing_note = "launch times from the timed region"
-    if world == 1:
-        eng.trim()          # hand the first handle's cached blocks back: the second handle needs the same footprint
-        ser = pkg.Engine(device=local_rank, validate=False, stream=stream.cuda_stream, two_phase=args.two_phase,
-                         single_pass=args.single_pass, serial=True)
-        sa = ser.wrap_device(da.shape[0], da.shape[1], da.nnz, *da.device_ptrs(), keepalive=da)
-        sb = sa if db is da else ser.wrap_device(db.shape[0], db.shape[1], db.nnz, *db.device_ptrs(), keepalive=db)
-        sb.prepare()
-        per_launch = {}
-        for it in range(8):
-            r_ = ser.spgemm_dev(sa, sb, lo, hi)
-            if it >= 3:
-                for L in r_.stats()["launches"]:
-                    d = per_launch.setdefault(L["name"], {"ms": 0.0, "n": 0, "products": 0, "rows": L["rows"],
-                                                          "grid": L["grid"]})
-                    d["ms"] += L["ms"]; d["n"] += 1; d["products"] += L["products"]
-            r_ = None
-        sa.free()
-        if sb is not sa:
-            sb.free()
-        ser.close()
-        timing_note = ("launch times from 5 serialised steps after the timed region (SPADA_B200_FLAG_SERIAL): the timed "
-                       "steps run the heavy/huge bins on a side stream beside the sort bins")
-
-    # ---- roofline of the dominant kernel launch ----------------------------------------------------
+    # ---- roofline of the dominant COMPUTE kernel (placement kernels do no algorithmic work) ---------------------
     peak, peak_src = peaks()
     alg_bytes = pkg.workloads.algorithmic_bytes(nnz_a, m, nnz_b, k, nnz_c)
-    dom_name, dom = max(per_launch.items(), key=lambda kv: kv[1]["ms"])
+    compute = {k_: v for k_, v in per_launch.items() if k_ not in PLACEMENT_KERNELS and v["products"] > 0}
+    dom_name, dom = max((compute or per_launch).items(), key=lambda kv: kv[1]["ms"])
     dom_ms = dom["ms"] / dom["n"]
-    # algorithmic bytes of one launch = whole-path compulsory bytes x the launch's share of products
-    local_products = st0["products"]
-    share = (dom["products"] / dom["n"] / local_products) if local_products else 1.0   # products of ONE launch
-    if dom["products"] == 0:
-        share = 1.0
-    dom_bytes = alg_bytes / world * share
+    # algorithmic bytes of one launch = whole-path compulsory bytes x the launch's share of ALL products of the workload
+    share = (dom["products"] / dom["n"] / products) if products else 1.0
+    dom_bytes = alg_bytes * share
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -449,52 +529,10 @@ def main():
                                "frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
                 "launch_ms": {k_: v["ms"] / v["n"] for k_, v in per_launch.items()}}
 
-    # ---- e2e: host-level C-ABI call with pinned host operands, C copied back (rank 0, N = 1) ---------
+    # ---- e2e: host-level C-ABI call with pinned host operands, C copied back (N = 1) --------------------------
     e2e = None
     if world == 1 and args.e2e_steps > 0:
-        eng.synchronize()
-        abi = pkg._abi
-        lib = abi.lib()
-        keep = []
-
-        def view32(mat):
-            ip, p1 = pinned_copy(pkg, np.ascontiguousarray(mat.indptr, dtype=np.int32))
-            ix, p2 = pinned_copy(pkg, np.ascontiguousarray(mat.indices, dtype=np.int32))
-            dx, p3 = pinned_copy(pkg, np.ascontiguousarray(mat.data, dtype=np.float64))
-            keep.extend([p1, p2, p3])
-            return abi.CsrView32(mat.shape[0], mat.shape[1], mat.nnz, ip.ctypes.data_as(C.POINTER(C.c_int32)),
-                                 ix.ctypes.data_as(C.POINTER(C.c_int32)), dx.ctypes.data_as(C.POINTER(C.c_double)))
-        va = view32(a)
-        vb = va if b is a else view32(b)
-        o_ptr, q1 = pinned_copy(pkg, np.zeros(m + 1, dtype=np.int64))
-        o_col, q2 = pinned_copy(pkg, np.zeros(nnz_c, dtype=np.int32))
-        o_val, q3 = pinned_copy(pkg, np.zeros(nnz_c, dtype=np.float64))
-        keep.extend([q1, q2, q3])
-        h2d = (4 * (m + 1) + 12 * nnz_a) + (0 if b is a else 4 * (k + 1) + 12 * nnz_b)
-        d2h = 8 * (m + 1) + 12 * nnz_c
-
-        def e2e_step():
-            out = C.c_void_p()
-            abi.check(lib.spada_b200_spgemm32(eng._h, C.byref(va), C.byref(vb), C.byref(out)))
-            abi.check(lib.spada_b200_result_copy32(out, o_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
-                                                   o_col.ctypes.data_as(C.POINTER(C.c_int32)),
-                                                   o_val.ctypes.data_as(C.POINTER(C.c_double))))
-            lib.spada_b200_result_free(out)
-        e2e_step()
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        f1.record()
-        torch.cuda.synchronize()
-        e2e_ms = f0.elapsed_time(f1) / args.e2e_steps
-        assert int(o_ptr[-1]) == nnz_c
-        e2e = {"value": 2.0 * products / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
-               "note": "spada_b200_spgemm32 + result_copy32: pinned host CSR in, validation, compute, whole C to pinned host"}
-        for p in keep:
-            lib.spada_b200_host_free(p)
+        e2e = e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, args.e2e_steps, torch)
 
     # ---- CPU baseline: the oracle port on a bounded sample of the same workload -------------------------
     cpu = None
@@ -502,24 +540,69 @@ def main():
         v, cores, sample, secs = cpu_oracle_rate(a, b, target_seconds=12.0)
         cpu = {"value": v, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample, "seconds": secs}
 
+    cfg = workload_config(pkg, args, a, b, products=products, nnz_c=nnz_c)
+    cfg["parallelism"] = (f"rows of A sharded over {world} GPU(s) by equal product count; B replicated (NCCL broadcast); "
+                          + ("C gathered by peer stores from the placement kernel" if world > 1 and args.gather == "peer"
+                             else "C all-gathered with NCCL" if world > 1 else "single GPU"))
     line = {
         "metric": "SpGEMM GFLOP/s (2 x intermediate products / time)", "value": gflops, "unit": "GFLOP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload], "scale": args.scale, "m": m, "k": k, "n": n,
-                   "nnz_a": nnz_a, "nnz_b": nnz_b, "products": products, "nnz_c": nnz_c, "device_transpose_ms": transpose_ms,
-                   "l2": "inputs+output larger than L2 (no flush)" if alg_bytes > 4 * 126e6 else "working set near L2 size",
-                   "parallelism": f"rows of A sharded over {world} GPU(s) by equal product count; B replicated; C all-gathered"
-                                  + (f" in {waves} waves overlapped with the computation" if world > 1 and waves > 1 else "")},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "compute_only": {"ms_per_step": compute_ms / args.steps,
-                         "value": 2.0 * products / (compute_ms / args.steps * 1e-3) / 1e9 if compute_ms else None,
-                         "note": "engine device time per step (max over ranks), without the C all-gather"},
-        "bins": st0["bins"],
+        "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "setup": setup, "multi_gpu": multi, "bins": st["bins"],
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, steps, torch):
+    """The same metric through the host-level C-ABI call: pinned host operands in, the whole C back in pinned host
+    memory, both copies inside the timed region."""
+    eng.synchronize()
+    abi = pkg._abi
+    lib = abi.lib()
+    keep = []
+
+    def view32(mat):
+        ip, p1 = pinned_copy(pkg, np.ascontiguousarray(mat.indptr, dtype=np.int32))
+        ix, p2 = pinned_copy(pkg, np.ascontiguousarray(mat.indices, dtype=np.int32))
+        dx, p3 = pinned_copy(pkg, np.ascontiguousarray(mat.data, dtype=np.float64))
+        keep.extend([p1, p2, p3])
+        return abi.CsrView32(mat.shape[0], mat.shape[1], mat.nnz, ip.ctypes.data_as(C.POINTER(C.c_int32)),
+                             ix.ctypes.data_as(C.POINTER(C.c_int32)), dx.ctypes.data_as(C.POINTER(C.c_double)))
+    va = view32(a)
+    vb = va if b is a else view32(b)
+    o_ptr, q1 = pinned_copy(pkg, np.zeros(m + 1, dtype=np.int64))
+    o_col, q2 = pinned_copy(pkg, np.zeros(nnz_c, dtype=np.int32))
+    o_val, q3 = pinned_copy(pkg, np.zeros(nnz_c, dtype=np.float64))
+    keep.extend([q1, q2, q3])
+    h2d = (4 * (m + 1) + 12 * nnz_a) + (0 if b is a else 4 * (k + 1) + 12 * nnz_b)
+    d2h = 8 * (m + 1) + 12 * nnz_c
+
+    def e2e_step():
+        out = C.c_void_p()
+        abi.check(lib.spada_b200_spgemm32(eng._h, C.byref(va), C.byref(vb), C.byref(out)))
+        abi.check(lib.spada_b200_result_copy32(out, o_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               o_col.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               o_val.ctypes.data_as(C.POINTER(C.c_double))))
+        lib.spada_b200_result_free(out)
+    e2e_step()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(steps):
+        e2e_step()
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_ms = f0.elapsed_time(f1) / steps
+    assert int(o_ptr[-1]) == nnz_c
+    out = {"value": 2.0 * products / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": steps,
+           "note": "spada_b200_spgemm32 + result_copy32: pinned host CSR in, validation, compute, whole C to pinned host"}
+    for p in keep:
+        lib.spada_b200_host_free(p)
+    return out
 
 
 if __name__ == "__main__":

@@ -109,6 +109,10 @@ typedef struct spada_b200_opts {
 typedef struct spada_b200 spada_b200_t;               /* engine handle (streams, workspace pool) */
 typedef struct spada_b200_csr spada_b200_csr_t;       /* device-resident operand */
 typedef struct spada_b200_result spada_b200_result_t; /* device-resident C (engine owned) */
+typedef struct spada_b200_shard spada_b200_shard_t;   /* a row shard's product between its two halves */
+typedef struct spada_b200_cbuf spada_b200_cbuf_t;     /* full-size C buffers (row_ptr, col, val) on one GPU */
+typedef struct spada_b200_group spada_b200_group_t;   /* the GPUs of one process, one engine handle each */
+#define SPADA_B200_IPC_HANDLE_BYTES 64                /* sizeof(cudaIpcMemHandle_t) */
 
 typedef struct spada_b200_launch {
     char name[32];     /* kernel family + bin, e.g. "esc_numeric<256>" */
@@ -195,6 +199,53 @@ SPADA_B200_API int spada_b200_flops(spada_b200_t *h, const spada_b200_csr_t *a, 
                      uint64_t *total_products, uint64_t *host_flops_or_null);
 SPADA_B200_API int spada_b200_plan_shards(spada_b200_t *h, const spada_b200_csr_t *a, const spada_b200_csr_t *b,
                            uint32_t n_shards, uint64_t *bounds);
+
+/* ---- sharded runs: A row-sharded by equal product count over several GPUs, B replicated,
+ * C gathered on every GPU.  The reference has no counterpart (single thread); each C row is an independent unit
+ * there too (every window row writes its own psum address, scheduler.rs:548-550), which is what makes rows the
+ * shard unit.  Every GPU owns a full-size set of C buffers; the second half of a shard's product stores the shard's
+ * rows into ALL of them at the shard's global offset -- its own through HBM, the peers' through NVLink peer
+ * mappings -- so the all-gather of C is fused into the kernel that writes C.
+ *
+ * One process per GPU (torchrun):  cbuf_create -> cbuf_export -> (handles exchanged by the launcher's collective)
+ * -> cbuf_import of every peer; per product: shard_begin (first pass into scratch rows, local row_ptr; the shard's
+ * nnz is left in d_nnz_local on the device) -> all-gather of the per-shard nnz (8 bytes per rank, NCCL) ->
+ * shard_finish with the gathered device array (no host round trip in between) -> a barrier before C is read.
+ * One handle carries one shard at a time. */
+SPADA_B200_API int spada_b200_cbuf_create(spada_b200_t *h, uint64_t rows, uint64_t cols, uint64_t capacity_nnz,
+                           spada_b200_cbuf_t **out);
+/* handles: 3 x SPADA_B200_IPC_HANDLE_BYTES (row_ptr, col, val), valid in other processes of this node */
+SPADA_B200_API int spada_b200_cbuf_export(const spada_b200_cbuf_t *c, void *handles);
+SPADA_B200_API int spada_b200_cbuf_import(spada_b200_t *h, const void *handles, uint64_t rows, uint64_t cols,
+                           uint64_t capacity_nnz, spada_b200_cbuf_t **out);
+SPADA_B200_API void spada_b200_cbuf_free(spada_b200_cbuf_t *c);
+SPADA_B200_API int spada_b200_cbuf_device_ptrs(const spada_b200_cbuf_t *c, const int64_t **d_indptr,
+                                const int32_t **d_indices, const double **d_data);
+SPADA_B200_API int spada_b200_cbuf_nnz(const spada_b200_cbuf_t *c, uint64_t *nnz); /* row_ptr[rows] */
+/* gathered C -> caller-allocated host arrays (int64 indptr [rows+1], int32 indices, float64 data of cbuf_nnz entries) */
+SPADA_B200_API int spada_b200_cbuf_copy32(const spada_b200_cbuf_t *c, int64_t *indptr, int32_t *indices, double *data);
+/* first half.  d_nnz_local (nullable, device): receives the shard's nnz; nnz_local (nullable, host): the same after
+ * a stream synchronisation. */
+SPADA_B200_API int spada_b200_shard_begin(spada_b200_t *h, const spada_b200_csr_t *a, const spada_b200_csr_t *b,
+                           uint64_t row_begin, uint64_t row_end, int64_t *d_nnz_local, uint64_t *nnz_local,
+                           spada_b200_shard_t **out);
+/* second half (consumes the shard, also on failure).  bufs[0] = this GPU's buffers, bufs[1..n) = the peers'.  The shard's
+ * first entry goes to nnz_offset + sum(d_shard_nnz[0 .. shard_index)) (d_shard_nnz: nullable device array). */
+SPADA_B200_API int spada_b200_shard_finish(spada_b200_shard_t *s, spada_b200_cbuf_t *const *bufs, uint32_t n_bufs,
+                            uint64_t nnz_offset, const int64_t *d_shard_nnz, uint32_t shard_index,
+                            spada_b200_stats *stats_or_null);
+SPADA_B200_API void spada_b200_shard_abort(spada_b200_shard_t *s);
+
+/* All GPUs of ONE process -- what the spada-sim CLI (a single process, main.rs:30-121) drives: n_gpus engine handles
+ * with peer access between every pair; a product uploads the operands to device 0, replicates them over NVLink,
+ * shards A by equal product count, runs the two halves with one host thread per device and returns device 0's
+ * gathered C.  Replaces Simulator::new / execute / get_exec_result at main.rs:74-100 for n_gpus > 1. */
+SPADA_B200_API int spada_b200_group_create(const spada_b200_opts *opts, uint32_t n_gpus, spada_b200_group_t **out);
+SPADA_B200_API int spada_b200_group_spgemm(spada_b200_group_t *g, const spada_csr_view *a, const spada_csr_view *b,
+                            spada_b200_result_t **out);
+SPADA_B200_API int spada_b200_group_spgemm32(spada_b200_group_t *g, const spada_csr_view32 *a, const spada_csr_view32 *b,
+                              spada_b200_result_t **out);
+SPADA_B200_API void spada_b200_group_destroy(spada_b200_group_t *g);
 
 /* ---- results: replaces get_exec_result (simulator.rs:1034-1062) ----------------------- */
 SPADA_B200_API int spada_b200_result_shape(const spada_b200_result_t *r, uint64_t *rows, uint64_t *cols,

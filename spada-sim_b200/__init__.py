@@ -11,13 +11,13 @@ without a GPU, creating an ``Engine`` does not.
 """
 from . import _abi, workloads
 from ._abi import SpadaB200Error
-from .engine import DeviceCsr, Engine, Result, device_count
+from .engine import CBuf, DeviceCsr, Engine, Group, Result, Shard, device_count
 from .frontend import Cli, OmegaConfig, parse_args, parse_config
 from .gemm import GEMM
 from .py2rust import load_mm_mat, load_pickled_gemms
 from .simulator import Simulator
 from .storage import CsrMatStorage, CsrRow, Element, sort_by_length
 
-__all__ = ["Engine", "DeviceCsr", "Result", "device_count", "SpadaB200Error", "GEMM", "load_mm_mat",
+__all__ = ["Engine", "DeviceCsr", "Result", "CBuf", "Shard", "Group", "device_count", "SpadaB200Error", "GEMM", "load_mm_mat",
            "load_pickled_gemms", "Simulator", "CsrMatStorage", "CsrRow", "Element", "sort_by_length", "Cli",
            "OmegaConfig", "parse_args", "parse_config", "workloads"]

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("SPADA_B200_LIB") or os.path.join(_HERE, "lib", "libsp
 MAX_BINS = 32
 MAX_LAUNCHES = 64
 ABI_VERSION = 2
+IPC_HANDLE_BYTES = 64
 
 STATUS = {0: "OK", 1: "INVALID_ARG", 2: "UNSORTED_INPUT", 3: "DIM_MISMATCH", 4: "CUDA_ERROR",
           5: "NCCL_ERROR", 6: "OOM", 7: "NO_DEVICE", 8: "TOO_LARGE"}
@@ -86,6 +87,20 @@ SYMBOLS = {
     "spada_b200_spgemm32": (C.c_int, [_vp, C.POINTER(CsrView32), C.POINTER(CsrView32), _vpp]),
     "spada_b200_flops": (C.c_int, [_vp, _vp, _vp, _u64p, _u64p]),
     "spada_b200_plan_shards": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _u64p]),
+    "spada_b200_cbuf_create": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vpp]),
+    "spada_b200_cbuf_export": (C.c_int, [_vp, _vp]),
+    "spada_b200_cbuf_import": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vpp]),
+    "spada_b200_cbuf_free": (None, [_vp]),
+    "spada_b200_cbuf_device_ptrs": (C.c_int, [_vp, _vpp, _vpp, _vpp]),
+    "spada_b200_cbuf_nnz": (C.c_int, [_vp, _u64p]),
+    "spada_b200_cbuf_copy32": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    "spada_b200_shard_begin": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _u64p, _vpp]),
+    "spada_b200_shard_finish": (C.c_int, [_vp, _vpp, C.c_uint32, C.c_uint64, _vp, C.c_uint32, C.POINTER(Stats)]),
+    "spada_b200_shard_abort": (None, [_vp]),
+    "spada_b200_group_create": (C.c_int, [C.POINTER(Opts), C.c_uint32, _vpp]),
+    "spada_b200_group_spgemm": (C.c_int, [_vp, C.POINTER(CsrView), C.POINTER(CsrView), _vpp]),
+    "spada_b200_group_spgemm32": (C.c_int, [_vp, C.POINTER(CsrView32), C.POINTER(CsrView32), _vpp]),
+    "spada_b200_group_destroy": (None, [_vp]),
     "spada_b200_result_shape": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "spada_b200_result_copy": (C.c_int, [_vp, _u64p, _u64p, C.POINTER(C.c_double)]),
     "spada_b200_result_copy32": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
@@ -117,6 +132,8 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
+        if l.spada_b200_abi_version() != ABI_VERSION:
+            raise ImportError(f"{LIB_PATH} has ABI version {l.spada_b200_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
         _lib = l
     return _lib
 

@@ -318,8 +318,17 @@ struct CopyDst {
     int32_t* col[8];
     double* val[8];
     int n;
-    int64_t off;
+    int64_t off;                 // host-known part of the shard's offset
+    const int64_t* shard_nnz;    // nullable, device: nnz of every shard (all-gathered); the shard's offset then also
+    int shard_idx;               // includes shard_nnz[0 .. shard_idx) -- no host round trip between the two halves
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ int64_t shard_offset(int64_t off, const int64_t* shard_nnz, int shard_idx) {
+    if (shard_nnz)
+        for (int i = 0; i < shard_idx; ++i) off += shard_nnz[i];
+    return off;
+}
+#endif
 void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t lo, uint32_t hi, const int64_t* t_ptr,
                       const int32_t* t_col, const double* t_val, const int64_t* c_ptr, const CopyDst& dst,
                       cudaStream_t s);
@@ -375,6 +384,8 @@ struct LongWave {
     uint32_t* u;                 // [n_rows]   chunks per row
     int64_t* prod_off;           // [n_rows+1] start of the row inside the ping-pong buffers
     int64_t* unit_off;           // [n_rows+1] first chunk of the row
+    uint32_t* unit_row;          // [unit_bound] row (index inside the wave) of every chunk / tile
+    void* tiles;                 // [unit_bound] x 32 B: merge-tile descriptors of the level in flight
     uint32_t* unit_heads;        // [unit_bound] distinct columns that start inside the chunk
     int64_t* unit_hoff;          // [unit_bound+1]
     int32_t* col[2];             // ping-pong buffers, one entry per product of the wave
@@ -393,12 +404,19 @@ struct LongStages {
 uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
                           const uint32_t* aseq, const LongWave& w, const int64_t* t_ptr, int32_t* t_col, double* t_val,
                           uint32_t* row_nnz, PlanCounters* ctr, cudaStream_t s, const LongStages* stages = nullptr);
+// long rows of a product with few columns (B.cols <= DENSE_MAX_COLS): dense accumulator in shared memory, B rows applied
+// one after the other in ascending k (longrow.cu)
+constexpr int64_t DENSE_MAX_COLS = 16384;
+bool dense_rows_fit(int64_t b_cols);
+void launch_dense_rows(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list, uint32_t n_rows,
+                       const int64_t* t_ptr, int32_t* t_col, double* t_val, uint32_t* row_nnz, cudaStream_t s);
 // shard row pointers shifted by the shard's global offset, written into every GPU's row_ptr (sharded runs)
 struct RowPtrDst {
     int64_t* ptr[8];
     int n;
 };
-void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const RowPtrDst& dst, int64_t row_off, cudaStream_t s);
+void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const int64_t* shard_nnz, int shard_idx,
+                          const RowPtrDst& dst, int64_t row_off, cudaStream_t s);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
 void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,

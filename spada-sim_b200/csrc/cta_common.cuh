@@ -24,11 +24,11 @@ struct CtaStage {
     int wtot[ESC_CTA_THREADS / 32];
 };
 
-// PACKED: keys carry the arrival index (column << log2 N | seq); LOAD_COL = false: values only
-template <typename K, int N, bool NUMERIC, bool PACKED = NUMERIC, bool LOAD_COL = true>
+// PACKED: keys carry the arrival index (column << log2(N/G) | seq inside the group); LOAD_COL = false: values only
+template <typename K, int N, bool NUMERIC, bool PACKED = NUMERIC, bool LOAD_COL = true, int G = 1>
 __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr& b, int64_t a_begin, int64_t a_end,
                                                   K* keys, double* vals, CtaStage& st) {
-    constexpr int SB = Log2<N>::v;
+    constexpr int SB = Log2<N / G>::v;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     int seq_base = 0;
     for (int64_t pb = a_begin; pb < a_end; pb += ESC_CTA_THREADS) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
             for (int u = 0; u < 2; ++u) {
                 if (t[u] < all) {
                     int sq = seq_base + t[u];
-                    if (LOAD_COL) keys[sq] = PACKED ? (((K)c[u] << SB) | (K)sq) : (K)c[u];
+                    if (LOAD_COL) keys[sq] = PACKED ? (((K)c[u] << SB) | (K)(sq & (N / G - 1))) : (K)c[u];
                     if (NUMERIC) vals[sq] = __dmul_rn(st.av[j[u]], bv[u]);
                 }
             }
@@ -101,7 +101,8 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
     return seq_base;
 }
 
-template <typename K, int N>
+// G > 1: the N keys are G independent groups of N / G keys (each sorted on its own: the merge phases stop at N / G)
+template <typename K, int N, int G = 1>
 __device__ __forceinline__ void bitonic_cta_sort(K* keys) {
     constexpr int WARPS = ESC_CTA_THREADS / 32;
     constexpr int CH = N / WARPS;  // keys per warp chunk
@@ -113,7 +114,7 @@ __device__ __forceinline__ void bitonic_cta_sort(K* keys) {
     store_blocked<K, E>(x, keys + warp * CH, lane);
     __syncthreads();
 #pragma unroll 1
-    for (int k = 2 * CH; k <= N; k <<= 1) {
+    for (int k = 2 * CH; k <= N / G; k <<= 1) {
         // flip stage: i against its mirror image inside the block of k keys
         for (int t = threadIdx.x; t < N / 2; t += ESC_CTA_THREADS) {
             const int h = k >> 1;
@@ -146,15 +147,69 @@ __device__ __forceinline__ void bitonic_cta_sort(K* keys) {
     }
 }
 
+// Two sorted groups of N / 2 packed keys (column << log2(N/2) | arrival inside the group; group 0 = the earlier
+// arrivals) merged into one sorted sequence: a stable merge by column, ties to group 0, so equal columns stay in
+// arrival order.  32-bit keys then serve columns up to 2^(32 - log2(N/2)) -- twice as many as one group of N.
+// On return keys[i] = column and vals[i] = value of the i-th product in (column, arrival) order.
+template <int N>
+__device__ __forceinline__ void cta_merge_groups2(uint32_t* keys, double* vals, int cnt) {
+    constexpr int H = N / 2;
+    constexpr int SBH = Log2<H>::v;
+    constexpr int ITEMS = N / ESC_CTA_THREADS;
+    const int c0 = cnt < H ? cnt : H, c1 = cnt - c0;
+    const uint32_t* X = keys;
+    const uint32_t* Y = keys + H;
+    const int d = threadIdx.x * ITEMS;
+    uint32_t oc[ITEMS];
+    double ov[ITEMS];
+    if (d < cnt) {
+        int lo = d > c1 ? d - c1 : 0, hi = d < c0 ? d : c0;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((X[mid] >> SBH) <= (Y[d - 1 - mid] >> SBH)) lo = mid + 1; else hi = mid;
+        }
+        int i = lo, j = d - lo;
+        uint32_t xk = i < c0 ? X[i] : 0xffffffffu, yk = j < c1 ? Y[j] : 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < ITEMS; ++q) {
+            if (d + q < cnt) {
+                const bool tx = j >= c1 || (i < c0 && (xk >> SBH) <= (yk >> SBH));
+                const uint32_t key = tx ? xk : yk;
+                oc[q] = key >> SBH;
+                ov[q] = vals[(int)(key & (uint32_t)(H - 1)) + (tx ? 0 : H)];
+                if (tx) {
+                    ++i;
+                    xk = i < c0 ? X[i] : 0xffffffffu;
+                } else {
+                    ++j;
+                    yk = j < c1 ? Y[j] : 0xffffffffu;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (d < cnt) {
+#pragma unroll
+        for (int q = 0; q < ITEMS; ++q)
+            if (d + q < cnt) {
+                keys[d + q] = oc[q];
+                vals[d + q] = ov[q];
+            }
+    }
+    __syncthreads();
+}
+
 // Segmented sums + store of a sorted row held in shared memory.  Warp w owns the positions
 // [w*32*ITEMS, (w+1)*32*ITEMS), lanes interleaved (position = base + e*32 + lane: conflict-free
 // shared-memory reads, coalesced stores); run heads are found with ballots, one scan over the eight
 // warp totals places them, then every head sums its run left to right.
-template <typename K, int N>
+// SORTED: keys[i] is the column itself and vals[i] its value (after cta_merge_groups2) instead of packed keys that
+// index vals by arrival
+template <typename K, int N, bool SORTED = false>
 __device__ __forceinline__ int cta_reduce_store(const K* keys, const double* vals, int p, int64_t cbase,
                                                 int32_t* __restrict__ c_col, double* __restrict__ c_val, CtaStage& st,
                                                 uint32_t col_offset = 0) {
-    constexpr int SB = Log2<N>::v;
+    constexpr int SB = SORTED ? 0 : Log2<N>::v;
     constexpr int ITEMS = N / ESC_CTA_THREADS;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int w0 = warp * 32 * ITEMS;
@@ -186,11 +241,11 @@ __device__ __forceinline__ int cta_reduce_store(const K* keys, const double* val
     for (int e = 0; e < ITEMS; ++e) {
         if ((hm[e] >> lane) & 1u) {
             const int i = w0 + e * 32 + lane;
-            double sum = vals[(int)(keys[i] & (K)(N - 1))];
+            double sum = vals[SORTED ? i : (int)(keys[i] & (K)(N - 1))];
             for (int j = i + 1; j < p; ++j) {
                 const K kj = keys[j];
                 if ((uint32_t)(kj >> SB) != col[e]) break;
-                sum = __dadd_rn(sum, vals[(int)(kj & (K)(N - 1))]);
+                sum = __dadd_rn(sum, vals[SORTED ? j : (int)(kj & (K)(N - 1))]);
             }
             const int oo = o + __popc(hm[e] & ((1u << lane) - 1u));
             st_out(c_col + (cbase + oo), (int32_t)(col[e] + col_offset));

@@ -24,6 +24,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/spada_b200.h"
@@ -833,7 +835,8 @@ struct spada_b200_shard {
     int32_t* d_tcol = nullptr;
     double* d_tval = nullptr;
     // long-row wave workspace
-    uint32_t *w_p = nullptr, *w_u = nullptr, *w_heads = nullptr;
+    uint32_t *w_p = nullptr, *w_u = nullptr, *w_heads = nullptr, *w_unit_row = nullptr;
+    uint64_t* w_tiles = nullptr;
     int64_t *w_prod_off = nullptr, *w_unit_off = nullptr, *w_hoff = nullptr;
     int32_t* w_col[2] = {nullptr, nullptr};
     double* w_val[2] = {nullptr, nullptr};
@@ -858,9 +861,9 @@ struct spada_b200_shard {
     void release_work() {
         if (forked) cudaStreamSynchronize(h->side);
         forked = false;
-        uint32_t** u32s[] = {&d_flops, &d_long, &d_perm, &d_nnz, &d_masked, &d_blen, &d_aseq, &w_p, &w_u, &w_heads};
+        uint32_t** u32s[] = {&d_flops, &d_long, &d_perm, &d_nnz, &d_masked, &d_blen, &d_aseq, &w_p, &w_u, &w_heads, &w_unit_row};
         for (auto pp : u32s) { dfree(h, *pp); *pp = nullptr; }
-        uint64_t** u64s[] = {&d_tiles, &d_tiles_side};
+        uint64_t** u64s[] = {&d_tiles, &d_tiles_side, &w_tiles};
         for (auto pp : u64s) { dfree(h, *pp); *pp = nullptr; }
         int64_t** i64s[] = {&d_prod_ptr, &w_prod_off, &w_unit_off, &w_hoff};
         for (auto pp : i64s) { dfree(h, *pp); *pp = nullptr; }
@@ -977,7 +980,7 @@ void shard_free(spada_b200_shard* S) {
 
 // first half: everything up to the local row_ptr.  force_scratch: sharded runs place every row in the second half.
 int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b, uint64_t row_begin,
-                uint64_t row_end, bool force_scratch, spada_b200_shard** out) {
+                uint64_t row_end, bool force_scratch, bool host_nnz, spada_b200_shard** out) {
     if (!h || !a || !b || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
     *out = nullptr;
     if (a->d.cols != b->d.rows)
@@ -1105,7 +1108,9 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
     // long rows: wave plan + workspace
     std::vector<WavePlan> waves;
     uint64_t wave_products = 0, wave_units = 0, wave_rows = 0;
-    if (S->n_long) {
+    // few output columns: the long rows keep a dense accumulator in shared memory instead (no merge levels)
+    const bool dense_long = S->n_long && dense_rows_fit(B.cols) && !getenv("SPADA_B200_NO_DENSE");
+    if (S->n_long && !dense_long) {
         waves = plan_waves(pc, std::max<uint64_t>(h->long_ws_budget / 24, (uint64_t)LONG_UNIT));
         for (auto& w : waves) {
             wave_products = std::max(wave_products, w.products_bound);
@@ -1136,13 +1141,15 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
         S->kernels += 2;
         S->end_rec();
     }
-    if (S->n_long) {
+    if (S->n_long && !dense_long) {
         TRY(dalloc(h, &S->d_aseq, (size_t)std::max<int64_t>(A.nnz, 1)));
         TRY(dalloc(h, &S->w_p, (size_t)wave_rows));
         TRY(dalloc(h, &S->w_u, (size_t)wave_rows));
         TRY(dalloc(h, &S->w_prod_off, (size_t)wave_rows + 1));
         TRY(dalloc(h, &S->w_unit_off, (size_t)wave_rows + 1));
         TRY(dalloc(h, &S->w_heads, (size_t)wave_units));
+        TRY(dalloc(h, &S->w_unit_row, (size_t)wave_units));
+        TRY(dalloc(h, &S->w_tiles, (size_t)wave_units * 4));   // 32-byte merge-tile descriptors
         TRY(dalloc(h, &S->w_hoff, (size_t)wave_units + 1));
         TRY(dalloc(h, &S->d_tiles_side, scan_tile_state_words((int64_t)std::max<uint64_t>(wave_units, wave_rows))));
         for (int i = 0; i < 2; ++i) {
@@ -1158,7 +1165,14 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
         CUT(cudaStreamWaitEvent(sh, h->ev_fork, 0));
         S->forked = true;
     }
-    if (S->n_long) {
+    if (dense_long) {
+        S->begin_rec("long_dense", 2, S->n_long, S->n_long, S->long_products, sh);
+        launch_dense_rows(A, B, (int64_t)row_begin, S->perm_of(BIN_LONG0), S->n_long, S->d_prod_ptr, S->d_tcol, S->d_tval,
+                          S->d_nnz, sh);
+        CUT(cudaGetLastError());
+        S->kernels += 1;
+        S->end_rec();
+    } else if (S->n_long) {
         const uint32_t* long_list = S->perm_of(BIN_LONG0);   // bins >= BIN_LONG0 are adjacent in perm[]
         S->begin_rec("long_prefix", 2, S->n_long, S->n_long, S->long_products, sh);
         launch_long_prefix(A, (int64_t)row_begin, long_list, S->n_long, S->d_blen, S->d_aseq, sh);
@@ -1179,6 +1193,8 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
             W.prod_off = S->w_prod_off;
             W.unit_off = S->w_unit_off;
             W.unit_heads = S->w_heads;
+            W.unit_row = S->w_unit_row;
+            W.tiles = S->w_tiles;
             W.unit_hoff = S->w_hoff;
             for (int i = 0; i < 2; ++i) {
                 W.col[i] = S->w_col[i];
@@ -1227,9 +1243,13 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
         CUT(cudaGetLastError());
         S->kernels += 1;
         S->end_rec();
-        CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        CUT(cudaStreamSynchronize(s));  // host read-back #2: nnz(C) sizes the output
-        S->nnz_c = h->h_scalar[0];
+        if (host_nnz) {
+            CUT(cudaMemcpyAsync(h->h_scalar, R->ptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            CUT(cudaStreamSynchronize(s));  // host read-back #2: nnz(C) sizes the output
+            S->nnz_c = h->h_scalar[0];
+        } else {
+            S->nnz_c = -1;   // stays on the device (sharded runs size C by its bound)
+        }
     }
     *out = S;
     return 0;
@@ -1240,7 +1260,7 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
 // dst->off + local offset in all of them; row_ptr_dst[d] (nullable) get the shard's row pointers shifted by dst->off
 // at row offset row_off.
 int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_ptr_dst, int64_t row_off,
-                 spada_b200_result_t** out) {
+                 spada_b200_result_t** out, spada_b200_stats* stats_out = nullptr) {
     spada_b200* h = S->h;
     DeviceGuard g(h->device);
     cudaStream_t s = h->stream;
@@ -1302,7 +1322,7 @@ int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_p
     }
     if (dst && row_ptr_dst) {
         S->begin_rec("row_ptr_gather", 3, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
-        launch_shift_row_ptr(R->ptr, m, D.off, *row_ptr_dst, row_off, s);
+        launch_shift_row_ptr(R->ptr, m, D.off, D.shard_nnz, D.shard_idx, *row_ptr_dst, row_off, s);
         CUT(cudaGetLastError());
         S->kernels += 1;
         S->end_rec();
@@ -1312,8 +1332,8 @@ int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_p
     CUT(cudaStreamSynchronize(s));
     CUT(cudaGetLastError());
     if (S->fused) S->nnz_c = h->h_scalar[0];
-    R->nnz = (uint64_t)S->nnz_c;
-    st.nnz_c = (uint64_t)S->nnz_c;
+    R->nnz = S->nnz_c < 0 ? 0 : (uint64_t)S->nnz_c;
+    st.nnz_c = R->nnz;
 
     // ---- stats ------------------------------------------------------------------------------
     st.n_launches = S->kernels;
@@ -1336,6 +1356,7 @@ int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_p
         }
     }
     if (!S->recs.empty()) cudaEventElapsedTime(&st.ms_total, S->recs.front().e0, S->e_end);
+    if (stats_out) *stats_out = st;
     if (out) {
         *out = R;
         S->R = nullptr;
@@ -1354,9 +1375,403 @@ extern "C" int spada_b200_spgemm_dev(spada_b200_t* h, const spada_b200_csr_t* a,
     if (!out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
     *out = nullptr;
     spada_b200_shard* S = nullptr;
-    int rc = shard_begin(h, a, b, row_begin, row_end, false, &S);
+    int rc = shard_begin(h, a, b, row_begin, row_end, false, true, &S);
     if (rc) return rc;
     return shard_finish(S, nullptr, nullptr, 0, out);
+}
+
+// ---- sharded runs: A row-sharded over several GPUs, B replicated, C gathered on every GPU ------------------
+// (SURVEY.md 8e).  Every GPU owns a full-size set of C buffers (spada_b200_cbuf); the second half of a shard's
+// product writes the shard's rows into ALL of them at the shard's global offset -- its own through HBM, the peers'
+// through NVLink peer mappings (CUDA IPC between the processes of a one-process-per-GPU run, peer access inside one
+// process) -- so the all-gather of C is the store itself, not a pass after it.
+struct spada_b200_cbuf {
+    spada_b200* h;
+    uint64_t rows, cols, cap;
+    int64_t* ptr;
+    int32_t* col;
+    double* val;
+    bool imported;
+};
+
+extern "C" int spada_b200_cbuf_create(spada_b200_t* h, uint64_t rows, uint64_t cols, uint64_t capacity_nnz,
+                                      spada_b200_cbuf_t** out) {
+    if (!h || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    DeviceGuard g(h->device);
+    spada_b200_cbuf* c = new (std::nothrow) spada_b200_cbuf{h, rows, cols, capacity_nnz, nullptr, nullptr, nullptr, false};
+    if (!c) return fail(SPADA_B200_OOM, "host allocation failed");
+    int rc;
+    if ((rc = dalloc(h, &c->ptr, (size_t)rows + 1)) || (rc = dalloc(h, &c->col, (size_t)std::max<uint64_t>(capacity_nnz, 1))) ||
+        (rc = dalloc(h, &c->val, (size_t)std::max<uint64_t>(capacity_nnz, 1)))) {
+        dfree(h, c->ptr);
+        dfree(h, c->col);
+        dfree(h, c->val);
+        delete c;
+        return rc;
+    }
+    if (cudaMemsetAsync(c->ptr, 0, ((size_t)rows + 1) * sizeof(int64_t), h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        spada_b200_cbuf_free(c);
+        return fail(SPADA_B200_CUDA_ERROR, "cbuf_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int spada_b200_cbuf_export(const spada_b200_cbuf_t* c, void* handles) {
+    if (!c || !handles) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    if (c->imported) return fail(SPADA_B200_INVALID_ARG, "an imported buffer cannot be exported again");
+    DeviceGuard g(c->h->device);
+    cudaIpcMemHandle_t* hs = reinterpret_cast<cudaIpcMemHandle_t*>(handles);
+    static_assert(sizeof(cudaIpcMemHandle_t) == SPADA_B200_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaIpcGetMemHandle(&hs[0], c->ptr));
+    CU(cudaIpcGetMemHandle(&hs[1], c->col));
+    CU(cudaIpcGetMemHandle(&hs[2], c->val));
+    return 0;
+}
+
+extern "C" int spada_b200_cbuf_import(spada_b200_t* h, const void* handles, uint64_t rows, uint64_t cols,
+                                      uint64_t capacity_nnz, spada_b200_cbuf_t** out) {
+    if (!h || !handles || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    DeviceGuard g(h->device);
+    const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(handles);
+    spada_b200_cbuf* c = new (std::nothrow) spada_b200_cbuf{h, rows, cols, capacity_nnz, nullptr, nullptr, nullptr, true};
+    if (!c) return fail(SPADA_B200_OOM, "host allocation failed");
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 3; ++i) {
+        cudaError_t e = cudaIpcOpenMemHandle(&p[i], hs[i], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int j = 0; j < i; ++j) cudaIpcCloseMemHandle(p[j]);
+            delete c;
+            cudaGetLastError();
+            return fail(SPADA_B200_CUDA_ERROR, "cudaIpcOpenMemHandle: %s (peer buffers need NVLink / P2P access)",
+                        cudaGetErrorString(e));
+        }
+    }
+    c->ptr = (int64_t*)p[0];
+    c->col = (int32_t*)p[1];
+    c->val = (double*)p[2];
+    *out = c;
+    return 0;
+}
+
+extern "C" void spada_b200_cbuf_free(spada_b200_cbuf_t* c) {
+    if (!c) return;
+    DeviceGuard g(c->h->device);
+    if (c->imported) {
+        cudaIpcCloseMemHandle(c->ptr);
+        cudaIpcCloseMemHandle(c->col);
+        cudaIpcCloseMemHandle(c->val);
+        cudaGetLastError();
+    } else {
+        cudaStreamSynchronize(c->h->stream);
+        dfree(c->h, c->ptr);
+        dfree(c->h, c->col);
+        dfree(c->h, c->val);
+    }
+    delete c;
+}
+
+extern "C" int spada_b200_cbuf_device_ptrs(const spada_b200_cbuf_t* c, const int64_t** d_indptr, const int32_t** d_indices,
+                                           const double** d_data) {
+    if (!c) return fail(SPADA_B200_INVALID_ARG, "buffer is NULL");
+    if (d_indptr) *d_indptr = c->ptr;
+    if (d_indices) *d_indices = c->col;
+    if (d_data) *d_data = c->val;
+    return 0;
+}
+
+extern "C" int spada_b200_cbuf_nnz(const spada_b200_cbuf_t* c, uint64_t* nnz) {
+    if (!c || !nnz) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    DeviceGuard g(c->h->device);
+    int64_t v = 0;
+    CU(cudaMemcpyAsync(&v, c->ptr + c->rows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->h->stream));
+    CU(cudaStreamSynchronize(c->h->stream));
+    *nnz = (uint64_t)v;
+    return 0;
+}
+
+extern "C" int spada_b200_cbuf_copy32(const spada_b200_cbuf_t* c, int64_t* indptr, int32_t* indices, double* data) {
+    if (!c || !indptr) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    DeviceGuard g(c->h->device);
+    cudaStream_t s = c->h->stream;
+    CU(cudaMemcpyAsync(indptr, c->ptr, (c->rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint64_t nnz = (uint64_t)indptr[c->rows];
+    if (nnz > c->cap) return fail(SPADA_B200_INVALID_ARG, "row_ptr[rows] = %llu exceeds the buffer's capacity", (unsigned long long)nnz);
+    if (nnz && indices) CU(cudaMemcpyAsync(indices, c->col, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (nnz && data) CU(cudaMemcpyAsync(data, c->val, nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int spada_b200_shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
+                                      uint64_t row_begin, uint64_t row_end, int64_t* d_nnz_local, uint64_t* nnz_local,
+                                      spada_b200_shard_t** out) {
+    if (!out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    spada_b200_shard* S = nullptr;
+    int rc = shard_begin(h, a, b, row_begin, row_end, true, nnz_local != nullptr, &S);
+    if (rc) return rc;
+    if (nnz_local) *nnz_local = (uint64_t)S->nnz_c;
+    if (d_nnz_local) {
+        DeviceGuard g(h->device);
+        cudaError_t e = cudaMemcpyAsync(d_nnz_local, S->R->ptr + S->m, sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream);
+        if (e != cudaSuccess) {
+            shard_free(S);
+            return fail(SPADA_B200_CUDA_ERROR, "shard_begin: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = S;
+    return 0;
+}
+
+extern "C" int spada_b200_shard_finish(spada_b200_shard_t* S, spada_b200_cbuf_t* const* bufs, uint32_t n_bufs,
+                                       uint64_t nnz_offset, const int64_t* d_shard_nnz, uint32_t shard_index,
+                                       spada_b200_stats* stats) {
+    if (!S || !bufs || n_bufs == 0 || n_bufs > 8) {
+        if (S) shard_free(S);
+        return fail(SPADA_B200_INVALID_ARG, "shard_finish: 1..8 destination buffers");
+    }
+    CopyDst D{};
+    RowPtrDst P{};
+    for (uint32_t i = 0; i < n_bufs; ++i) {
+        if (!bufs[i] || bufs[i]->rows < (uint64_t)(S->row_begin + S->m)) {
+            shard_free(S);
+            return fail(SPADA_B200_INVALID_ARG, "shard_finish: destination buffer %u is missing or too small", i);
+        }
+        D.col[i] = bufs[i]->col;
+        D.val[i] = bufs[i]->val;
+        P.ptr[i] = bufs[i]->ptr;
+    }
+    D.n = P.n = (int)n_bufs;
+    D.off = (int64_t)nnz_offset;
+    D.shard_nnz = d_shard_nnz;
+    D.shard_idx = (int)shard_index;
+    return shard_finish(S, &D, &P, S->row_begin, nullptr, stats);
+}
+
+extern "C" void spada_b200_shard_abort(spada_b200_shard_t* S) { shard_free(S); }
+
+// ---- all GPUs of one process (what the spada-sim CLI, a single process, drives: SURVEY.md 8b) -----------------------
+// One engine handle per device, peer access between every pair, one host thread per device for the two halves.
+struct spada_b200_group {
+    std::vector<spada_b200*> h;
+    std::vector<spada_b200_cbuf*> bufs;
+    uint64_t buf_rows = 0, buf_cap = 0;
+};
+
+extern "C" void spada_b200_group_destroy(spada_b200_group_t* G) {
+    if (!G) return;
+    for (auto* c : G->bufs) spada_b200_cbuf_free(c);
+    for (auto* h : G->h) spada_b200_destroy(h);
+    delete G;
+}
+
+extern "C" int spada_b200_group_create(const spada_b200_opts* opts, uint32_t n_gpus, spada_b200_group_t** out) {
+    if (!out || n_gpus == 0 || n_gpus > 8) return fail(SPADA_B200_INVALID_ARG, "group_create: 1..8 GPUs");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SPADA_B200_NO_DEVICE, "no CUDA device; this engine has no CPU fallback");
+    }
+    if ((int)n_gpus > n) return fail(SPADA_B200_INVALID_ARG, "group_create: %u GPUs asked, %d present", n_gpus, n);
+    spada_b200_group* G = new (std::nothrow) spada_b200_group;
+    if (!G) return fail(SPADA_B200_OOM, "host allocation failed");
+    for (uint32_t d = 0; d < n_gpus; ++d) {
+        spada_b200_opts o{};
+        if (opts) o = *opts;
+        else {
+            o.accelerator = SPADA_B200_ACC_SPADA;
+            o.flags = SPADA_B200_FLAG_VALIDATE;
+        }
+        o.device = (int32_t)d;
+        o.stream = nullptr;
+        spada_b200* h = nullptr;
+        int rc = spada_b200_create(&o, &h);
+        if (rc) {
+            spada_b200_group_destroy(G);
+            return rc;
+        }
+        G->h.push_back(h);
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (uint32_t i = 0; i < n_gpus; ++i)
+        for (uint32_t j = 0; j < n_gpus; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, (int)i, (int)j);
+            if (!can) {
+                cudaSetDevice(prev);
+                spada_b200_group_destroy(G);
+                return fail(SPADA_B200_CUDA_ERROR, "device %u cannot map device %u's memory (no NVLink / P2P)", i, j);
+            }
+            cudaSetDevice((int)i);
+            cudaError_t e = cudaDeviceEnablePeerAccess((int)j, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                cudaSetDevice(prev);
+                spada_b200_group_destroy(G);
+                return fail(SPADA_B200_CUDA_ERROR, "cudaDeviceEnablePeerAccess(%u -> %u): %s", i, j, cudaGetErrorString(e));
+            }
+            cudaGetLastError();
+        }
+    cudaSetDevice(prev);
+    *out = G;
+    return 0;
+}
+
+namespace {
+// replicate a device operand of device 0 onto device d (NVLink peer copies)
+int replicate(spada_b200* h0, const spada_b200_csr* src, spada_b200* hd, spada_b200_csr** out) {
+    DeviceGuard g(hd->device);
+    int64_t* ptr;
+    int32_t* col;
+    double* val;
+    int rc = make_csr(hd, (uint64_t)src->d.rows, (uint64_t)src->d.cols, (uint64_t)src->d.nnz, out, &ptr, &col, &val);
+    if (rc) return rc;
+    cudaStream_t s = hd->stream;
+    cudaError_t e = cudaMemcpyPeerAsync(ptr, hd->device, src->d.ptr, h0->device, (size_t)(src->d.rows + 1) * sizeof(int64_t), s);
+    if (e == cudaSuccess && src->d.nnz)
+        e = cudaMemcpyPeerAsync(col, hd->device, src->d.col, h0->device, (size_t)src->d.nnz * sizeof(int32_t), s);
+    if (e == cudaSuccess && src->d.nnz)
+        e = cudaMemcpyPeerAsync(val, hd->device, src->d.val, h0->device, (size_t)src->d.nnz * sizeof(double), s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        spada_b200_csr_free(*out);
+        *out = nullptr;
+        return fail(SPADA_B200_CUDA_ERROR, "replicating an operand to device %d: %s", hd->device, cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+template <typename View, typename UploadFn>
+int group_spgemm(spada_b200_group* G, const View* a, const View* b, spada_b200_result_t** out, UploadFn upload) {
+    if (!G || !a || !b || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    const uint32_t N = (uint32_t)G->h.size();
+    if (a->cols != b->rows)
+        return fail(SPADA_B200_DIM_MISMATCH, "A is %llu x %llu but B has %llu rows", (unsigned long long)a->rows,
+                    (unsigned long long)a->cols, (unsigned long long)b->rows);
+    std::vector<spada_b200_csr*> A(N, nullptr), B(N, nullptr);
+    std::vector<spada_b200_shard*> S(N, nullptr);
+    auto cleanup = [&]() {
+        for (uint32_t d = 0; d < N; ++d) {
+            if (S[d]) shard_free(S[d]);
+            if (B[d] && B[d] != A[d]) spada_b200_csr_free(B[d]);
+            if (A[d]) spada_b200_csr_free(A[d]);
+        }
+    };
+    int rc;
+    const bool alias = (const void*)a == (const void*)b ||
+                       (a->indptr == b->indptr && a->indices == b->indices && a->data == b->data && a->rows == b->rows &&
+                        a->cols == b->cols);
+    if ((rc = upload(G->h[0], a, &A[0]))) return rc;
+    if (alias) B[0] = A[0];
+    else if ((rc = upload(G->h[0], b, &B[0]))) { cleanup(); return rc; }
+    for (uint32_t d = 1; d < N; ++d) {
+        if ((rc = replicate(G->h[0], A[0], G->h[d], &A[d]))) { cleanup(); return rc; }
+        if (alias) B[d] = A[d];
+        else if ((rc = replicate(G->h[0], B[0], G->h[d], &B[d]))) { cleanup(); return rc; }
+    }
+    std::vector<uint64_t> bounds(N + 1, 0);
+    uint64_t products = 0;
+    if ((rc = spada_b200_plan_shards(G->h[0], A[0], B[0], N, bounds.data()))) { cleanup(); return rc; }
+    products = G->h[0]->h_ctr->total_products;
+    if (G->bufs.empty() || G->buf_rows != a->rows || G->buf_cap < products) {
+        for (auto* c : G->bufs) spada_b200_cbuf_free(c);
+        G->bufs.assign(N, nullptr);
+        for (uint32_t d = 0; d < N; ++d)
+            if ((rc = spada_b200_cbuf_create(G->h[d], a->rows, b->cols, products, &G->bufs[d]))) {
+                for (auto*& c : G->bufs) { spada_b200_cbuf_free(c); c = nullptr; }
+                G->bufs.clear();
+                cleanup();
+                return rc;
+            }
+        G->buf_rows = a->rows;
+        G->buf_cap = products;
+    }
+    // first halves, one host thread per device
+    std::vector<int> rcs(N, 0);
+    std::vector<std::string> errs(N);
+    std::vector<uint64_t> nnz(N, 0);
+    {
+        std::vector<std::thread> th;
+        for (uint32_t d = 0; d < N; ++d)
+            th.emplace_back([&, d]() {
+                rcs[d] = spada_b200_shard_begin(G->h[d], A[d], B[d], bounds[d], bounds[d + 1], nullptr, &nnz[d], &S[d]);
+                if (rcs[d]) errs[d] = g_err;
+            });
+        for (auto& t : th) t.join();
+    }
+    for (uint32_t d = 0; d < N; ++d)
+        if (rcs[d]) {
+            cleanup();
+            return fail(rcs[d], "device %u: %s", d, errs[d].c_str());
+        }
+    // second halves: every shard goes into every device's buffers at its global offset
+    std::vector<uint64_t> off(N + 1, 0);
+    for (uint32_t d = 0; d < N; ++d) off[d + 1] = off[d] + nnz[d];
+    std::vector<spada_b200_stats> stats(N);
+    {
+        std::vector<std::thread> th;
+        for (uint32_t d = 0; d < N; ++d)
+            th.emplace_back([&, d]() {
+                std::vector<spada_b200_cbuf*> order;
+                order.push_back(G->bufs[d]);
+                for (uint32_t e = 0; e < N; ++e)
+                    if (e != d) order.push_back(G->bufs[e]);
+                spada_b200_shard* s = S[d];
+                S[d] = nullptr;   // finish releases it
+                rcs[d] = spada_b200_shard_finish(s, order.data(), N, off[d], nullptr, d, &stats[d]);
+                if (rcs[d]) errs[d] = g_err;
+            });
+        for (auto& t : th) t.join();
+    }
+    for (uint32_t d = 0; d < N; ++d)
+        if (rcs[d]) {
+            cleanup();
+            return fail(rcs[d], "device %u: %s", d, errs[d].c_str());
+        }
+    // the gathered C of device 0 becomes the result (its buffers change owner)
+    spada_b200_result* R = new (std::nothrow) spada_b200_result;
+    if (!R) { cleanup(); return fail(SPADA_B200_OOM, "host allocation failed"); }
+    memset(R, 0, sizeof(*R));
+    spada_b200_cbuf* c0 = G->bufs[0];
+    R->h = G->h[0];
+    R->rows = a->rows;
+    R->cols = b->cols;
+    R->nnz = off[N];
+    R->ptr = c0->ptr;
+    R->col = c0->col;
+    R->val = c0->val;
+    R->stats = stats[0];
+    R->stats.rows = a->rows;
+    R->stats.nnz_a = a->nnz;
+    R->stats.products = products;
+    R->stats.nnz_c = off[N];
+    float ms = 0.f;
+    for (uint32_t d = 0; d < N; ++d) ms = std::max(ms, stats[d].ms_total);
+    R->stats.ms_total = ms;
+    delete c0;
+    for (uint32_t d = 1; d < N; ++d) spada_b200_cbuf_free(G->bufs[d]);
+    G->bufs.clear();
+    cleanup();
+    *out = R;
+    return 0;
+}
+}  // namespace
+
+extern "C" int spada_b200_group_spgemm(spada_b200_group_t* G, const spada_csr_view* a, const spada_csr_view* b,
+                                       spada_b200_result_t** out) {
+    return group_spgemm(G, a, b, out, spada_b200_upload);
+}
+extern "C" int spada_b200_group_spgemm32(spada_b200_group_t* G, const spada_csr_view32* a, const spada_csr_view32* b,
+                                         spada_b200_result_t** out) {
+    return group_spgemm(G, a, b, out, spada_b200_upload32);
 }
 
 namespace {

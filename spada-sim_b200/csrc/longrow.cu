@@ -25,13 +25,13 @@
 //           sums its run left to right and the finished row goes to its scratch row, nnz recorded.
 //
 // HBM traffic per product: 12 B written by the sort, 24 B per merge level, 4 + 24 B for the sums.
+#include <algorithm>
+
 #include "cta_common.cuh"
 
 namespace spada {
 
 constexpr int LR_THREADS = ESC_CTA_THREADS;
-constexpr int LR_ITEMS = LONG_UNIT / LR_THREADS;   // outputs per thread of a merge tile
-static_assert(LR_ITEMS == 16, "merge tiles are 256 threads x 16 outputs");
 
 // largest i in [0, n) with off[i] <= v; off is non-decreasing and off[0] <= v.  The whole warp probes 32 positions
 // per step (a 32-ary search: 4 dependent loads for a million rows instead of 20).
@@ -101,39 +101,53 @@ struct UnitInfo {
     uint32_t t;        // chunk / tile number inside the row
     int64_t base;      // start of the row inside the ping-pong buffers
 };
-__device__ __forceinline__ bool find_unit(int64_t g, const int64_t* __restrict__ unit_off,
-                                          const int64_t* __restrict__ prod_off, const uint32_t* __restrict__ p,
-                                          const uint32_t* __restrict__ rows_list, uint32_t n, UnitInfo* s_info) {
+__device__ __forceinline__ bool find_unit(int64_t g, const uint32_t* __restrict__ unit_row,
+                                          const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
+                                          const uint32_t* __restrict__ p, const uint32_t* __restrict__ rows_list, uint32_t n,
+                                          UnitInfo* s_info) {
     if (g >= unit_off[n]) return false;   // uniform over the CTA
-    if (threadIdx.x < 32) {
-        const uint32_t i = (uint32_t)warp_search_le<int64_t, int64_t>(unit_off, n, g, lane_id());
-        if (threadIdx.x == 0) {
-            s_info->i = i;
-            s_info->row = rows_list[i];
-            s_info->P = p[i];
-            s_info->t = (uint32_t)(g - unit_off[i]);
-            s_info->base = prod_off[i];
-        }
+    if (threadIdx.x == 0) {
+        const uint32_t i = unit_row[g];
+        s_info->i = i;
+        s_info->row = rows_list[i];
+        s_info->P = p[i];
+        s_info->t = (uint32_t)(g - unit_off[i]);
+        s_info->base = prod_off[i];
     }
     __syncthreads();
     return true;
 }
 
+// unit_row[g] = row (index inside the wave) of chunk / tile g: one binary search per unit, once per wave
+__global__ void k_long_units(const int64_t* __restrict__ unit_off, uint32_t n, uint32_t* __restrict__ unit_row) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= unit_off[n]) return;
+    uint32_t lo = 0, hi = n;   // unit_off[lo] <= g < unit_off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (unit_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    unit_row[g] = lo;
+}
+
 // ---- sort: one CTA per chunk ---------------------------------------------------------------------------------
-template <typename K>
+// G = 2: the chunk is sorted as two groups of 2048 with 32-bit keys and the groups are merged in shared memory
+// (columns up to 2^21 without 64-bit keys: the 64-bit network measured 3.2x slower per product)
+template <typename K, int G>
 __global__ void __launch_bounds__(LR_THREADS)
 k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list, uint32_t n,
-                  const uint32_t* __restrict__ p, const int64_t* __restrict__ unit_off,
+                  const uint32_t* __restrict__ p, const uint32_t* __restrict__ unit_row, const int64_t* __restrict__ unit_off,
                   const int64_t* __restrict__ prod_off, const uint32_t* __restrict__ aseq,
                   int32_t* __restrict__ out_col, double* __restrict__ out_val) {
     constexpr int N = LONG_UNIT;
+    constexpr int SBG = Log2<N / G>::v;
     extern __shared__ __align__(16) unsigned char s_raw[];
     K* keys = reinterpret_cast<K*>(s_raw);
     double* vals = reinterpret_cast<double*>(s_raw + sizeof(K) * N);
     __shared__ CtaStage st;
     __shared__ UnitInfo info;
     __shared__ int64_t s_e[2];
-    if (!find_unit(blockIdx.x, unit_off, prod_off, p, rows_list, n, &info)) return;
+    if (!find_unit(blockIdx.x, unit_row, unit_off, prod_off, p, rows_list, n, &info)) return;
     const int lane = lane_id();
     const uint32_t s0 = info.t << LONG_UNIT_LOG;
     const uint32_t cnt = info.P - s0 < (uint32_t)N ? info.P - s0 : (uint32_t)N;
@@ -202,7 +216,7 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restr
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (t[u] < end) {
-                    keys[t[u]] = ((K)c[u] << LONG_UNIT_LOG) | (K)t[u];
+                    keys[t[u]] = ((K)c[u] << SBG) | (K)(t[u] & (N / G - 1));
                     vals[t[u]] = __dmul_rn(st.av[j[u]], bv[u]);
                 }
         }
@@ -210,12 +224,20 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restr
     }
     for (int t = (int)cnt + threadIdx.x; t < N; t += LR_THREADS) keys[t] = KeyTraits<K>::sentinel;
     __syncthreads();
-    bitonic_cta_sort<K, N>(keys);
+    bitonic_cta_sort<K, N, G>(keys);
     const int64_t dst = info.base + s0;
-    for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
-        const K key = keys[t];
-        out_col[dst + t] = (int32_t)(uint32_t)(key >> LONG_UNIT_LOG);
-        out_val[dst + t] = vals[(int)(key & (K)(N - 1))];
+    if constexpr (G == 2) {
+        cta_merge_groups2<N>(keys, vals, (int)cnt);
+        for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
+            out_col[dst + t] = (int32_t)keys[t];
+            out_val[dst + t] = vals[t];
+        }
+    } else {
+        for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
+            const K key = keys[t];
+            out_col[dst + t] = (int32_t)(uint32_t)(key >> LONG_UNIT_LOG);
+            out_val[dst + t] = vals[(int)(key & (K)(N - 1))];
+        }
     }
 }
 
@@ -231,84 +253,171 @@ __device__ __forceinline__ int merge_path(P x, int nx, P y, int ny, int d) {
     return lo;
 }
 
-__global__ void __launch_bounds__(LR_THREADS, 3)
-k_long_merge(const uint32_t* __restrict__ rows_list, uint32_t n, uint32_t i_lo, int level,
-             const uint32_t* __restrict__ p, const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
-             const int32_t* __restrict__ in_col, const double* __restrict__ in_val, int32_t* __restrict__ out_col,
-             double* __restrict__ out_val) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    int32_t* s_col = reinterpret_cast<int32_t*>(s_raw);
-    double* s_val = reinterpret_cast<double*>(s_raw + sizeof(int32_t) * LONG_UNIT);
-    __shared__ UnitInfo info;
-    __shared__ int s_part[2];
-    if (!find_unit(unit_off[i_lo] + blockIdx.x, unit_off, prod_off, p, rows_list, n, &info)) return;
-    const uint32_t P = info.P;
-    if (level > long_levels(P)) return;   // the row was finished by an earlier level (cannot happen inside level bins)
-    const uint64_t RL = (uint64_t)LONG_UNIT << (level - 1);
-    const uint64_t o0 = (uint64_t)info.t << LONG_UNIT_LOG;
-    const uint64_t o1 = o0 + LONG_UNIT < P ? o0 + LONG_UNIT : P;
-    const uint64_t pbase = o0 / (2 * RL) * (2 * RL);
-    const uint64_t xe = pbase + RL < P ? pbase + RL : P;
-    const uint64_t ye = pbase + 2 * RL < P ? pbase + 2 * RL : P;
-    const int nx = (int)(xe - pbase), ny = (int)(ye - xe);
-    const int32_t* X = in_col + info.base + pbase;
-    const int32_t* Y = in_col + info.base + xe;
-    if (threadIdx.x == 0) s_part[0] = merge_path(X, nx, Y, ny, (int)(o0 - pbase));
-    if (threadIdx.x == 32) s_part[1] = merge_path(X, nx, Y, ny, (int)(o1 - pbase));
-    __syncthreads();
-    const int i0 = s_part[0], i1 = s_part[1];
-    const int j0 = (int)(o0 - pbase) - i0, j1 = (int)(o1 - pbase) - i1;
-    const int cx = i1 - i0, cy = j1 - j0, tot = cx + cy;
-    const double* Xv = in_val + info.base + pbase;
-    const double* Yv = in_val + info.base + xe;
-    for (int t = threadIdx.x; t < cx; t += LR_THREADS) {
-        s_col[t] = X[i0 + t];
-        s_val[t] = Xv[i0 + t];
+// Every level runs two kernels.  k_long_partition: one thread per output tile finds the tile's input slices with two
+// merge-path searches (millions of independent searches hide their latency) and leaves a 32-byte descriptor.
+// k_long_merge: persistent CTAs with two shared-memory stages; thread 0 reads a descriptor and starts the four TMA
+// bulk copies (cp.async.bulk, SASS UBLKCP) of a tile two tiles ahead, so the input slices of tile k+1 are in flight
+// while tile k is merged; completion is counted by the stage's mbarrier.  Bulk copies need 16-byte aligned addresses
+// and sizes: every slice is fetched from the aligned address below its start to the aligned address above its end,
+// the merge indexes past the few extra elements.
+constexpr int MG_THREADS = 512;
+constexpr int MG_ITEMS = LONG_UNIT / MG_THREADS;   // outputs per thread
+constexpr int MG_PAD = 16;
+struct MergeStage {
+    int32_t col[LONG_UNIT + MG_PAD];
+    double val[LONG_UNIT + MG_PAD];
+};
+struct __align__(16) MergeTile {
+    int64_t ax, ay;       // element index (inside the buffers) of the first X / Y element the tile consumes
+    int64_t out;          // where the tile's outputs go
+    int32_t cx, cy;       // elements taken from X and from Y
+};
+
+__global__ void __launch_bounds__(256)
+k_long_partition(const uint32_t* __restrict__ unit_row, uint32_t n, uint32_t i_lo, int level, const uint32_t* __restrict__ p,
+                 const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
+                 const int32_t* __restrict__ in_col, MergeTile* __restrict__ tiles) {
+    const int64_t g0 = unit_off[i_lo];
+    const int64_t g = g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= unit_off[n]) return;
+    const uint32_t i = unit_row[g];
+    const uint32_t P = p[i];
+    const int64_t base = prod_off[i];
+    MergeTile T{};
+    if (level <= long_levels(P)) {   // rows finished by an earlier level take no part (cannot happen inside level bins)
+        const uint64_t RL = (uint64_t)LONG_UNIT << (level - 1);
+        const uint64_t o0 = (uint64_t)(g - unit_off[i]) << LONG_UNIT_LOG;
+        const uint64_t o1 = o0 + LONG_UNIT < P ? o0 + LONG_UNIT : P;
+        const uint64_t pbase = o0 / (2 * RL) * (2 * RL);
+        const uint64_t xe = pbase + RL < P ? pbase + RL : P;
+        const uint64_t ye = pbase + 2 * RL < P ? pbase + 2 * RL : P;
+        const int nx = (int)(xe - pbase), ny = (int)(ye - xe);
+        const int32_t* X = in_col + base + pbase;
+        const int32_t* Y = in_col + base + xe;
+        const int d0 = (int)(o0 - pbase), d1 = (int)(o1 - pbase);
+        const int i0 = merge_path(X, nx, Y, ny, d0);
+        const int i1 = (d1 == nx + ny) ? nx : merge_path(X, nx, Y, ny, d1);
+        T.ax = base + (int64_t)pbase + i0;
+        T.ay = base + (int64_t)xe + (d0 - i0);
+        T.out = base + (int64_t)o0;
+        T.cx = i1 - i0;
+        T.cy = (d1 - i1) - (d0 - i0);
     }
-    for (int t = threadIdx.x; t < cy; t += LR_THREADS) {
-        s_col[cx + t] = Y[j0 + t];
-        s_val[cx + t] = Yv[j0 + t];
+    tiles[g - g0] = T;
+}
+
+__global__ void __launch_bounds__(MG_THREADS, 2)
+k_long_merge(const MergeTile* __restrict__ tiles, int64_t n_tiles_bound, const int64_t* __restrict__ unit_off, uint32_t n,
+             uint32_t i_lo, const int32_t* __restrict__ in_col, const double* __restrict__ in_val,
+             int32_t* __restrict__ out_col, double* __restrict__ out_val) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    MergeStage* stage = reinterpret_cast<MergeStage*>(s_raw);
+    __shared__ __align__(8) uint64_t bar[2];
+    const int64_t n_tiles = unit_off[n] - unit_off[i_lo];
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
     }
     __syncthreads();
-    const int d = threadIdx.x * LR_ITEMS;
-    int32_t oc[LR_ITEMS];
-    double ov[LR_ITEMS];
-    if (d < tot) {
-        int i = merge_path(s_col, cx, s_col + cx, cy, d);
-        int j = d - i;
-        int32_t xk = i < cx ? s_col[i] : 0x7fffffff;
-        int32_t yk = j < cy ? s_col[cx + j] : 0x7fffffff;
+
+    // where the X and Y slices of a tile sit inside a stage (both start on 16-byte boundaries of the source)
+    auto layout = [](const MergeTile& T, int& xc, int& yc, int& xv, int& yv, int& nxc, int& nyc, int& nxv, int& nyv) {
+        const int dxc = (int)(T.ax & 3), dyc = (int)(T.ay & 3);
+        nxc = T.cx ? (dxc + T.cx + 3) & ~3 : 0;
+        nyc = T.cy ? (dyc + T.cy + 3) & ~3 : 0;
+        xc = dxc;
+        yc = nxc + dyc;
+        const int dxv = (int)(T.ax & 1), dyv = (int)(T.ay & 1);
+        nxv = T.cx ? (dxv + T.cx + 1) & ~1 : 0;
+        nyv = T.cy ? (dyv + T.cy + 1) & ~1 : 0;
+        xv = dxv;
+        yv = nxv + dyv;
+    };
+    auto issue = [&](const MergeTile& T, int sidx) {   // thread 0 only
+        if (T.cx + T.cy == 0) return;
+        int xc, yc, xv, yv, nxc, nyc, nxv, nyv;
+        layout(T, xc, yc, xv, yv, nxc, nyc, nxv, nyv);
+        MergeStage& st = stage[sidx];
+        mbar_expect_tx(&bar[sidx], (uint32_t)(nxc + nyc) * 4u + (uint32_t)(nxv + nyv) * 8u);
+        if (T.cx) {
+            tma_load_1d(st.col, in_col + (T.ax - xc), (uint32_t)nxc * 4u, &bar[sidx]);
+            tma_load_1d(st.val, in_val + (T.ax - xv), (uint32_t)nxv * 8u, &bar[sidx]);
+        }
+        if (T.cy) {
+            tma_load_1d(st.col + nxc, in_col + (T.ay - (yc - nxc)), (uint32_t)nyc * 4u, &bar[sidx]);
+            tma_load_1d(st.val + nxv, in_val + (T.ay - (yv - nxv)), (uint32_t)nyv * 8u, &bar[sidx]);
+        }
+    };
+
+    const int64_t G = gridDim.x;
+    int64_t t = blockIdx.x;
+    if (threadIdx.x == 0) {
+        if (t < n_tiles) issue(tiles[t], 0);
+        if (t + G < n_tiles) issue(tiles[t + G], 1);
+    }
+    uint32_t phase[2] = {0u, 0u};
+    for (int k = 0; t < n_tiles; ++k, t += G) {
+        const int cur = k & 1;
+        const MergeTile T = tiles[t];
+        MergeTile ahead{};   // descriptor of the tile two ahead: loaded now, used when this stage is free again
+        const bool has_ahead = threadIdx.x == 0 && t + 2 * G < n_tiles;
+        if (has_ahead) ahead = tiles[t + 2 * G];
+        const int cx = T.cx, cy = T.cy, tot = cx + cy;
+        if (tot == 0) {                       // uniform; nothing was issued for this tile
+            if (has_ahead) issue(ahead, cur);
+            continue;
+        }
+        int ixc, iyc, ixv, iyv, nxc, nyc, nxv, nyv;
+        layout(T, ixc, iyc, ixv, iyv, nxc, nyc, nxv, nyv);
+        mbar_wait(&bar[cur], phase[cur]);
+        phase[cur] ^= 1u;
+        MergeStage& st = stage[cur];
+        const int32_t* xc = st.col + ixc;
+        const int32_t* yc = st.col + iyc;
+        const double* xv = st.val + ixv;
+        const double* yv = st.val + iyv;
+        const int d = threadIdx.x * MG_ITEMS;
+        int32_t oc[MG_ITEMS];
+        double ov[MG_ITEMS];
+        if (d < tot) {
+            int i = merge_path(xc, cx, yc, cy, d);
+            int j = d - i;
+            int32_t xk = i < cx ? xc[i] : 0x7fffffff;
+            int32_t yk = j < cy ? yc[j] : 0x7fffffff;
 #pragma unroll
-        for (int q = 0; q < LR_ITEMS; ++q) {
-            if (d + q < tot) {
-                const bool tx = j >= cy || (i < cx && xk <= yk);
-                const int src = tx ? i : cx + j;
-                oc[q] = tx ? xk : yk;
-                ov[q] = s_val[src];
-                if (tx) {
-                    ++i;
-                    xk = i < cx ? s_col[i] : 0x7fffffff;
-                } else {
-                    ++j;
-                    yk = j < cy ? s_col[cx + j] : 0x7fffffff;
+            for (int q = 0; q < MG_ITEMS; ++q) {
+                if (d + q < tot) {
+                    const bool tx = j >= cy || (i < cx && xk <= yk);
+                    oc[q] = tx ? xk : yk;
+                    ov[q] = tx ? xv[i] : yv[j];
+                    if (tx) {
+                        ++i;
+                        xk = i < cx ? xc[i] : 0x7fffffff;
+                    } else {
+                        ++j;
+                        yk = j < cy ? yc[j] : 0x7fffffff;
+                    }
                 }
             }
         }
-    }
-    __syncthreads();
-    if (d < tot) {
+        __syncthreads();
+        if (d < tot) {
 #pragma unroll
-        for (int q = 0; q < LR_ITEMS; ++q)
-            if (d + q < tot) {
-                s_col[d + q] = oc[q];
-                s_val[d + q] = ov[q];
-            }
-    }
-    __syncthreads();
-    const int64_t dst = info.base + (int64_t)o0;
-    for (int t = threadIdx.x; t < tot; t += LR_THREADS) {
-        out_col[dst + t] = s_col[t];
-        out_val[dst + t] = s_val[t];
+            for (int q = 0; q < MG_ITEMS; ++q)
+                if (d + q < tot) {
+                    st.col[d + q] = oc[q];
+                    st.val[d + q] = ov[q];
+                }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < tot; e += MG_THREADS) {
+            out_col[T.out + e] = st.col[e];
+            out_val[T.out + e] = st.val[e];
+        }
+        // the stage goes back to the async proxy: the bulk copies of the tile two ahead write it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (has_ahead) issue(ahead, cur);
     }
 }
 
@@ -316,11 +425,11 @@ k_long_merge(const uint32_t* __restrict__ rows_list, uint32_t n, uint32_t i_lo, 
 // heads (first entry of a run of equal columns) that start inside every tile of 4096 sorted products
 __global__ void __launch_bounds__(LR_THREADS)
 k_long_count(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t* __restrict__ p,
-             const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
+             const uint32_t* __restrict__ unit_row, const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
              const int32_t* __restrict__ col0, const int32_t* __restrict__ col1, uint32_t* __restrict__ unit_heads) {
     __shared__ UnitInfo info;
     __shared__ int s_w[LR_THREADS / 32];
-    if (!find_unit(blockIdx.x, unit_off, prod_off, p, rows_list, n, &info)) return;
+    if (!find_unit(blockIdx.x, unit_row, unit_off, prod_off, p, rows_list, n, &info)) return;
     const int32_t* col = ((long_levels(info.P) & 1) ? col1 : col0) + info.base;
     const uint32_t o0 = info.t << LONG_UNIT_LOG;
     const uint32_t o1 = info.P - o0 < (uint32_t)LONG_UNIT ? info.P : o0 + LONG_UNIT;
@@ -338,54 +447,241 @@ k_long_count(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t*
     }
 }
 
-// every head sums its run left to right (the oracle's order: ascending k) and writes the entry of the finished row
+// Every head sums its run left to right (the oracle's order: ascending k) and writes the entry of the finished row.
+// The tile's 4096 sorted products are staged in shared memory first (coalesced loads, all in flight at once), so
+// the dependent chain of a run (compare the next column, add the next value) runs at shared-memory latency, and all
+// heads of the tile run side by side: warp w owns the positions [512 w, 512 (w + 1)), lanes interleaved.  A run that
+// leaves the tile (at most one: the tile's last) is streamed by the whole CTA, 4096 products at a time, with one
+// thread doing the adds in order -- the diagonal of A x A^T is one run of nnz(A row) products.
 __global__ void __launch_bounds__(LR_THREADS)
 k_long_reduce(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t* __restrict__ p,
-              const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
+              const uint32_t* __restrict__ unit_row, const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
               const int32_t* __restrict__ col0, const int32_t* __restrict__ col1, const double* __restrict__ val0,
               const double* __restrict__ val1, const int64_t* __restrict__ unit_hoff, const int64_t* __restrict__ t_ptr,
               int32_t* __restrict__ t_col, double* __restrict__ t_val, uint32_t* __restrict__ row_nnz) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    int32_t* s_col = reinterpret_cast<int32_t*>(s_raw);
+    double* s_val = reinterpret_cast<double*>(s_raw + sizeof(int32_t) * LONG_UNIT);
     __shared__ UnitInfo info;
     __shared__ int s_w[LR_THREADS / 32];
-    if (!find_unit(blockIdx.x, unit_off, prod_off, p, rows_list, n, &info)) return;
+    __shared__ int s_prev;            // column of the product before the tile
+    __shared__ int s_open_rank;       // output slot of the run that leaves the tile, -1: none
+    __shared__ double s_open_sum;
+    __shared__ int s_end;
+    if (!find_unit(blockIdx.x, unit_row, unit_off, prod_off, p, rows_list, n, &info)) return;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const bool odd = long_levels(info.P) & 1;
     const int32_t* col = (odd ? col1 : col0) + info.base;
     const double* val = (odd ? val1 : val0) + info.base;
     const uint32_t P = info.P;
     const uint32_t o0 = info.t << LONG_UNIT_LOG;
-    const uint32_t o1 = P - o0 < (uint32_t)LONG_UNIT ? P : o0 + LONG_UNIT;
+    const int cnt = (int)(P - o0 < (uint32_t)LONG_UNIT ? P - o0 : (uint32_t)LONG_UNIT);
     const int64_t row_h0 = unit_hoff[unit_off[info.i]];
-    int64_t dst = t_ptr[info.row] + (unit_hoff[blockIdx.x] - row_h0);
+    const int64_t dst = t_ptr[info.row] + (unit_hoff[blockIdx.x] - row_h0);
     if (info.t == 0 && threadIdx.x == 0) row_nnz[info.row] = (uint32_t)(unit_hoff[unit_off[info.i + 1]] - row_h0);
-    for (uint32_t pb = o0; pb < o1; pb += LR_THREADS) {
-        const uint32_t pos = pb + threadIdx.x;
-        int32_t c = 0;
-        bool head = false;
-        if (pos < o1) {
-            c = col[pos];
-            head = pos == 0 || col[pos - 1] != c;
-        }
-        const unsigned hm = __ballot_sync(FULL, head);
-        if (lane == 0) s_w[warp] = __popc(hm);
-        __syncthreads();
-        int before = 0, all = 0;
-#pragma unroll
-        for (int w = 0; w < LR_THREADS / 32; ++w) {
-            const int t = s_w[w];
-            if (w < warp) before += t;
-            all += t;
-        }
-        if (head) {
-            double sum = val[pos];
-            for (uint32_t j = pos + 1; j < P && col[j] == c; ++j) sum = __dadd_rn(sum, val[j]);
-            const int64_t o = dst + before + __popc(hm & ((1u << lane) - 1u));
-            st_out(t_col + o, c);
-            st_out(t_val + o, sum);
-        }
-        dst += all;
-        __syncthreads();
+    for (int t = threadIdx.x; t < cnt; t += LR_THREADS) {
+        s_col[t] = col[o0 + t];
+        s_val[t] = val[o0 + t];
     }
+    if (threadIdx.x == 0) {
+        s_prev = o0 ? col[o0 - 1] : -1;
+        s_open_rank = -1;
+    }
+    __syncthreads();
+    constexpr int SEG = LONG_UNIT / (LR_THREADS / 32);   // positions per warp
+    constexpr int ITERS = SEG / 32;
+    unsigned hm[ITERS];
+    int mine = 0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int t = warp * SEG + it * 32 + lane;
+        bool head = false;
+        if (t < cnt) {
+            const int32_t c = s_col[t];
+            head = (t == 0) ? (s_prev != c) : (s_col[t - 1] != c);
+        }
+        hm[it] = __ballot_sync(FULL, head);
+        mine += __popc(hm[it]);
+    }
+    if (lane == 0) s_w[warp] = mine;
+    __syncthreads();
+    int rank = 0;
+#pragma unroll
+    for (int w = 0; w < LR_THREADS / 32; ++w)
+        if (w < warp) rank += s_w[w];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        if ((hm[it] >> lane) & 1u) {
+            const int t = warp * SEG + it * 32 + lane;
+            const int32_t c = s_col[t];
+            double sum = s_val[t];
+            int j = t + 1;
+            while (j < cnt && s_col[j] == c) {
+                sum = __dadd_rn(sum, s_val[j]);
+                ++j;
+            }
+            const int o = rank + __popc(hm[it] & ((1u << lane) - 1u));
+            st_out(t_col + dst + o, c);
+            if (j == cnt && o0 + (uint32_t)cnt < P) {   // the run may go on in the next tile: finished below
+                s_open_rank = o;
+                s_open_sum = sum;
+            } else {
+                st_out(t_val + dst + o, sum);
+            }
+        }
+        rank += __popc(hm[it]);
+    }
+    __syncthreads();
+    if (s_open_rank < 0) return;   // uniform
+    const int32_t c = s_col[cnt - 1];
+    double sum = s_open_sum;
+    for (uint32_t q0 = o0 + (uint32_t)cnt; q0 < P; q0 += LONG_UNIT) {
+        const int len = (int)(P - q0 < (uint32_t)LONG_UNIT ? P - q0 : (uint32_t)LONG_UNIT);
+        __syncthreads();
+        if (threadIdx.x == 0) s_end = len;
+        for (int t = threadIdx.x; t < len; t += LR_THREADS) {
+            s_col[t] = col[q0 + t];
+            s_val[t] = val[q0 + t];
+        }
+        __syncthreads();
+        // first position whose column differs: the sorted order makes "differs" monotone, so probing the chunk's
+        // positions with one atomicMin per warp that sees the change is enough
+        for (int tb = 0; tb < len; tb += LR_THREADS) {
+            const int t = tb + threadIdx.x;
+            const bool diff = t < len && s_col[t] != c;
+            const unsigned dm = __ballot_sync(FULL, diff);
+            if (diff && (dm & ((1u << lane) - 1u)) == 0) atomicMin(&s_end, t);
+        }
+        __syncthreads();
+        const int e = s_end;
+        if (threadIdx.x == 0) {
+            int j = 0;
+            for (; j + 8 <= e; j += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = s_val[j + u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, v[u]);
+            }
+            for (; j < e; ++j) sum = __dadd_rn(sum, s_val[j]);
+        }
+        if (e < len) break;   // uniform: s_end is shared
+    }
+    if (threadIdx.x == 0) st_out(t_val + dst + s_open_rank, sum);
+}
+
+// ---- narrow outputs: long rows of a product with few columns ------------------------------------------------
+// When B has few columns (cari: 400) a long row lands on few outputs, every one hit hundreds of times; carrying all
+// those products through merge levels is wasted traffic.  One CTA per row keeps a dense accumulator of B.cols values
+// in shared memory and walks the A row in stored order: all threads take the elements of ONE B row (distinct columns,
+// no conflicts), then a barrier, then the next B row -- every column is updated in ascending k, the oracle's order,
+// without atomics.  The first product of a column is stored as it is (not added to +0.0: -0.0 survives).  The
+// elements of the next B row are fetched into registers while the current one is applied.
+constexpr int DN_THREADS = 128;
+constexpr int DN_BATCH = 256;     // A entries staged per batch
+
+__global__ void __launch_bounds__(DN_THREADS)
+k_dense_rows(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list, const int64_t* __restrict__ t_ptr,
+             int32_t* __restrict__ t_col, double* __restrict__ t_val, uint32_t* __restrict__ row_nnz) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int ncols = (int)b.cols;
+    double* acc = reinterpret_cast<double*>(s_raw);
+    unsigned char* hit = s_raw + sizeof(double) * (size_t)ncols;
+    __shared__ int64_t s_bs[DN_BATCH];
+    __shared__ int s_len[DN_BATCH];
+    __shared__ double s_av[DN_BATCH];
+    __shared__ int s_w[DN_THREADS / 32];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t r = rows_list[blockIdx.x];
+    const int64_t a0 = a.ptr[row_begin + r], a1 = a.ptr[row_begin + r + 1];
+    for (int c = threadIdx.x; c < ncols; c += DN_THREADS) hit[c] = 0;
+    for (int64_t pb = a0; pb < a1; pb += DN_BATCH) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < DN_BATCH; t += DN_THREADS) {
+            const int64_t e = pb + t;
+            int64_t bs = 0;
+            int len = 0;
+            double av = 0.0;
+            if (e < a1) {
+                av = ldg_f64(a.val + e);
+                b_row(b, ldg_i32(a.col + e), bs, len);
+            }
+            s_bs[t] = bs;
+            s_len[t] = len;
+            s_av[t] = av;
+        }
+        __syncthreads();
+        const int n_ent = (int)((a1 - pb) < DN_BATCH ? (a1 - pb) : DN_BATCH);
+        // software pipeline: the first DN_THREADS elements of entry i + 1 are loaded while entry i is applied
+        int32_t nc = 0;
+        double nv = 0.0;
+        if ((int)threadIdx.x < s_len[0]) {
+            nc = ldg_i32(b.col + s_bs[0] + threadIdx.x);
+            nv = ldg_f64(b.val + s_bs[0] + threadIdx.x);
+        }
+        for (int i = 0; i < n_ent; ++i) {
+            const int32_t c0 = nc;
+            const double v0 = nv;
+            if (i + 1 < n_ent && (int)threadIdx.x < s_len[i + 1]) {
+                nc = ldg_i32(b.col + s_bs[i + 1] + threadIdx.x);
+                nv = ldg_f64(b.val + s_bs[i + 1] + threadIdx.x);
+            }
+            const int len = s_len[i];
+            const double av = s_av[i];
+            if ((int)threadIdx.x < len) {
+                const double prod = __dmul_rn(av, v0);
+                acc[c0] = hit[c0] ? __dadd_rn(acc[c0], prod) : prod;
+                hit[c0] = 1;
+            }
+            for (int t = threadIdx.x + DN_THREADS; t < len; t += DN_THREADS) {   // B rows longer than the CTA
+                const int32_t c = ldg_i32(b.col + s_bs[i] + t);
+                const double prod = __dmul_rn(av, ldg_f64(b.val + s_bs[i] + t));
+                acc[c] = hit[c] ? __dadd_rn(acc[c], prod) : prod;
+                hit[c] = 1;
+            }
+            __syncthreads();   // the next B row may hit the same columns: strictly after this one
+        }
+    }
+    __syncthreads();
+    // compaction in ascending column order: every thread owns a contiguous range of columns
+    const int per = (ncols + DN_THREADS - 1) / DN_THREADS;
+    const int cbeg = threadIdx.x * per, cend = cbeg + per < ncols ? cbeg + per : ncols;
+    int cnt = 0;
+    for (int c = cbeg; c < cend; ++c) cnt += hit[c];
+    int x = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    int base = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < DN_THREADS / 32; ++w) {
+        if (w < warp) base += s_w[w];
+        all += s_w[w];
+    }
+    int64_t o = t_ptr[r] + base + (x - cnt);
+    for (int c = cbeg; c < cend; ++c)
+        if (hit[c]) {
+            st_out(t_col + o, (int32_t)c);
+            st_out(t_val + o, acc[c]);
+            ++o;
+        }
+    if (threadIdx.x == 0) row_nnz[r] = (uint32_t)all;
+}
+
+bool dense_rows_fit(int64_t b_cols) { return b_cols > 0 && b_cols <= DENSE_MAX_COLS; }
+
+void launch_dense_rows(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* rows_list, uint32_t n_rows,
+                       const int64_t* t_ptr, int32_t* t_col, double* t_val, uint32_t* row_nnz, cudaStream_t s) {
+    if (!n_rows) return;
+    const size_t smem = (size_t)b.cols * (sizeof(double) + 1) + 16;
+    static PerDeviceOnce attr;
+    if (attr.first())
+        cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DENSE_MAX_COLS * 9 + 16));
+    k_dense_rows<<<n_rows, DN_THREADS, smem, s>>>(a, b, row_begin, rows_list, t_ptr, t_col, t_val, row_nnz);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -394,15 +690,16 @@ void launch_long_prefix(const DevCsr& a, int64_t row_begin, const uint32_t* rows
     if (n_rows) k_long_prefix<<<n_rows, LR_THREADS, 0, s>>>(a, row_begin, rows_list, b_len, aseq);
 }
 
-template <typename K>
+template <typename K, int G>
 static void chunk_sort_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* aseq, const LongWave& w,
                               cudaStream_t s) {
     const size_t smem = (sizeof(K) + sizeof(double)) * LONG_UNIT;
     static PerDeviceOnce attr;
     if (attr.first())
-        cudaFuncSetAttribute(k_long_chunk_sort<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_long_chunk_sort<K><<<(unsigned)w.unit_bound, LR_THREADS, smem, s>>>(a, b, row_begin, w.rows_list, w.n_rows, w.p,
-                                                                         w.unit_off, w.prod_off, aseq, w.col[0], w.val[0]);
+        cudaFuncSetAttribute(k_long_chunk_sort<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_long_chunk_sort<K, G><<<(unsigned)w.unit_bound, LR_THREADS, smem, s>>>(a, b, row_begin, w.rows_list, w.n_rows, w.p,
+                                                                         w.unit_row, w.unit_off, w.prod_off, aseq, w.col[0],
+                                                                         w.val[0]);
 }
 
 uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
@@ -416,30 +713,46 @@ uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, c
     k_long_setup<<<(w.n_rows + 255) / 256, 256, 0, s>>>(w.rows_list, w.n_rows, flops, w.p, w.u);
     launch_scan_u32_i64(w.p, w.n_rows, w.prod_off, w.tile_state, ctr, s);
     launch_scan_u32_i64(w.u, w.n_rows, w.unit_off, w.tile_state, ctr, s);
+    k_long_units<<<(unsigned)((w.unit_bound + 255) / 256), 256, 0, s>>>(w.unit_off, w.n_rows, w.unit_row);
     // sort: 32-bit (column << 12 | arrival) keys whenever they fit
-    if ((uint64_t)b.cols <= (1ull << (32 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t>(a, b, row_begin, aseq, w, s);
-    else chunk_sort_launch<uint64_t>(a, b, row_begin, aseq, w, s);
-    kernels += 4;
+    if ((uint64_t)b.cols <= (1ull << (32 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 1>(a, b, row_begin, aseq, w, s);
+    else if ((uint64_t)b.cols <= (1ull << (33 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 2>(a, b, row_begin, aseq, w, s);
+    else chunk_sort_launch<uint64_t, 1>(a, b, row_begin, aseq, w, s);
+    kernels += 5;
     off();
     // merge levels: rows are listed by ascending level count, level l takes the list from level_lo[l] on
     const size_t msmem = (sizeof(int32_t) + sizeof(double)) * LONG_UNIT;
+    const size_t mgsmem = 2 * sizeof(MergeStage);
     static PerDeviceOnce attr;
-    if (attr.first()) cudaFuncSetAttribute(k_long_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+    if (attr.first()) cudaFuncSetAttribute(k_long_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mgsmem);
+    static int merge_ctas = 0;   // persistent grid: two CTAs per SM
+    if (!merge_ctas) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        merge_ctas = 2 * sms;
+    }
     on("long_merge", w.level_grid[1]);
     for (int l = 1; l <= w.max_level; ++l) {
         if (w.level_grid[l] == 0) continue;
-        k_long_merge<<<w.level_grid[l], LR_THREADS, msmem, s>>>(w.rows_list, w.n_rows, w.level_lo[l], l, w.p, w.unit_off,
-                                                               w.prod_off, w.col[(l - 1) & 1], w.val[(l - 1) & 1],
-                                                               w.col[l & 1], w.val[l & 1]);
-        ++kernels;
+        const unsigned grid = std::min<unsigned>(w.level_grid[l], (unsigned)merge_ctas);
+        k_long_partition<<<(w.level_grid[l] + 255) / 256, 256, 0, s>>>(w.unit_row, w.n_rows, w.level_lo[l], l, w.p, w.unit_off,
+                                                                       w.prod_off, w.col[(l - 1) & 1],
+                                                                       reinterpret_cast<MergeTile*>(w.tiles));
+        k_long_merge<<<grid, MG_THREADS, mgsmem, s>>>(reinterpret_cast<const MergeTile*>(w.tiles), (int64_t)w.level_grid[l],
+                                                      w.unit_off, w.n_rows, w.level_lo[l], w.col[(l - 1) & 1],
+                                                      w.val[(l - 1) & 1], w.col[l & 1], w.val[l & 1]);
+        kernels += 2;
     }
     off();
     on("long_sums", (uint32_t)w.unit_bound);
     cudaMemsetAsync(w.unit_heads, 0, (size_t)w.unit_bound * sizeof(uint32_t), s);
-    k_long_count<<<(unsigned)w.unit_bound, LR_THREADS, 0, s>>>(w.rows_list, w.n_rows, w.p, w.unit_off, w.prod_off, w.col[0],
-                                                              w.col[1], w.unit_heads);
+    k_long_count<<<(unsigned)w.unit_bound, LR_THREADS, 0, s>>>(w.rows_list, w.n_rows, w.p, w.unit_row, w.unit_off, w.prod_off,
+                                                              w.col[0], w.col[1], w.unit_heads);
     launch_scan_u32_i64(w.unit_heads, (int64_t)w.unit_bound, w.unit_hoff, w.tile_state, ctr, s);
-    k_long_reduce<<<(unsigned)w.unit_bound, LR_THREADS, 0, s>>>(w.rows_list, w.n_rows, w.p, w.unit_off, w.prod_off,
+    static PerDeviceOnce rattr;
+    if (rattr.first()) cudaFuncSetAttribute(k_long_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+    k_long_reduce<<<(unsigned)w.unit_bound, LR_THREADS, msmem, s>>>(w.rows_list, w.n_rows, w.p, w.unit_row, w.unit_off, w.prod_off,
                                                                w.col[0], w.col[1], w.val[0], w.val[1], w.unit_hoff, t_ptr,
                                                                t_col, t_val, row_nnz);
     kernels += 3;

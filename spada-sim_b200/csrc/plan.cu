@@ -305,7 +305,7 @@ k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, uint32_t lo, uint32_t
     if (f <= lo || f > hi) return;  // rows outside (lo, hi] are written by their own kernels
     const int64_t src = t_ptr[r], d0 = c_ptr[r];
     const int n = (int)(c_ptr[r + 1] - d0);
-    const int64_t o = d0 + dst.off;
+    const int64_t o = d0 + shard_offset(dst.off, dst.shard_nnz, dst.shard_idx);
     for (int j = lane; j < n; j += 32) {
         const int32_t c = t_col[src + j];
         const double v = t_val[src + j];
@@ -339,7 +339,7 @@ k_copy_rows_list(const uint32_t* __restrict__ rows_list, const int64_t* __restri
     const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
     const int64_t src = t_ptr[r], d0 = c_ptr[r];
     const int64_t n = c_ptr[r + 1] - d0;
-    const int64_t o = d0 + dst.off;
+    const int64_t o = d0 + shard_offset(dst.off, dst.shard_nnz, dst.shard_idx);
     for (int64_t j = threadIdx.x; j < n; j += 256) {
         const int32_t c = t_col[src + j];
         const double v = t_val[src + j];
@@ -362,14 +362,16 @@ void launch_copy_rows_list(const uint32_t* rows_list, uint32_t n_rows, const int
 }
 
 // row pointers of a shard, shifted by the shard's global nnz offset, into the row_ptr of every GPU
-__global__ void k_shift_row_ptr(const int64_t* __restrict__ ptr, int64_t m, int64_t off, RowPtrDst dst, int64_t row_off) {
+__global__ void k_shift_row_ptr(const int64_t* __restrict__ ptr, int64_t m, int64_t off, const int64_t* shard_nnz,
+                                int shard_idx, RowPtrDst dst, int64_t row_off) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > m) return;
-    const int64_t v = ptr[r] + off;
+    const int64_t v = ptr[r] + shard_offset(off, shard_nnz, shard_idx);
     for (int d = 0; d < dst.n; ++d) dst.ptr[d][row_off + r] = v;
 }
-void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const RowPtrDst& dst, int64_t row_off, cudaStream_t s) {
-    k_shift_row_ptr<<<(unsigned)((m + 1 + 255) / 256), 256, 0, s>>>(ptr, m, off, dst, row_off);
+void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const int64_t* shard_nnz, int shard_idx,
+                          const RowPtrDst& dst, int64_t row_off, cudaStream_t s) {
+    k_shift_row_ptr<<<(unsigned)((m + 1 + 255) / 256), 256, 0, s>>>(ptr, m, off, shard_nnz, shard_idx, dst, row_off);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -4,8 +4,10 @@ torch.distributed (NCCL over NVLink on the B200 box, gloo in the CPU tests).
   * B (and A) replicated from rank 0 with ``dist.broadcast``            -> ``broadcast_csr``
   * A row-sharded into contiguous ranges of equal intermediate-product
     count: the C ABI's ``spada_b200_plan_shards`` on rank 0, broadcast   -> ``plan_bounds``
-  * C shards all-gathered in place at their final offsets
-    (NCCL has no all-gather-v: one grouped batch of sends/receives)     -> ``allgather_csr``
+  * C gathered on every rank by the store itself: the kernel that places a shard's rows writes
+    them into every rank's C buffers over NVLink peer mappings (CUDA IPC)  -> ``PeerGather``
+  * the NCCL-only exchange kept as the baseline to compare against (and
+    for the gloo tests): padded all-gather / grouped send+recv           -> ``allgather_csr``
 
 torch is plumbing only (device memory views, streams, collectives); every SpGEMM kernel is in
 libspada_b200.so.
@@ -170,111 +172,64 @@ def allgather_csr(local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: t
     return g_ptr, g_col, g_val
 
 
-class WaveGather:
-    """All-gather of C overlapped with the computation, in waves.
+class PeerGather:
+    """Sharded product with the all-gather of C fused into the store (one process per GPU).
 
-    The rows of A are cut into ``world * waves`` contiguous shards of equal product count; shard
-    ``j * world + r`` belongs to rank ``r`` and wave ``j``, so wave j of all ranks together is one
-    contiguous block of C's rows.  As soon as a rank has computed its shard of wave j it starts the
-    exchange of that wave (asynchronous NCCL work on the communicator's own stream) and goes on
-    computing wave j+1: the 3 GB of C cross NVLink while the SMs are busy, instead of after them.
-    Final offsets of a wave are known when the wave starts (everything before it is already counted),
-    so two ranks (and gloo) receive straight into place; more than two ranks on GPUs use NCCL's
-    all-gather on buffers padded to the wave's largest shard and compact them afterwards
-    (see ``allgather_csr`` for the measurements behind that choice).
-
-    ``capacity`` bounds nnz(C) (the intermediate-product count does); the arrays are allocated once and
-    reused across steps.
+    Every rank owns a full-size set of C buffers (``spada_b200_cbuf``) sized by an upper bound of nnz(C) (the
+    intermediate-product count); their CUDA IPC handles are exchanged ONCE through the process group, so every rank
+    holds peer mappings of all of them.  One product = ``shard_begin`` on this rank's rows (first pass into scratch
+    rows, local row_ptr, nnz left on the device) -> ``all_gather_into_tensor`` of the per-rank nnz (8 bytes each,
+    NCCL, no host read-back) -> ``shard_finish``: the kernel that places the scratch rows reads the shard's global
+    offset from that device array and stores every row into ALL ranks' buffers -- its own through HBM, the peers'
+    over NVLink -- so the exchange overlaps the placement instead of following it.  A one-element all-reduce
+    afterwards is the barrier that makes every rank's C complete before anybody reads it.
     """
 
-    def __init__(self, total_rows: int, capacity: int, device, group=None):
-        self.group = group
+    def __init__(self, engine, rows: int, cols: int, capacity: int, device, group=None):
+        self.engine, self.group, self.dev = engine, group, device
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.dev = device
-        self.g_ptr = torch.empty(total_rows + 1, dtype=torch.int64, device=device)
-        self.g_col = torch.empty(max(capacity, 1), dtype=torch.int32, device=device)
-        self.g_val = torch.empty(max(capacity, 1), dtype=torch.float64, device=device)
-        self.reset()
+        self.rows, self.cols, self.capacity = rows, cols, capacity
+        self.own = engine.cbuf_create(rows, cols, capacity)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.own.export(), group=group)
+        self.peers = [engine.cbuf_import(handles[r], rows, cols, capacity) for r in range(self.world) if r != self.rank]
+        self.bufs = [self.own] + self.peers           # own first: spada_b200_shard_finish's convention
+        self.shard_nnz = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self.local_nnz = torch.zeros(1, dtype=torch.int64, device=device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
 
-    def reset(self):
-        self.g_ptr[:1] = 0
-        self.rows_done = 0
-        self.nnz_done = 0
-        self.pending = []     # (works, compaction closures, keepalive)
+    def step(self, da, db, row_begin: int, row_end: int, compute_only: bool = False) -> dict:
+        """One sharded product; returns the engine's stats of this rank's shard.  On return (after the barrier
+        collective, stream-ordered) every rank's buffers hold the whole C."""
+        shard = self.engine.shard_begin(da, db, row_begin, row_end, d_nnz_local=self.local_nnz.data_ptr())
+        dist.all_gather_into_tensor(self.shard_nnz, self.local_nnz, group=self.group)
+        bufs = [self.own] if compute_only else self.bufs
+        st = shard.finish(bufs, 0, self.shard_nnz.data_ptr(), self.rank)
+        dist.all_reduce(self.flag, group=self.group)   # every rank's stores have landed when this completes
+        return st
 
-    def add(self, local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: torch.Tensor, keepalive=None):
-        """Starts the exchange of the next wave; (local_ptr, local_col, local_val) is this rank's shard of it
-        (row_ptr starting at 0)."""
-        world, rank, dev, group = self.world, self.rank, self.dev, self.group
-        mine = torch.tensor([local_ptr.numel() - 1, local_col.numel()], dtype=torch.int64, device=dev)
-        sizes = torch.empty(world * 2, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(sizes, mine, group=group)
-        sizes = sizes.view(world, 2).cpu()
-        rows, nnzs = sizes[:, 0].tolist(), sizes[:, 1].tolist()
-        row_off = self.rows_done + np.concatenate([[0], np.cumsum(rows)])
-        nnz_off = self.nnz_done + np.concatenate([[0], np.cumsum(nnzs)])
-        if int(nnz_off[-1]) > self.g_col.numel():
-            raise RuntimeError("WaveGather: capacity below nnz(C)")
-        g_ptr, g_col, g_val = self.g_ptr, self.g_col, self.g_val
-        r0, n0 = int(row_off[rank]), int(nnz_off[rank])
-        g_ptr[r0 + 1:r0 + 1 + rows[rank]] = local_ptr[1:] + n0
-        g_col[n0:n0 + nnzs[rank]] = local_col
-        g_val[n0:n0 + nnzs[rank]] = local_val
-        works, after = [], []
-        if world > 2 and dev.type == "cuda":
-            mx, mr = max(max(nnzs), 1), max(max(rows), 1)
-            pad_col = torch.empty((world, mx), dtype=torch.int32, device=dev)
-            pad_val = torch.empty((world, mx), dtype=torch.float64, device=dev)
-            pad_ptr = torch.empty((world, mr), dtype=torch.int64, device=dev)
-            pad_col[rank, :nnzs[rank]] = local_col
-            pad_val[rank, :nnzs[rank]] = local_val
-            pad_ptr[rank, :rows[rank]] = local_ptr[1:] + n0
-            for pad in (pad_col, pad_val, pad_ptr):
-                works.append(dist.all_gather_into_tensor(pad.view(-1), pad[rank], group=group, async_op=True))
+    def nvlink_bytes(self) -> int:
+        """Bytes this rank pushed to its peers in the last step (12 per entry of its shard + 8 per row, per peer)."""
+        nnz = int(self.local_nnz.item())
+        return (self.world - 1) * 12 * nnz
 
-            def compact(rows=rows, nnzs=nnzs, row_off=row_off, nnz_off=nnz_off, pads=(pad_ptr, pad_col, pad_val)):
-                pp, pc, pv = pads
-                for r in range(world):
-                    if r == rank:
-                        continue
-                    rs, ns = int(row_off[r]), int(nnz_off[r])
-                    g_ptr[rs + 1:rs + 1 + rows[r]] = pp[r, :rows[r]]
-                    g_col[ns:ns + nnzs[r]] = pc[r, :nnzs[r]]
-                    g_val[ns:ns + nnzs[r]] = pv[r, :nnzs[r]]
-            after.append(compact)
-        else:
-            ops = []
-            my_ptr = g_ptr[r0 + 1:r0 + 1 + rows[rank]]
-            my_col = g_col[n0:n0 + nnzs[rank]]
-            my_val = g_val[n0:n0 + nnzs[rank]]
-            for r in range(world):
-                if r == rank:
-                    continue
-                peer = dist.get_global_rank(group, r) if group else r
-                rs, ns = int(row_off[r]), int(nnz_off[r])
-                if rows[rank]:
-                    ops.append(dist.P2POp(dist.isend, my_ptr, peer, group))
-                if rows[r]:
-                    ops.append(dist.P2POp(dist.irecv, g_ptr[rs + 1:rs + 1 + rows[r]], peer, group))
-                if nnzs[rank]:
-                    ops.append(dist.P2POp(dist.isend, my_col, peer, group))
-                    ops.append(dist.P2POp(dist.isend, my_val, peer, group))
-                if nnzs[r]:
-                    ops.append(dist.P2POp(dist.irecv, g_col[ns:ns + nnzs[r]], peer, group))
-                    ops.append(dist.P2POp(dist.irecv, g_val[ns:ns + nnzs[r]], peer, group))
-            if ops:
-                works = dist.batch_isend_irecv(ops)
-        self.pending.append((works, after, keepalive))
-        self.rows_done = int(row_off[-1])
-        self.nnz_done = int(nnz_off[-1])
+    def result(self):
+        """(row_ptr, col, val) torch views of this rank's copy of the gathered C."""
+        p, c, v = self.own.device_ptrs()
+        nnz = self.own.nnz
+        return (device_view(p, self.rows + 1, torch.int64, self.dev, self.own), device_view(c, nnz, torch.int32, self.dev, self.own),
+                device_view(v, nnz, torch.float64, self.dev, self.own))
 
-    def finish(self):
-        """Waits for every wave; returns (row_ptr, col, val) of the whole C (views of the reused buffers)."""
-        for works, after, _keep in self.pending:
-            for w in works:
-                w.wait()
-            for fn in after:
-                fn()
-        self.pending = []
-        return self.g_ptr[:self.rows_done + 1], self.g_col[:self.nnz_done], self.g_val[:self.nnz_done]
+    def checksum(self):
+        """(nnz, sum of row_ptr, sum of col ids, sum of values) of this rank's gathered C, as a device tensor."""
+        rp, col, val = self.result()
+        return torch.stack([rp[-1].double(), rp.double().sum(), col.double().sum(), val.sum()])
+
+    def close(self):
+        for b in self.peers:
+            b.free()
+        self.peers = []
+        dist.barrier(group=self.group)     # nobody frees buffers a peer still has mapped
+        self.own.free()

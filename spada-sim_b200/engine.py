@@ -83,16 +83,7 @@ class Result:
     def stats(self) -> dict:
         st = _abi.Stats()
         check(lib().spada_b200_result_stats(self._h, C.byref(st)))
-        out = {k: getattr(st, k) for k in ("rows", "cols", "nnz_a", "nnz_b", "products", "nnz_c", "ms_total",
-                                            "ms_flops", "ms_symbolic", "ms_scan", "ms_numeric", "ms_h2d", "ms_d2h",
-                                            "n_launches")}
-        out["bins"] = {BIN_NAMES[i]: {"rows": st.bin_rows[i], "products": st.bin_products[i],
-                                      "window": [st.bin_window_rows[i], st.bin_window_lanes[i]]}
-                       for i in range(len(BIN_NAMES)) if st.bin_rows[i]}
-        out["launches"] = [{"name": st.launches[i].name.decode(), "ms": st.launches[i].ms,
-                            "grid": st.launches[i].grid, "rows": st.launches[i].rows,
-                            "products": st.launches[i].products} for i in range(st.n_recorded)]
-        return out
+        return _stats_dict(st)
 
     def device_ptrs(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -129,6 +120,122 @@ class Result:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+def _stats_dict(st) -> dict:
+    out = {k: getattr(st, k) for k in ("rows", "cols", "nnz_a", "nnz_b", "products", "nnz_c", "ms_total",
+                                        "ms_flops", "ms_symbolic", "ms_scan", "ms_numeric", "ms_h2d", "ms_d2h",
+                                        "n_launches")}
+    out["bins"] = {BIN_NAMES[i]: {"rows": st.bin_rows[i], "products": st.bin_products[i],
+                                  "window": [st.bin_window_rows[i], st.bin_window_lanes[i]]}
+                   for i in range(len(BIN_NAMES)) if st.bin_rows[i]}
+    out["launches"] = [{"name": st.launches[i].name.decode(), "ms": st.launches[i].ms,
+                        "grid": st.launches[i].grid, "rows": st.launches[i].rows,
+                        "products": st.launches[i].products} for i in range(st.n_recorded)]
+    return out
+
+
+class CBuf:
+    """Full-size C buffers on one GPU (spada_b200_cbuf_t): the destination of sharded products."""
+
+    def __init__(self, engine: "Engine", handle, rows, cols, capacity, imported=False):
+        self.engine, self._h = engine, handle
+        self.shape, self.capacity, self.imported = (rows, cols), capacity, imported
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(3 * _abi.IPC_HANDLE_BYTES)
+        check(lib().spada_b200_cbuf_export(self._h, buf))
+        return buf.raw
+
+    def device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().spada_b200_cbuf_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    @property
+    def nnz(self) -> int:
+        n = C.c_uint64()
+        check(lib().spada_b200_cbuf_nnz(self._h, C.byref(n)))
+        return n.value
+
+    def to_host(self):
+        n = self.nnz
+        ip = np.empty(self.shape[0] + 1, dtype=np.int64)
+        ix = np.empty(n, dtype=np.int32)
+        dx = np.empty(n, dtype=np.float64)
+        check(lib().spada_b200_cbuf_copy32(self._h, _ptr(ip, C.c_int64), _ptr(ix, C.c_int32), _ptr(dx, C.c_double)))
+        return ip, ix, dx
+
+    def free(self):
+        if self._h is not None:
+            if self.engine._h is not None:
+                lib().spada_b200_cbuf_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Shard:
+    """A row shard's product between its two halves (spada_b200_shard_t)."""
+
+    def __init__(self, engine: "Engine", handle, nnz_local):
+        self.engine, self._h, self.nnz_local = engine, handle, nnz_local
+
+    def finish(self, bufs, nnz_offset: int = 0, d_shard_nnz: int = 0, shard_index: int = 0) -> dict:
+        """Stores the shard's rows into every buffer of ``bufs`` (own first, then the peers') at its global offset."""
+        arr = (C.c_void_p * len(bufs))(*[b._h for b in bufs])
+        st = _abi.Stats()
+        h, self._h = self._h, None
+        check(lib().spada_b200_shard_finish(h, arr, len(bufs), nnz_offset, d_shard_nnz or None, shard_index, C.byref(st)))
+        return _stats_dict(st)
+
+    def __del__(self):
+        try:
+            if self._h is not None and self.engine._h is not None:
+                lib().spada_b200_shard_abort(self._h)
+            self._h = None
+        except Exception:
+            pass
+
+
+class Group:
+    """All GPUs of this process behind one call (spada_b200_group_t): what the single-process CLI drives."""
+
+    def __init__(self, n_gpus: int, accelerator: str = "spada", lane_num: int = 8, block_shape=(1, 10000000),
+                 validate: bool = True):
+        opts = _abi.Opts()
+        opts.device = 0
+        opts.accelerator = _abi.ACCELERATORS[accelerator.lower()]
+        opts.lane_num = lane_num
+        opts.block_shape[0] = min(int(block_shape[0]), 0xffffffff)
+        opts.block_shape[1] = min(int(block_shape[1]), 0xffffffff)
+        opts.flags = _abi.FLAG_VALIDATE if validate else 0
+        h = C.c_void_p()
+        check(lib().spada_b200_group_create(C.byref(opts), n_gpus, C.byref(h)))
+        self._h = h
+        self.n_gpus = n_gpus
+
+    def spgemm(self, a: sp.csr_matrix, b: sp.csr_matrix) -> "Result":
+        out = C.c_void_p()
+        va, ka = Engine._view32(a)
+        vb, kb = (va, ka) if b is a else Engine._view32(b)
+        check(lib().spada_b200_group_spgemm32(self._h, C.byref(va), C.byref(vb), C.byref(out)))
+        return Result(self, out)
+
+    def close(self):
+        if self._h is not None:
+            lib().spada_b200_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 
@@ -233,6 +340,27 @@ class Engine:
             vb, kb = (va, ka) if b is a else self._view32(b)
             check(lib().spada_b200_spgemm32(self._h, C.byref(va), C.byref(vb), C.byref(out)))
         return Result(self, out)
+
+    # -- sharded runs --
+    def cbuf_create(self, rows: int, cols: int, capacity_nnz: int) -> CBuf:
+        out = C.c_void_p()
+        check(lib().spada_b200_cbuf_create(self._h, rows, cols, capacity_nnz, C.byref(out)))
+        return CBuf(self, out, rows, cols, capacity_nnz)
+
+    def cbuf_import(self, handles: bytes, rows: int, cols: int, capacity_nnz: int) -> CBuf:
+        out = C.c_void_p()
+        buf = C.create_string_buffer(handles, len(handles))
+        check(lib().spada_b200_cbuf_import(self._h, buf, rows, cols, capacity_nnz, C.byref(out)))
+        return CBuf(self, out, rows, cols, capacity_nnz, imported=True)
+
+    def shard_begin(self, a: DeviceCsr, b: DeviceCsr, row_begin: int, row_end: int, d_nnz_local: int = 0,
+                    host_nnz: bool = False) -> Shard:
+        """First half of a shard's product; the shard's nnz lands at device address ``d_nnz_local``."""
+        out = C.c_void_p()
+        n = C.c_uint64()
+        check(lib().spada_b200_shard_begin(self._h, a._h, b._h, row_begin, row_end, d_nnz_local or None,
+                                           C.byref(n) if host_nnz else None, C.byref(out)))
+        return Shard(self, out, n.value if host_nnz else None)
 
     def flops(self, a: DeviceCsr, b: DeviceCsr, per_row: bool = False):
         total = C.c_uint64()

@@ -35,19 +35,6 @@ def _worker(rank, world, port, q, shape=(301, 200, 150)):
         gp, gj, gx = D.allgather_csr(torch.from_numpy(cp), torch.from_numpy(cj), torch.from_numpy(cx))
         fp, fj, fx = oracle.spgemm(A, B)
         ok = (np.array_equal(gp.numpy(), fp) and np.array_equal(gj.numpy(), fj) and np.array_equal(gx.numpy(), fx))
-        # the same C assembled in waves (exchange of wave j overlaps the computation of wave j+1), twice over the
-        # same buffers like the steps of bench.py
-        waves = 3
-        wb = D.balanced_bounds(oracle.flops(A, B) + 1, world * waves)
-        wg = D.WaveGather(A.shape[0], int(oracle.flops(A, B).sum()), torch.device("cpu"))
-        for _ in range(2):
-            wg.reset()
-            for j in range(waves):
-                s0, s1 = int(wb[j * world + rank]), int(wb[j * world + rank + 1])
-                wp, wj, wx = oracle.spgemm(A[s0:s1], B)
-                wg.add(torch.from_numpy(wp), torch.from_numpy(wj), torch.from_numpy(wx))
-            hp, hj, hx = wg.finish()
-            ok = ok and (np.array_equal(hp.numpy(), fp) and np.array_equal(hj.numpy(), fj) and np.array_equal(hx.numpy(), fx))
         q.put((rank, ok, (lo, hi)))
     finally:
         dist.destroy_process_group()

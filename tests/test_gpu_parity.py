@@ -63,12 +63,13 @@ def test_each_bin(engine, oracle, ka, lb, expect_bin):
     assert st["bins"][expect_bin]["rows"] == m
 
 
-@pytest.mark.parametrize("n_cols", [1 << 10, 1 << 21, (1 << 28) + 5])
+@pytest.mark.parametrize("n_cols", [1 << 10, 1 << 20, 1 << 21, 1 << 22, 1 << 23, (1 << 28) + 5])
 def test_key_width_paths(engine, oracle, n_cols):
-    # 32-bit packed (column, arrival) keys when they fit, 64-bit keys otherwise
-    for ka, lb in [(4, 6), (16, 16), (40, 50), (80, 90)]:
-        a = random_csr(130, 300, row_nnz=ka, seed=3)
-        b = random_csr(300, n_cols, row_nnz=lb, seed=4)
+    # 32-bit packed (column, arrival) keys when they fit; one bit short: two 32-bit groups merged in shared memory;
+    # 64-bit keys otherwise
+    for ka, lb in [(4, 6), (16, 16), (30, 30), (40, 50), (60, 60), (80, 90), (200, 120)]:
+        a = random_csr(130, 300, row_nnz=ka, seed=3, values="signed")
+        b = random_csr(300, n_cols, row_nnz=lb, seed=4, values="signed")
         run(engine, oracle, a, b)
 
 
