@@ -581,12 +581,21 @@ def e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, steps, torch
     d2h = 8 * (m + 1) + 12 * nnz_c
 
     def e2e_step():
-        out = C.c_void_p()
-        abi.check(lib.spada_b200_spgemm32(eng._h, C.byref(va), C.byref(vb), C.byref(out)))
-        abi.check(lib.spada_b200_result_copy32(out, o_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
-                                               o_col.ctypes.data_as(C.POINTER(C.c_int32)),
-                                               o_val.ctypes.data_as(C.POINTER(C.c_double))))
-        lib.spada_b200_result_free(out)
+        # upload (H2D, validation) -> row panels computed while the previous panel's D2H runs -> operands freed
+        pa, pb = C.c_void_p(), C.c_void_p()
+        abi.check(lib.spada_b200_upload32(eng._h, C.byref(va), C.byref(pa)))
+        if vb is va:
+            pb = pa
+        else:
+            abi.check(lib.spada_b200_upload32(eng._h, C.byref(vb), C.byref(pb)))
+        try:
+            abi.check(lib.spada_b200_spgemm_to_host(eng._h, pa, pb, 0, o_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    o_col.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    o_val.ctypes.data_as(C.POINTER(C.c_double)), len(o_col), None))
+        finally:
+            if pb is not pa:
+                lib.spada_b200_csr_free(pb)
+            lib.spada_b200_csr_free(pa)
     e2e_step()
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -599,7 +608,8 @@ def e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, steps, torch
     assert int(o_ptr[-1]) == nnz_c
     out = {"value": 2.0 * products / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": steps,
-           "note": "spada_b200_spgemm32 + result_copy32: pinned host CSR in, validation, compute, whole C to pinned host"}
+           "note": "spada_b200_upload32 x2 + spada_b200_spgemm_to_host: pinned host CSR in, validation, C computed in row "
+                   "panels whose D2H copies overlap the next panel's kernels, whole C in pinned host arrays"}
     for p in keep:
         lib.spada_b200_host_free(p)
     return out

@@ -247,6 +247,30 @@ SPADA_B200_API int spada_b200_group_spgemm32(spada_b200_group_t *g, const spada_
                               spada_b200_result_t **out);
 SPADA_B200_API void spada_b200_group_destroy(spada_b200_group_t *g);
 
+/* ---- row-panel streaming: the step after the path (main.rs:113-116 prints ten rows of C and drops the rest) --------
+ * C is computed in panels of consecutive rows (at most panel_products intermediate products each; 0 = engine's choice);
+ * every finished panel is copied to pinned host memory while the next one is computed and handed to `sink` in row
+ * order.  The arrays a sink receives are valid only during the call: indptr has row_end - row_begin + 1 entries holding
+ * GLOBAL offsets (indptr[0] == nnz_begin), indices / data hold the panel's entries.  A non-zero return aborts the run.
+ * C never has to fit in HBM, nor to be kept at all (a checksum sink stores nothing). */
+typedef int (*spada_b200_panel_sink)(void *user, uint64_t row_begin, uint64_t row_end, uint64_t nnz_begin,
+                                     const int64_t *indptr, const int32_t *indices, const double *data);
+typedef struct spada_b200_stream_stats {
+    uint64_t panels, products, nnz_c, max_panel_products;
+    float ms_total; /* first panel's first kernel -> last panel handed over */
+} spada_b200_stream_stats;
+SPADA_B200_API int spada_b200_spgemm_stream(spada_b200_t *h, const spada_b200_csr_t *a, const spada_b200_csr_t *b,
+                             uint64_t panel_products, spada_b200_panel_sink sink, void *user,
+                             spada_b200_stream_stats *stats_or_null);
+
+/* The same panels copied straight into caller-allocated host arrays at their global offsets (pin them for full PCIe
+ * speed): int64 indptr [A.rows + 1], int32 indices / float64 data [capacity_nnz >= nnz(C), e.g. the product count of
+ * spada_b200_flops].  What the Rust wrapper calls when it wants the whole of C on the host: the D2H copy of a panel
+ * runs beside the computation of the next one. */
+SPADA_B200_API int spada_b200_spgemm_to_host(spada_b200_t *h, const spada_b200_csr_t *a, const spada_b200_csr_t *b,
+                              uint64_t panel_products, int64_t *indptr, int32_t *indices, double *data,
+                              uint64_t capacity_nnz, spada_b200_stream_stats *stats_or_null);
+
 /* ---- results: replaces get_exec_result (simulator.rs:1034-1062) ----------------------- */
 SPADA_B200_API int spada_b200_result_shape(const spada_b200_result_t *r, uint64_t *rows, uint64_t *cols,
                             uint64_t *nnz);

@@ -59,6 +59,14 @@ class Stats(C.Structure):
                 ("launches", Launch * MAX_LAUNCHES)]
 
 
+class StreamStats(C.Structure):
+    _fields_ = [("panels", C.c_uint64), ("products", C.c_uint64), ("nnz_c", C.c_uint64), ("max_panel_products", C.c_uint64),
+                ("ms_total", C.c_float)]
+
+
+PANEL_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int64),
+                         C.POINTER(C.c_int32), C.POINTER(C.c_double))
+
 # every symbol include/spada_b200.h declares: name -> (restype, argtypes)
 _vp, _vpp = C.c_void_p, C.POINTER(C.c_void_p)
 _u64p = C.POINTER(C.c_uint64)
@@ -101,6 +109,9 @@ SYMBOLS = {
     "spada_b200_group_spgemm": (C.c_int, [_vp, C.POINTER(CsrView), C.POINTER(CsrView), _vpp]),
     "spada_b200_group_spgemm32": (C.c_int, [_vp, C.POINTER(CsrView32), C.POINTER(CsrView32), _vpp]),
     "spada_b200_group_destroy": (None, [_vp]),
+    "spada_b200_spgemm_stream": (C.c_int, [_vp, _vp, _vp, C.c_uint64, PANEL_SINK, _vp, C.POINTER(StreamStats)]),
+    "spada_b200_spgemm_to_host": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_double), C.c_uint64, C.POINTER(StreamStats)]),
     "spada_b200_result_shape": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "spada_b200_result_copy": (C.c_int, [_vp, _u64p, _u64p, C.POINTER(C.c_double)]),
     "spada_b200_result_copy32": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),

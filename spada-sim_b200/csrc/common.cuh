@@ -65,6 +65,8 @@ struct PlanCounters {
     uint32_t invalid_rows;   // validation failures
     uint32_t scan_ticket;    // dynamic tile id of the look-back scan
     uint32_t max_flops;      // largest per-row product count (saturates at 2^32-1)
+    uint32_t tiny_fit;       // rows of bin 1 with at most 8 A entries: they fit an 8-lane group (window [4, 8])
+    uint32_t pad;
 };
 
 // ---- device-side CSR view ------------------------------------------------------------
@@ -419,7 +421,8 @@ void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const int6
                           const RowPtrDst& dst, int64_t row_off, cudaStream_t s);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
-void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
+// tiny_quad: rows of bin 1 run four to a warp (window [4, 8]) instead of one per warp ([1, 32])
+void launch_fused_light(int max_bin, bool tiny_quad, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
                         const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,
                         uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s);
 

@@ -767,16 +767,47 @@ extern "C" int spada_b200_plan_shards(spada_b200_t* h, const spada_b200_csr_t* a
     return 0;
 }
 
-// ---- window report --------------------------------------------------------------------------
-// The shape [R, L/R] every bin runs with (scheduler.rs:729-753: R rows share the L lanes of a window): R = rows
-// that share one cooperative group (a warp or a CTA), lanes = lanes that cooperate on one row.
-static void window_report(const spada_b200* h, const PlanCounters& pc, spada_b200_stats& st) {
-    (void)h;
+// ---- window choice ----------------------------------------------------------------------------
+// Spada's window [R, L/R] (scheduler.rs:729-753, rowwise_perf_adjust.rs:121-252): R rows share the L lanes of a
+// window, every row gets L/R of them.  On the GPU the bin of a row (its intermediate-product count) fixes the lanes that
+// cooperate on it; what is still chosen per operand -- and per accelerator argument, main.rs:67-72 -- is how many rows
+// share one cooperative group:
+//   bin 1 (<= 32 products)   [4, 8]  four rows per warp, 8 lanes x 4 keys each, or [1, 32] one row per warp.  The
+//                            4-row window only holds rows with at most 8 A entries (one per lane of the group).
+//       Spada (adaptive)     [4, 8] when at least half of the bin's rows fit it (counted by stage 1), else [1, 32]
+//       Ip  (row-wise)       [1, L']: one row per group, L' = 32 lanes
+//       Op  (column-wise)    [L'/8, 8]: rows share the lanes
+//       MultiRow             [R, L'/R] with R = block_shape[0]: R >= 4 -> [4, 8], else [1, 32]; lane_num > 8 widens
+//                            the per-row share to a full warp ([1, 32])
+//   bins 2..5                one warp per row; rows per tile 4 (scratch pass) or 8 / 4 (single pass, look-back tile)
+//   bins 6..8, long rows     one CTA (256 lanes) per row / per chunk of 4096 products ("K-tiling": chunks x [1, 256])
+struct WindowChoice {
+    bool tiny_quad;
+};
+static WindowChoice window_choice(const spada_b200* h, const PlanCounters& pc) {
+    WindowChoice w{};
+    switch (h->opts.accelerator) {
+        case SPADA_B200_ACC_IP: w.tiny_quad = false; break;
+        case SPADA_B200_ACC_OP: w.tiny_quad = h->opts.lane_num <= 8; break;
+        case SPADA_B200_ACC_MULTIROW: w.tiny_quad = h->opts.block_shape[0] >= 4 && h->opts.lane_num <= 8; break;
+        default: w.tiny_quad = (uint64_t)pc.tiny_fit * 2 >= pc.bin_rows[1]; break;
+    }
+    return w;
+}
+static void window_report(const WindowChoice& w, bool fused, const PlanCounters& pc, spada_b200_stats& st) {
     for (int bnum = 0; bnum < NUM_BINS; ++bnum) {
         uint32_t R = 0, lanes = 0;
-        if (bnum == 1) { R = 4; lanes = 8; }
-        else if (bnum >= 2 && bnum <= 5) { R = 1; lanes = 32; }
-        else if (bnum >= 6) { R = 1; lanes = 256; }
+        if (bnum == 1) {
+            const bool quad = fused && w.tiny_quad;   // the scratch pass runs bin 1 one row per warp
+            R = quad ? 4 : 1;
+            lanes = quad ? 8 : 32;
+        } else if (bnum >= 2 && bnum <= 5) {
+            R = 1;
+            lanes = 32;
+        } else if (bnum >= 6) {
+            R = 1;
+            lanes = 256;
+        }
         st.bin_window_rows[bnum] = pc.bin_rows[bnum] ? R : 0;
         st.bin_window_lanes[bnum] = pc.bin_rows[bnum] ? lanes : 0;
     }
@@ -820,6 +851,7 @@ struct spada_b200_shard {
     PlanCounters pc{};
     BinTable tbl{};
     bool identity = false;
+    WindowChoice window{};
     uint32_t scratch_lo = 0;      // rows with more than this many products go through the scratch CSR
     uint64_t scratch_products = 0;
     uint32_t n_long = 0;
@@ -1085,7 +1117,6 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
         if (pc.bin_rows[bnum] == (uint64_t)m && bnum >= 1 && bnum < BIN_LONG0) S->identity = true;
     }
     tbl.offset[NUM_BINS] = off;
-    window_report(h, pc, st);
     if (!S->identity && off > 0) {
         S->begin_rec("bin_scatter", 1, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);
         launch_bin_scatter(S->d_flops, m, tbl, S->d_perm, h->d_ctr, s);
@@ -1101,6 +1132,8 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
                  (double)pc.total_products * 12.0 <= 0.45 * (double)h->dev_total_mem;
     if (fused && !(h->opts.flags & SPADA_B200_FLAG_SINGLE_PASS) && dominant * 10 < non_empty * 8) fused = false;
     S->fused = fused;
+    S->window = window_choice(h, pc);
+    window_report(S->window, fused, pc, st);
     S->scratch_lo = fused ? 512u : 0u;
     for (int bnum = fused ? 6 : 1; bnum < NUM_BINS; ++bnum) S->scratch_products += pc.bin_products[bnum];
     S->scratch = S->scratch_products > 0;
@@ -1301,7 +1334,7 @@ int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_p
         uint64_t light_products = 0;
         for (int bnum = 1; bnum <= 5; ++bnum) light_products += pc.bin_products[bnum];
         S->begin_rec(name, 3, (uint32_t)((m + 7) / 8), S->light_rows, light_products);
-        launch_fused_light(S->max_light_bin, S->A, S->B, S->row_begin, m, S->d_flops, S->d_nnz, R->ptr, R->col, R->val,
+        launch_fused_light(S->max_light_bin, S->window.tiny_quad, S->A, S->B, S->row_begin, m, S->d_flops, S->d_nnz, R->ptr, R->col, R->val,
                            S->d_tiles, h->d_ctr, s);
         CUT(cudaGetLastError());
         S->kernels += 1;
@@ -1554,6 +1587,185 @@ extern "C" int spada_b200_shard_finish(spada_b200_shard_t* S, spada_b200_cbuf_t*
 }
 
 extern "C" void spada_b200_shard_abort(spada_b200_shard_t* S) { shard_free(S); }
+
+// ---- row-panel streaming (the step after main.rs:113-116, which prints ten rows and drops the rest) ----
+// C is produced in panels of consecutive rows.  Every finished panel is copied to pinned host memory on a copy stream
+// while the next panel is computed, and handed to the caller's sink: the D2H of C (the bulk of an end-to-end run: 12
+// bytes per output entry over PCIe) overlaps the computation, and C never has to fit in HBM -- or be kept at all.
+namespace {
+struct PanelBuf {
+    int64_t* ptr = nullptr;   // pinned
+    int32_t* col = nullptr;
+    double* val = nullptr;
+    cudaEvent_t done = nullptr;
+    spada_b200_result* R = nullptr;
+    uint64_t row_begin = 0, row_end = 0, nnz_begin = 0;
+};
+}  // namespace
+
+namespace {
+// dst_*: nullable.  With destination arrays the panels are copied straight into them at their global offsets (no
+// staging, no sink); otherwise into two pinned staging buffers that take turns and are handed to the sink.
+int stream_panels(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b, uint64_t panel_products,
+                  spada_b200_panel_sink sink, void* user, int64_t* dst_ptr, int32_t* dst_col, double* dst_val,
+                  uint64_t dst_capacity, spada_b200_stream_stats* stats) {
+    if (a->d.cols != b->d.rows)
+        return fail(SPADA_B200_DIM_MISMATCH, "A is %lld x %lld but B has %lld rows", (long long)a->d.rows,
+                    (long long)a->d.cols, (long long)b->d.rows);
+    DeviceGuard g(h->device);
+    const bool direct = dst_ptr != nullptr;
+    const uint64_t m = (uint64_t)a->d.rows;
+    std::vector<uint64_t> f((size_t)m);
+    uint64_t total = 0;
+    int rc = spada_b200_flops(h, a, b, &total, f.data());
+    if (rc) return rc;
+    // panels: consecutive rows up to panel_products intermediate products each (a row heavier than that is a panel of
+    // its own).  Default: what keeps scratch rows + C + staging of a panel within a quarter of the device, at least
+    // eight panels so that the copies have something to overlap with.
+    if (panel_products == 0) {
+        const uint64_t by_mem = (uint64_t)(0.25 * (double)h->dev_total_mem / 36.0);
+        panel_products = std::max<uint64_t>(1u << 20, std::min<uint64_t>(by_mem, total / 8 + 1));
+    }
+    std::vector<uint64_t> bounds{0};
+    uint64_t acc = 0, max_panel = 0, max_rows = 0;
+    for (uint64_t r = 0; r < m; ++r) {
+        if (acc && acc + f[(size_t)r] > panel_products) {
+            max_panel = std::max(max_panel, acc);
+            max_rows = std::max(max_rows, r - bounds.back());
+            bounds.push_back(r);
+            acc = 0;
+        }
+        acc += f[(size_t)r];
+    }
+    max_panel = std::max(max_panel, acc);
+    max_rows = std::max(max_rows, m - bounds.back());
+    bounds.push_back(m);
+    f.clear();
+    f.shrink_to_fit();
+    const size_t n_panels = bounds.size() - 1;
+    cudaStream_t cs = nullptr;
+    PanelBuf buf[2];
+    float ms_total = 0.f;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        for (auto& B : buf) {
+            if (B.done) cudaEventSynchronize(B.done);
+            if (B.R) spada_b200_result_free(B.R);
+            if (!direct) {
+                if (B.ptr) cudaFreeHost(B.ptr);
+                if (B.col) cudaFreeHost(B.col);
+                if (B.val) cudaFreeHost(B.val);
+            }
+            if (B.done) cudaEventDestroy(B.done);
+        }
+        if (cs) cudaStreamDestroy(cs);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        cudaGetLastError();
+    };
+    auto body = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        for (auto& B : buf) {
+            if (!direct) {
+                CU(cudaMallocHost((void**)&B.ptr, (size_t)(max_rows + 1) * sizeof(int64_t)));
+                CU(cudaMallocHost((void**)&B.col, (size_t)std::max<uint64_t>(max_panel, 1) * sizeof(int32_t)));
+                CU(cudaMallocHost((void**)&B.val, (size_t)std::max<uint64_t>(max_panel, 1) * sizeof(double)));
+            }
+            CU(cudaEventCreateWithFlags(&B.done, cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(e0, h->stream));
+        uint64_t nnz_done = 0;
+        auto drain = [&](PanelBuf& B) -> int {   // waits for the panel's copy; staging mode: hands it to the sink
+            if (!B.R) return 0;
+            CU(cudaEventSynchronize(B.done));
+            int src = 0;
+            if (!direct) {
+                const uint64_t rows = B.row_end - B.row_begin;
+                for (uint64_t i = 0; i <= rows; ++i) B.ptr[i] += (int64_t)B.nnz_begin;   // global offsets
+                src = sink(user, B.row_begin, B.row_end, B.nnz_begin, B.ptr, B.col, B.val);
+            }
+            spada_b200_result_free(B.R);
+            B.R = nullptr;
+            if (src) return fail(SPADA_B200_INVALID_ARG, "the panel sink returned %d for rows [%llu, %llu)", src,
+                                 (unsigned long long)B.row_begin, (unsigned long long)B.row_end);
+            return 0;
+        };
+        for (size_t p = 0; p < n_panels; ++p) {
+            PanelBuf& B = buf[p & 1];
+            int rc2 = drain(B);    // the buffer's previous panel (p - 2): its copy ran beside the computation of p - 1
+            if (rc2) return rc2;
+            spada_b200_result* R = nullptr;
+            if ((rc2 = spada_b200_spgemm_dev(h, a, b, bounds[p], bounds[p + 1], &R))) return rc2;   // synchronous
+            B.R = R;
+            B.row_begin = bounds[p];
+            B.row_end = bounds[p + 1];
+            B.nnz_begin = nnz_done;
+            nnz_done += R->nnz;
+            // the copy of panel p runs on the copy stream while panel p + 1 is computed
+            int64_t* hp = B.ptr;
+            int32_t* hc = B.col;
+            double* hv = B.val;
+            size_t n_ptr = (size_t)R->rows + 1;
+            if (direct) {
+                if (nnz_done > dst_capacity)
+                    return fail(SPADA_B200_INVALID_ARG, "C has more than the %llu entries the destination arrays hold",
+                                (unsigned long long)dst_capacity);
+                // global offsets on the device, then every array straight to its place (row 0's pointer comes with panel 0)
+                RowPtrDst self{};
+                self.ptr[0] = R->ptr;
+                self.n = 1;
+                launch_shift_row_ptr(R->ptr, (int64_t)R->rows, (int64_t)B.nnz_begin, nullptr, 0, self, 0, h->stream);
+                CU(cudaGetLastError());
+                CU(cudaStreamSynchronize(h->stream));
+                hp = dst_ptr + B.row_begin;
+                hc = dst_col + B.nnz_begin;
+                hv = dst_val + B.nnz_begin;
+            }
+            CU(cudaMemcpyAsync(hp, R->ptr, n_ptr * sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
+            if (R->nnz) {
+                CU(cudaMemcpyAsync(hc, R->col, (size_t)R->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+                CU(cudaMemcpyAsync(hv, R->val, (size_t)R->nnz * sizeof(double), cudaMemcpyDeviceToHost, cs));
+            }
+            CU(cudaEventRecord(B.done, cs));
+        }
+        for (size_t q = 0; q < 2; ++q) {
+            int rc2 = drain(buf[(n_panels + q) & 1]);
+            if (rc2) return rc2;
+        }
+        if (direct && m == 0) dst_ptr[0] = 0;
+        CU(cudaEventRecord(e1, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        cudaEventElapsedTime(&ms_total, e0, e1);
+        if (stats) {
+            stats->panels = n_panels;
+            stats->products = total;
+            stats->nnz_c = nnz_done;
+            stats->max_panel_products = max_panel;
+            stats->ms_total = ms_total;
+        }
+        return 0;
+    };
+    rc = body();
+    cleanup();
+    return rc;
+}
+}  // namespace
+
+extern "C" int spada_b200_spgemm_stream(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
+                                        uint64_t panel_products, spada_b200_panel_sink sink, void* user,
+                                        spada_b200_stream_stats* stats) {
+    if (!h || !a || !b || !sink) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    return stream_panels(h, a, b, panel_products, sink, user, nullptr, nullptr, nullptr, 0, stats);
+}
+
+extern "C" int spada_b200_spgemm_to_host(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b,
+                                         uint64_t panel_products, int64_t* indptr, int32_t* indices, double* data,
+                                         uint64_t capacity_nnz, spada_b200_stream_stats* stats) {
+    if (!h || !a || !b || !indptr || (capacity_nnz && (!indices || !data))) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    return stream_panels(h, a, b, panel_products, nullptr, nullptr, indptr, indices, data, capacity_nnz, stats);
+}
 
 // ---- all GPUs of one process (what the spada-sim CLI, a single process, drives: SURVEY.md 8b) -----------------------
 // One engine handle per device, peer access between every pair, one host thread per device for the two halves.

@@ -613,7 +613,7 @@ static void fused_dispatch(int max_bin, const DevCsr& a, const DevCsr& b, int64_
 }
 
 // max_bin: the largest warp-per-row bin (1..5) that holds rows; it sizes the shared memory of a tile.
-void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
+void launch_fused_light(int max_bin, bool tiny_quad, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
                         const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,
                         uint64_t* tile_state, PlanCounters* ctr, cudaStream_t s) {
     if (m <= 0) return;
@@ -624,11 +624,7 @@ void launch_fused_light(int max_bin, const DevCsr& a, const DevCsr& b, int64_t r
         size_t tiles = (size_t)((m + TINY_TILE - 1) / TINY_TILE);
         cudaMemsetAsync(tile_state, 0, tiles * sizeof(uint64_t), s);
         cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s);
-        static int quad = -1;   // SPADA_B200_TINY=warp keeps the one-row-per-warp kernel (A/B measurements)
-        if (quad < 0) {
-            const char* e = getenv("SPADA_B200_TINY");
-            quad = (e && !strcmp(e, "warp")) ? 0 : 1;
-        }
+        const bool quad = tiny_quad;   // the window of bin 1: [4, 8] or [1, 32] (engine.cu: window_choice)
         const bool narrow = (uint64_t)b.cols < (1ull << 27);
         if (quad) {
             if (narrow)

@@ -468,7 +468,12 @@ k_long_reduce(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t
     __shared__ int s_open_rank;       // output slot of the run that leaves the tile, -1: none
     __shared__ double s_open_sum;
     __shared__ int s_end;
-    if (!find_unit(blockIdx.x, unit_row, unit_off, prod_off, p, rows_list, n, &info)) return;
+    // rows are listed by ascending product count: the tiles are taken from the far end, so that the longest runs
+    // (strictly sequential sums, e.g. the diagonal of A x A^T) start first and the short tiles fill in beside them
+    const int64_t n_units = unit_off[n];
+    const int64_t unit = n_units - 1 - (int64_t)blockIdx.x;
+    if (unit < 0) return;
+    find_unit(unit, unit_row, unit_off, prod_off, p, rows_list, n, &info);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const bool odd = long_levels(info.P) & 1;
     const int32_t* col = (odd ? col1 : col0) + info.base;
@@ -477,7 +482,7 @@ k_long_reduce(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t
     const uint32_t o0 = info.t << LONG_UNIT_LOG;
     const int cnt = (int)(P - o0 < (uint32_t)LONG_UNIT ? P - o0 : (uint32_t)LONG_UNIT);
     const int64_t row_h0 = unit_hoff[unit_off[info.i]];
-    const int64_t dst = t_ptr[info.row] + (unit_hoff[blockIdx.x] - row_h0);
+    const int64_t dst = t_ptr[info.row] + (unit_hoff[unit] - row_h0);
     if (info.t == 0 && threadIdx.x == 0) row_nnz[info.row] = (uint32_t)(unit_hoff[unit_off[info.i + 1]] - row_h0);
     for (int t = threadIdx.x; t < cnt; t += LR_THREADS) {
         s_col[t] = col[o0 + t];

@@ -29,15 +29,19 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
         uint32_t* __restrict__ flops, uint32_t* __restrict__ long_list, PlanCounters* ctr) {
     __shared__ uint32_t s_rows[NUM_BINS];
     __shared__ unsigned long long s_prod[NUM_BINS];
-    __shared__ uint32_t s_max;
+    __shared__ uint32_t s_max, s_fit;
     if (threadIdx.x < NUM_BINS) {
         s_rows[threadIdx.x] = 0;
         s_prod[threadIdx.x] = 0;
     }
-    if (threadIdx.x == 0) s_max = 0;
+    if (threadIdx.x == 0) {
+        s_max = 0;
+        s_fit = 0;
+    }
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * FLOPS_THREADS + threadIdx.x;
     int b = -1;   // bin of this thread's row, -1: nothing to count here
+    bool fits = false;   // a row of bin 1 with at most 8 A entries
     unsigned long long f = 0;
     if (i < m) {
         int64_t s = a.ptr[row_begin + i], e = a.ptr[row_begin + i + 1];
@@ -50,6 +54,7 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
             flops[i] = f32;
             b = bin_of(f32);
             if (f32 > ESC_MAX_PRODUCTS) atomicMax(&s_max, f32);
+            fits = b == 1 && e - s <= 8;
             if (f >> 32) {   // cannot happen below 2^32 products per row; counted directly
                 atomicAdd(&s_rows[b], 1u);
                 atomicAdd(&s_prod[b], f);
@@ -60,6 +65,8 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
     // one shared-memory update per (warp, bin): the lanes of a bin are found with match.any, their counts summed
     // with redux (16-bit halves, so 32 lanes cannot overflow) -- per-thread 64-bit shared atomics on one address
     // serialised the whole CTA when every row falls in the same bin (stencils)
+    const unsigned fm = __ballot_sync(FULL, fits);
+    if (fm && lane_id() == 0) atomicAdd(&s_fit, (uint32_t)__popc(fm));
     const unsigned grp = __match_any_sync(FULL, b);
     if (b >= 0) {
         const unsigned lo = __reduce_add_sync(grp, (unsigned)(f & 0xffffull));
@@ -76,6 +83,7 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
         atomicAdd(&ctr->total_products, s_prod[threadIdx.x]);
     }
     if (threadIdx.x == 0 && s_max) atomicMax(&ctr->max_flops, s_max);
+    if (threadIdx.x == 0 && s_fit) atomicAdd(&ctr->tiny_fit, s_fit);
 }
 
 // K1b: long A rows, one CTA of 1024 threads per row (persistent over the deferred list); four

@@ -341,6 +341,42 @@ class Engine:
             check(lib().spada_b200_spgemm32(self._h, C.byref(va), C.byref(vb), C.byref(out)))
         return Result(self, out)
 
+    # -- row-panel streaming --
+    def spgemm_stream(self, a: DeviceCsr, b: DeviceCsr, sink, panel_products: int = 0) -> dict:
+        """C in row panels; ``sink(row_begin, row_end, nnz_begin, indptr, indices, data)`` gets numpy views that are valid
+        only during the call (indptr holds global offsets).  The D2H copy of a panel overlaps the next panel's kernels."""
+        err = []
+
+        def tramp(_user, r0, r1, n0, ip, ix, dx):
+            try:
+                rows = r1 - r0
+                p = np.ctypeslib.as_array(ip, shape=(rows + 1,))
+                nnz = int(p[-1] - p[0])
+                c = np.ctypeslib.as_array(ix, shape=(max(nnz, 1),))[:nnz]
+                v = np.ctypeslib.as_array(dx, shape=(max(nnz, 1),))[:nnz]
+                sink(int(r0), int(r1), int(n0), p, c, v)
+                return 0
+            except Exception as e:   # never unwind through the C frames
+                err.append(e)
+                return 1
+        cb = _abi.PANEL_SINK(tramp)
+        st = _abi.StreamStats()
+        rc = lib().spada_b200_spgemm_stream(self._h, a._h, b._h, panel_products, cb, None, C.byref(st))
+        if err:
+            raise err[0]
+        check(rc)
+        return {k: getattr(st, k) for k in ("panels", "products", "nnz_c", "max_panel_products", "ms_total")}
+
+    def spgemm_to_host(self, a: DeviceCsr, b: DeviceCsr, indptr: np.ndarray, indices: np.ndarray, data: np.ndarray,
+                       panel_products: int = 0) -> dict:
+        """The whole C into caller-allocated host arrays (int64 / int32 / float64; pinned for full PCIe speed)."""
+        assert indptr.dtype == np.int64 and indices.dtype == np.int32 and data.dtype == np.float64
+        assert len(indptr) >= a.shape[0] + 1 and len(indices) == len(data)
+        st = _abi.StreamStats()
+        check(lib().spada_b200_spgemm_to_host(self._h, a._h, b._h, panel_products, _ptr(indptr, C.c_int64),
+                                              _ptr(indices, C.c_int32), _ptr(data, C.c_double), len(indices), C.byref(st)))
+        return {k: getattr(st, k) for k in ("panels", "products", "nnz_c", "max_panel_products", "ms_total")}
+
     # -- sharded runs --
     def cbuf_create(self, rows: int, cols: int, capacity_nnz: int) -> CBuf:
         out = C.c_void_p()

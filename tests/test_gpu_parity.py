@@ -415,3 +415,127 @@ def test_accelerator_policies_do_not_change_c(spada, oracle, acc):
         check(e.spgemm(a, b), oracle.spgemm(a, b, threads=oracle.max_threads()), True)
     finally:
         e.close()
+
+
+# ---- sharded products, row-panel streaming ------------------------------------------------------------------------
+def test_shards_into_one_buffer(engine, oracle, spada):
+    # the two halves of a sharded product on ONE GPU: three shards stored one after the other into the same full-size
+    # C buffers at their global offsets (host-known offsets and the device-side offset array) == the whole product
+    rng = np.random.default_rng(80)
+    lens = rng.choice([0, 2, 9, 40, 150, 500], size=900, p=[.1, .3, .3, .2, .07, .03])
+    a = random_csr(900, 1500, row_nnz=lens, seed=81, values="signed")
+    b = random_csr(1500, 30000, row_nnz=rng.integers(0, 60, size=1500), seed=82, values="signed")
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    da, db = engine.upload(a), engine.upload(b)
+    bounds = engine.plan_shards(da, db, 3)
+    cap = engine.flops(da, db)
+    for device_offsets in (False, True):
+        buf = engine.cbuf_create(a.shape[0], b.shape[1], cap)
+        nnz, off = [], 0
+        arr = None
+        if device_offsets:
+            import torch
+            arr = torch.zeros(3, dtype=torch.int64, device="cuda")
+        for i in range(3):
+            sh = engine.shard_begin(da, db, int(bounds[i]), int(bounds[i + 1]), host_nnz=True)   # one shard in flight per handle
+            n_i = sh.nnz_local
+            if device_offsets:
+                arr[i] = n_i
+                torch.cuda.synchronize()
+                st = sh.finish([buf], 0, arr.data_ptr(), i)
+            else:
+                st = sh.finish([buf], off, 0, i)
+            assert st["rows"] == bounds[i + 1] - bounds[i]
+            off += n_i
+            nnz.append(n_i)
+        assert buf.nnz == len(ref[1]) == sum(nnz)
+        ip, ix, dx = buf.to_host()
+        assert np.array_equal(ip, ref[0]) and np.array_equal(ix, ref[1])
+        assert np.array_equal(dx.view(np.uint64), ref[2].view(np.uint64))
+        buf.free()
+
+
+def test_group_of_all_gpus(spada, oracle):
+    # every GPU of this process behind one call (what the single-process CLI drives); needs at least two devices
+    n = spada.device_count()
+    if n < 2:
+        pytest.skip("needs two CUDA devices")
+    rng = np.random.default_rng(83)
+    lens = rng.choice([0, 3, 20, 90, 400], size=2000, p=[.1, .4, .3, .15, .05])
+    a = random_csr(2000, 1800, row_nnz=lens, seed=84, values="signed")
+    b = random_csr(1800, 50000, row_nnz=rng.integers(0, 80, size=1800), seed=85, values="signed")
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    g = spada.Group(min(n, 8))
+    try:
+        for _ in range(2):
+            check(g.spgemm(a, b), ref, True)
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("panel_products", [0, 3000, 200000])
+def test_row_panel_streaming(engine, oracle, panel_products):
+    # C in row panels handed to a sink (D2H of a panel beside the next panel's kernels) and straight into host arrays
+    rng = np.random.default_rng(86)
+    lens = rng.choice([0, 2, 9, 40, 150, 900], size=1200, p=[.1, .3, .3, .2, .07, .03])
+    a = random_csr(1200, 1500, row_nnz=lens, seed=87, values="signed")
+    b = random_csr(1500, 20000, row_nnz=rng.integers(0, 50, size=1500), seed=88, values="signed")
+    ref = oracle.spgemm(a, b, threads=oracle.max_threads())
+    da, db = engine.upload(a), engine.upload(b)
+    got_p, got_c, got_v, spans = [np.zeros(1, dtype=np.int64)], [], [], []
+
+    def sink(r0, r1, n0, ip, ix, dx):
+        assert ip[0] == n0 and len(ip) == r1 - r0 + 1
+        spans.append((r0, r1))
+        got_p.append(ip[1:].copy()); got_c.append(ix.copy()); got_v.append(dx.copy())
+    st = engine.spgemm_stream(da, db, sink, panel_products)
+    assert spans[0][0] == 0 and spans[-1][1] == a.shape[0] and all(x[1] == y[0] for x, y in zip(spans, spans[1:]))
+    assert st["panels"] == len(spans) and st["nnz_c"] == len(ref[1])
+    if panel_products == 3000:
+        assert st["panels"] > 20
+    assert np.array_equal(np.concatenate(got_p), ref[0]) and np.array_equal(np.concatenate(got_c), ref[1])
+    assert np.array_equal(np.concatenate(got_v).view(np.uint64), ref[2].view(np.uint64))
+    ip = np.zeros(a.shape[0] + 1, dtype=np.int64); ix = np.zeros(len(ref[1]) + 7, dtype=np.int32); dx = np.zeros(len(ref[1]) + 7)
+    st = engine.spgemm_to_host(da, db, ip, ix, dx, panel_products)
+    n = st["nnz_c"]
+    assert np.array_equal(ip, ref[0]) and np.array_equal(ix[:n], ref[1]) and np.array_equal(dx[:n].view(np.uint64), ref[2].view(np.uint64))
+    with pytest.raises(Exception):
+        engine.spgemm_to_host(da, db, ip, ix[:10], dx[:10], panel_products)     # capacity below nnz(C)
+
+
+def test_sink_error_aborts(engine):
+    a = random_csr(300, 300, density=0.02, seed=89)
+    da = engine.upload(a)
+
+    def bad(*_):
+        raise ValueError("sink failed")
+    with pytest.raises(ValueError):
+        engine.spgemm_stream(da, da, bad, 500)
+    check(engine.spgemm_dev(da, da), (lambda c: (c.indptr.astype(np.int64), c.indices, c.data))(
+        (lambda c: (c.sort_indices(), c)[1])((a @ a).tocsr())), False)   # the engine is still usable
+
+
+# ---- window choice (a-6): picked per operand / accelerator, reported, never changes C ---------------------------------
+def test_window_choice_follows_the_operand(spada, oracle):
+    if spada.device_count() == 0:
+        pytest.skip("no CUDA device")
+    b = random_csr(400, 3000, row_nnz=2, seed=91, values="signed")
+    short = random_csr(500, 400, row_nnz=5, seed=92, values="signed")     # 10 products from 5 A entries: fits [4, 8]
+    wide = random_csr(500, 400, row_nnz=14, seed=93, values="signed")     # 28 products from 14 A entries: does not
+    cases = [
+        (dict(accelerator="spada"), short, [4, 8]), (dict(accelerator="spada"), wide, [1, 32]),
+        (dict(accelerator="ip"), short, [1, 32]), (dict(accelerator="op"), short, [4, 8]),
+        (dict(accelerator="op", lane_num=32), short, [1, 32]),
+        (dict(accelerator="multirow", block_shape=(4, 2)), short, [4, 8]),
+        (dict(accelerator="multirow", block_shape=(2, 4)), short, [1, 32]),
+    ]
+    for kw, a, want in cases:
+        e = spada.Engine(single_pass=True, **kw)      # the single pass is where bin 1 has two window shapes
+        try:
+            r = e.spgemm(a, b)
+            st = r.stats()
+            assert list(st["bins"]) == ["32"], st["bins"]
+            assert st["bins"]["32"]["window"] == want, (kw, st["bins"])
+            check(r, oracle.spgemm(a, b, threads=oracle.max_threads()), True)
+        finally:
+            e.close()
