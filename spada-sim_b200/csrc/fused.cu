@@ -113,7 +113,8 @@ k_fused_light(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
 
     // Tile id = a ticket drawn when the CTA starts: every tile this one looks back at is held by a CTA that is
     // already running (or done), whatever order the hardware dispatches the grid in and whatever else shares the
-    // GPU (side streams, NCCL kernels) -- the look-back can always make progress.
+    // GPU (side streams, NCCL kernels) -- the look-back can always make progress.  (Persistent CTAs that draw the next
+    // ticket while the current tile is placed were measured: ER 5.2 -> 11.9 ms, Poisson 1.34 -> 1.53 ms; reverted.)
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;

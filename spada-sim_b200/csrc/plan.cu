@@ -138,6 +138,18 @@ void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t b_rows, uint32_
     k_flops_long<<<148 * 2, FLOPS_LONG_THREADS, 0, s>>>(a, b_len, row_begin, flops, long_list, ctr);
 }
 
+// a few bytes from device memory into mapped pinned host memory, written by the SM (no copy engine: engine.cu)
+__global__ void k_publish(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int words) {
+    for (int i = threadIdx.x; i < words; i += 32) dst[i] = src[i];
+    __threadfence_system();
+}
+}  // namespace spada
+void launch_publish(const void* d_src, void* h_dst, size_t bytes, cudaStream_t s) {
+    spada::k_publish<<<1, 32, 0, s>>>(reinterpret_cast<const uint32_t*>(d_src), reinterpret_cast<uint32_t*>(h_dst),
+                                      (int)(bytes / 4));
+}
+namespace spada {
+
 // ---------------------------------------------------------------------------------------
 // K1c: scatter row ids into per-bin lists.  One smem histogram per CTA, one global
 // reservation per (CTA, bin).
@@ -301,6 +313,39 @@ void launch_mask_sorted(const uint32_t* flops, int64_t m, uint32_t lo, uint32_t 
 // row feeds the local store and the stores into every peer -- the all-gather of C fused into the kernel that writes C
 // (SURVEY.md 8e "fusion candidate").  With a single destination it is a plain copy.
 constexpr int COPY_WARPS = 8;
+// one element of a row into every destination
+template <int ND>
+__device__ __forceinline__ void copy_store(const CopyDst& dst, int64_t o, int32_t c, double v) {
+    if (ND == 1) {
+        st_out(dst.col[0] + o, c);
+        st_out(dst.val[0] + o, v);
+    } else {
+        // the peers first: their stores cross NVLink and take longest to drain
+        for (int d = dst.n - 1; d >= 0; --d) {
+            st_out(dst.col[d] + o, c);
+            st_out(dst.val[d] + o, v);
+        }
+    }
+}
+// A row of n entries from scratch (src) to its place (o) by `width` threads (lane = this thread's index among them).
+// The stores are what crosses NVLink in a sharded run, so they are the aligned side: a short head brings the
+// destination to a multiple of 32 entries (128 bytes of column ids, 256 of values), after which every warp store is
+// whole aligned lines instead of two partial ones.
+template <int ND>
+__device__ __forceinline__ void copy_row(const CopyDst& dst, int64_t o, const int32_t* __restrict__ t_col,
+                                         const double* __restrict__ t_val, int64_t src, int64_t n, int lane, int width) {
+    const int64_t head = (32 - (o & 31)) & 31;
+    if (lane < head && lane < n) copy_store<ND>(dst, o + lane, t_col[src + lane], t_val[src + lane]);
+    int64_t j = head + lane;
+    for (; j + width < n; j += 2 * width) {   // two elements per thread in flight
+        const int32_t c0 = t_col[src + j], c1 = t_col[src + j + width];
+        const double v0 = t_val[src + j], v1 = t_val[src + j + width];
+        copy_store<ND>(dst, o + j, c0, v0);
+        copy_store<ND>(dst, o + j + width, c1, v1);
+    }
+    if (j < n) copy_store<ND>(dst, o + j, t_col[src + j], t_val[src + j]);
+}
+
 template <int ND>
 __global__ void __launch_bounds__(COPY_WARPS * 32)
 k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, uint32_t lo, uint32_t hi, const int64_t* __restrict__ t_ptr,
@@ -312,21 +357,8 @@ k_copy_rows(const uint32_t* __restrict__ flops, int64_t m, uint32_t lo, uint32_t
     const uint32_t f = flops[r];
     if (f <= lo || f > hi) return;  // rows outside (lo, hi] are written by their own kernels
     const int64_t src = t_ptr[r], d0 = c_ptr[r];
-    const int n = (int)(c_ptr[r + 1] - d0);
-    const int64_t o = d0 + shard_offset(dst.off, dst.shard_nnz, dst.shard_idx);
-    for (int j = lane; j < n; j += 32) {
-        const int32_t c = t_col[src + j];
-        const double v = t_val[src + j];
-        if (ND == 1) {
-            st_out(dst.col[0] + o + j, c);
-            st_out(dst.val[0] + o + j, v);
-        } else {
-            for (int d = 0; d < dst.n; ++d) {
-                st_out(dst.col[d] + o + j, c);
-                st_out(dst.val[d] + o + j, v);
-            }
-        }
-    }
+    const int64_t n = c_ptr[r + 1] - d0;
+    copy_row<ND>(dst, d0 + shard_offset(dst.off, dst.shard_nnz, dst.shard_idx), t_col, t_val, src, n, lane, 32);
 }
 void launch_copy_rows(const uint32_t* flops, int64_t m, uint32_t lo, uint32_t hi, const int64_t* t_ptr,
                       const int32_t* t_col, const double* t_val, const int64_t* c_ptr, const CopyDst& dst,
@@ -347,20 +379,7 @@ k_copy_rows_list(const uint32_t* __restrict__ rows_list, const int64_t* __restri
     const uint32_t r = rows_list ? rows_list[blockIdx.x] : blockIdx.x;
     const int64_t src = t_ptr[r], d0 = c_ptr[r];
     const int64_t n = c_ptr[r + 1] - d0;
-    const int64_t o = d0 + shard_offset(dst.off, dst.shard_nnz, dst.shard_idx);
-    for (int64_t j = threadIdx.x; j < n; j += 256) {
-        const int32_t c = t_col[src + j];
-        const double v = t_val[src + j];
-        if (ND == 1) {
-            st_out(dst.col[0] + o + j, c);
-            st_out(dst.val[0] + o + j, v);
-        } else {
-            for (int d = 0; d < dst.n; ++d) {
-                st_out(dst.col[d] + o + j, c);
-                st_out(dst.val[d] + o + j, v);
-            }
-        }
-    }
+    copy_row<ND>(dst, d0 + shard_offset(dst.off, dst.shard_nnz, dst.shard_idx), t_col, t_val, src, n, (int)threadIdx.x, 256);
 }
 void launch_copy_rows_list(const uint32_t* rows_list, uint32_t n_rows, const int64_t* t_ptr, const int32_t* t_col,
                            const double* t_val, const int64_t* c_ptr, const CopyDst& dst, cudaStream_t s) {

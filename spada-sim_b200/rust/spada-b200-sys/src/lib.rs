@@ -85,6 +85,28 @@ pub struct spada_b200_stats {
 pub enum spada_b200_t {}
 pub enum spada_b200_csr_t {}
 pub enum spada_b200_result_t {}
+pub enum spada_b200_shard_t {}
+pub enum spada_b200_cbuf_t {}
+pub enum spada_b200_group_t {}
+pub const SPADA_B200_IPC_HANDLE_BYTES: usize = 64;
+
+/// Row-panel sink of `spada_b200_spgemm_stream`: the arrays are valid during the call only.
+pub type spada_b200_panel_sink = Option<
+    unsafe extern "C" fn(
+        user: *mut c_void, row_begin: u64, row_end: u64, nnz_begin: u64, indptr: *const i64, indices: *const i32,
+        data: *const f64,
+    ) -> c_int,
+>;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct spada_b200_stream_stats {
+    pub panels: u64,
+    pub products: u64,
+    pub nnz_c: u64,
+    pub max_panel_products: u64,
+    pub ms_total: f32,
+}
 
 extern "C" {
     pub fn spada_b200_abi_version() -> c_int;
@@ -128,6 +150,50 @@ extern "C" {
     ) -> c_int;
     pub fn spada_b200_plan_shards(
         h: *mut spada_b200_t, a: *const spada_b200_csr_t, b: *const spada_b200_csr_t, n_shards: u32, bounds: *mut u64,
+    ) -> c_int;
+    // sharded runs: A row-sharded over several GPUs, B replicated, C gathered on every GPU by the placement kernel
+    pub fn spada_b200_cbuf_create(
+        h: *mut spada_b200_t, rows: u64, cols: u64, capacity_nnz: u64, out: *mut *mut spada_b200_cbuf_t,
+    ) -> c_int;
+    pub fn spada_b200_cbuf_export(c: *const spada_b200_cbuf_t, handles: *mut c_void) -> c_int;
+    pub fn spada_b200_cbuf_import(
+        h: *mut spada_b200_t, handles: *const c_void, rows: u64, cols: u64, capacity_nnz: u64,
+        out: *mut *mut spada_b200_cbuf_t,
+    ) -> c_int;
+    pub fn spada_b200_cbuf_free(c: *mut spada_b200_cbuf_t);
+    pub fn spada_b200_cbuf_device_ptrs(
+        c: *const spada_b200_cbuf_t, d_indptr: *mut *const i64, d_indices: *mut *const i32, d_data: *mut *const f64,
+    ) -> c_int;
+    pub fn spada_b200_cbuf_nnz(c: *const spada_b200_cbuf_t, nnz: *mut u64) -> c_int;
+    pub fn spada_b200_cbuf_copy32(c: *const spada_b200_cbuf_t, indptr: *mut i64, indices: *mut i32, data: *mut f64) -> c_int;
+    pub fn spada_b200_shard_begin(
+        h: *mut spada_b200_t, a: *const spada_b200_csr_t, b: *const spada_b200_csr_t, row_begin: u64, row_end: u64,
+        d_nnz_local: *mut i64, nnz_local: *mut u64, out: *mut *mut spada_b200_shard_t,
+    ) -> c_int;
+    pub fn spada_b200_shard_finish(
+        s: *mut spada_b200_shard_t, bufs: *const *mut spada_b200_cbuf_t, n_bufs: u32, nnz_offset: u64,
+        d_shard_nnz: *const i64, shard_index: u32, stats_or_null: *mut spada_b200_stats,
+    ) -> c_int;
+    pub fn spada_b200_shard_abort(s: *mut spada_b200_shard_t);
+    // all GPUs of this process behind one call (what main.rs drives when n_gpus > 1)
+    pub fn spada_b200_group_create(opts: *const spada_b200_opts, n_gpus: u32, out: *mut *mut spada_b200_group_t) -> c_int;
+    pub fn spada_b200_group_spgemm(
+        g: *mut spada_b200_group_t, a: *const spada_csr_view, b: *const spada_csr_view, out: *mut *mut spada_b200_result_t,
+    ) -> c_int;
+    pub fn spada_b200_group_spgemm32(
+        g: *mut spada_b200_group_t, a: *const spada_csr_view32, b: *const spada_csr_view32,
+        out: *mut *mut spada_b200_result_t,
+    ) -> c_int;
+    pub fn spada_b200_group_destroy(g: *mut spada_b200_group_t);
+    // row panels: C larger than HBM, D2H of a panel beside the next panel's kernels
+    pub fn spada_b200_spgemm_stream(
+        h: *mut spada_b200_t, a: *const spada_b200_csr_t, b: *const spada_b200_csr_t, panel_products: u64,
+        sink: spada_b200_panel_sink, user: *mut c_void, stats_or_null: *mut spada_b200_stream_stats,
+    ) -> c_int;
+    pub fn spada_b200_spgemm_to_host(
+        h: *mut spada_b200_t, a: *const spada_b200_csr_t, b: *const spada_b200_csr_t, panel_products: u64,
+        indptr: *mut i64, indices: *mut i32, data: *mut f64, capacity_nnz: u64,
+        stats_or_null: *mut spada_b200_stream_stats,
     ) -> c_int;
     pub fn spada_b200_result_shape(r: *const spada_b200_result_t, rows: *mut u64, cols: *mut u64, nnz: *mut u64) -> c_int;
     pub fn spada_b200_result_copy(r: *const spada_b200_result_t, indptr: *mut u64, indices: *mut u64, data: *mut f64) -> c_int;

@@ -374,6 +374,54 @@ def test_poisson_full_size(engine, spada):
     assert np.array_equal(ip, ref.indptr) and np.array_equal(ix, ref.indices) and np.array_equal(dx, ref.data)
 
 
+def test_rect_full_size_vs_oracle(engine, oracle, spada):
+    # BASELINE configs[4] at full size against the oracle, bit for bit (288 M products; the oracle takes ~1.5 s on 16 cores)
+    a, b = spada.workloads.build("rect")
+    da = engine.upload(a)
+    db = engine.transpose(da)
+    r = engine.spgemm_dev(da, db)
+    check(r, oracle.spgemm(a, b, threads=oracle.max_threads()), True)
+    assert r.stats()["nnz_c"] == spada.workloads.KNOWN["rect"][4]
+
+
+def test_er_full_size_vs_oracle(engine, oracle, spada):
+    # BASELINE configs[2] at full size against the oracle, bit for bit (537 M products, 6.4 GB of C)
+    a, b = spada.workloads.build("er")
+    da = engine.upload(a)
+    r = engine.spgemm_dev(da, da)
+    assert r.stats()["nnz_c"] == spada.workloads.KNOWN["er"][4]
+    check(r, oracle.spgemm(a, b, threads=oracle.max_threads()), True)
+
+
+def test_rmat_full_size_row_sample(engine, oracle, spada):
+    # BASELINE configs[3]: the 200 heaviest rows (up to 1.1 M products each, 9 merge levels) and 10 000 random rows
+    # of the full-size operand against the oracle, bit for bit; B is the whole 2M x 2M matrix
+    a, b = spada.workloads.build("rmat")
+    f = oracle.flops(a, b)
+    assert int(f.sum()) == spada.workloads.KNOWN["rmat"][3]
+    rows = np.union1d(np.argsort(f)[-200:], np.random.default_rng(7).choice(a.shape[0], 10000, replace=False))
+    sub = a[rows]
+    sub.sort_indices()
+    db = engine.upload(b)
+    r = engine.spgemm_dev(engine.upload(sub), db)
+    st = r.stats()
+    assert max(int(k) for k in st["bins"] if k != "empty") >= 1 << 20
+    check(r, oracle.spgemm(sub, b, threads=oracle.max_threads()), True)
+
+
+def test_signed_zero_survives(engine, oracle):
+    # a column whose only product is -0.0 stays -0.0 (nothing is added to a +0.0 initial value), in the sort bins, the
+    # merge path of the long rows and the dense accumulator path
+    for ka, lb, n in [(3, 4, 500), (90, 80, 1 << 15), (90, 80, 300)]:
+        a = random_csr(40, 200, row_nnz=ka, seed=94, values="signed")
+        b = random_csr(200, n, row_nnz=min(lb, n), seed=95, values="signed")
+        a.data[::7] = -0.0
+        b.data[::5] = 0.0
+        r, _ = run(engine, oracle, a, b)
+        dx = r.to_host()[2]
+        assert np.signbit(dx[dx == 0.0]).any()
+
+
 def test_rect_full_size_properties(engine, spada):
     a, b = spada.workloads.build("rect")
     m, k, nnz_a, products, nnz_c = spada.workloads.KNOWN["rect"]
