@@ -421,6 +421,13 @@ void launch_shift_row_ptr(const int64_t* ptr, int64_t m, int64_t off, const int6
                           const RowPtrDst& dst, int64_t row_off, cudaStream_t s);
 // stages 2+3+4 fused for the warp-per-row bins (fused.cu)
 size_t fused_tile_state_words(int64_t m);
+// single pass for mixed row lengths: tiles cut by sort-slot budget (fused.cu: k_tile_pass)
+size_t tile_pass_bound(int64_t m, uint64_t light_slots);
+int tile_pass_cut();
+void launch_tile_pass(const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m, const uint32_t* flops,
+                      const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val, uint32_t* w, int64_t* lp,
+                      int64_t* tidx, uint32_t* tile_start, uint64_t* tile_state, size_t bound, uint64_t* scan_state,
+                      PlanCounters* ctr, cudaStream_t s);
 // tiny_quad: rows of bin 1 run four to a warp (window [4, 8]) instead of one per warp ([1, 32])
 void launch_fused_light(int max_bin, bool tiny_quad, const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m,
                         const uint32_t* flops, const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val,

@@ -76,6 +76,9 @@ struct spada_b200 {
     int fiber_pad = -1;            // SPADA_B200_FIBER_PAD: -1 auto (16 when rows average >= 6 nonzeros, else descriptors
                                    // only), 0 no fiber store, 1 descriptors only, 16 always pad
     size_t long_ws_budget = (size_t)24 << 30;   // ping-pong buffers of one wave of long rows (SPADA_B200_LONG_WS_MB)
+    bool tile_pass = false;        // SPADA_B200_TILE_PASS=1: mixed row lengths in one pass with work-cut tiles (k_tile_pass).
+                                   // Off by default: measured on the power-law config 4.6-6.2 ms for the tile pass (four
+                                   // shapes of tile) against 2.2 ms of sort passes + 0.6 ms of copy for the same rows
     spada_b200_opts opts{};
     PlanCounters* d_ctr = nullptr;
     PlanCounters* d_ctr_side = nullptr;   // scan tickets of the side stream
@@ -358,6 +361,7 @@ extern "C" int spada_b200_create(const spada_b200_opts* opts, spada_b200_t** out
         CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         if (const char* e = getenv("SPADA_B200_FIBER_PAD")) h->fiber_pad = atoi(e);
+        if (const char* e = getenv("SPADA_B200_TILE_PASS")) h->tile_pass = atoi(e) != 0;
         if (const char* e = getenv("SPADA_B200_LONG_WS_MB")) {
             long mb = atol(e);
             if (mb > 0) h->long_ws_budget = (size_t)mb << 20;
@@ -801,10 +805,13 @@ static WindowChoice window_choice(const spada_b200* h, const PlanCounters& pc) {
     }
     return w;
 }
-static void window_report(const WindowChoice& w, bool fused, const PlanCounters& pc, spada_b200_stats& st) {
+static void window_report(const WindowChoice& w, bool fused, bool tile_mode, const PlanCounters& pc, spada_b200_stats& st) {
     for (int bnum = 0; bnum < NUM_BINS; ++bnum) {
         uint32_t R = 0, lanes = 0;
-        if (bnum == 1) {
+        if (tile_mode && bnum >= 1 && bnum <= 5) {
+            R = (uint32_t)(tile_pass_cut() / bin_capacity(bnum));   // rows of this size that share a work-cut tile
+            lanes = 32;
+        } else if (bnum == 1) {
             const bool quad = fused && w.tiny_quad;   // the scratch pass runs bin 1 one row per warp
             R = quad ? 4 : 1;
             lanes = quad ? 8 : 32;
@@ -854,7 +861,7 @@ struct spada_b200_shard {
     spada_b200_result* R = nullptr;
     DevCsr A{}, B{};
     int64_t row_begin = 0, m = 0;
-    bool fused = false, scratch = false, forked = false, finished = false;
+    bool fused = false, tile_mode = false, scratch = false, forked = false, finished = false;
     PlanCounters pc{};
     BinTable tbl{};
     bool identity = false;
@@ -874,6 +881,11 @@ struct spada_b200_shard {
     int32_t* d_tcol = nullptr;
     double* d_tval = nullptr;
     // long-row wave workspace
+    // tile pass workspace
+    uint32_t *t_w = nullptr, *t_start = nullptr;
+    int64_t *t_lp = nullptr, *t_idx = nullptr;
+    uint64_t* t_state = nullptr;
+    size_t t_bound = 0;
     uint32_t *w_p = nullptr, *w_u = nullptr, *w_heads = nullptr, *w_unit_row = nullptr;
     uint64_t* w_tiles = nullptr;
     int64_t *w_prod_off = nullptr, *w_unit_off = nullptr, *w_hoff = nullptr;
@@ -900,11 +912,12 @@ struct spada_b200_shard {
     void release_work() {
         if (forked) cudaStreamSynchronize(h->side);
         forked = false;
-        uint32_t** u32s[] = {&d_flops, &d_long, &d_perm, &d_nnz, &d_masked, &d_blen, &d_aseq, &w_p, &w_u, &w_heads, &w_unit_row};
+        uint32_t** u32s[] = {&d_flops, &d_long, &d_perm, &d_nnz, &d_masked, &d_blen, &d_aseq, &w_p, &w_u, &w_heads, &w_unit_row,
+                             &t_w, &t_start};
         for (auto pp : u32s) { dfree(h, *pp); *pp = nullptr; }
-        uint64_t** u64s[] = {&d_tiles, &d_tiles_side, &w_tiles};
+        uint64_t** u64s[] = {&d_tiles, &d_tiles_side, &w_tiles, &t_state};
         for (auto pp : u64s) { dfree(h, *pp); *pp = nullptr; }
-        int64_t** i64s[] = {&d_prod_ptr, &w_prod_off, &w_unit_off, &w_hoff};
+        int64_t** i64s[] = {&d_prod_ptr, &w_prod_off, &w_unit_off, &w_hoff, &t_lp, &t_idx};
         for (auto pp : i64s) { dfree(h, *pp); *pp = nullptr; }
         dfree(h, d_tcol); d_tcol = nullptr;
         dfree(h, d_tval); d_tval = nullptr;
@@ -1137,10 +1150,14 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
     // uniform random graphs: measured 1.3x-1.6x), not on heavy-tailed row lengths (0.9x) -- DESIGN.md section 4.
     bool fused = !force_scratch && !(h->opts.flags & SPADA_B200_FLAG_TWO_PHASE) && S->light_rows > 0 &&
                  (double)pc.total_products * 12.0 <= 0.45 * (double)h->dev_total_mem;
-    if (fused && !(h->opts.flags & SPADA_B200_FLAG_SINGLE_PASS) && dominant * 10 < non_empty * 8) fused = false;
+    // rows that look alike: fixed tiles of 4..32 rows (k_fused_light / k_fused_tiny4); mixed lengths: the scratch pass,
+    // or with SPADA_B200_TILE_PASS=1 one pass over tiles cut by work (k_tile_pass)
+    const bool uniform = dominant * 10 >= non_empty * 8;
+    S->tile_mode = fused && !uniform && h->tile_pass;
+    if (fused && !uniform && !h->tile_pass && !(h->opts.flags & SPADA_B200_FLAG_SINGLE_PASS)) fused = false;
     S->fused = fused;
     S->window = window_choice(h, pc);
-    window_report(S->window, fused, pc, st);
+    window_report(S->window, fused, S->tile_mode, pc, st);
     S->scratch_lo = fused ? 512u : 0u;
     for (int bnum = fused ? 6 : 1; bnum < NUM_BINS; ++bnum) S->scratch_products += pc.bin_products[bnum];
     S->scratch = S->scratch_products > 0;
@@ -1168,6 +1185,16 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
                         "compute C in row panels with spada_b200_spgemm_stream",
                         need / 1e9, (unsigned long long)pc.total_products, (double)h->dev_total_mem / 1e9);
         }
+    }
+    if (S->tile_mode) {
+        uint64_t slots = 0;
+        for (int bnum = 1; bnum <= 5; ++bnum) slots += (uint64_t)pc.bin_rows[bnum] * bin_capacity(bnum);
+        S->t_bound = tile_pass_bound(m, slots);
+        TRY(dalloc(h, &S->t_w, (size_t)m));
+        TRY(dalloc(h, &S->t_lp, (size_t)m + 1));
+        TRY(dalloc(h, &S->t_idx, (size_t)m + 1));
+        TRY(dalloc(h, &S->t_start, S->t_bound + 1));
+        TRY(dalloc(h, &S->t_state, S->t_bound + 1));
     }
     if (S->scratch) {
         TRY(dalloc(h, &S->d_masked, (size_t)m));
@@ -1337,14 +1364,20 @@ int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_p
     if (S->fused) {
         // ---- stages 2+3+4 fused for the warp-per-row bins: straight into C ----------------------------------
         char name[32];
-        snprintf(name, sizeof(name), "fused<%s>", bin_name(S->max_light_bin));
+        snprintf(name, sizeof(name), S->tile_mode ? "tile_pass<%s>" : "fused<%s>", bin_name(S->max_light_bin));
         uint64_t light_products = 0;
         for (int bnum = 1; bnum <= 5; ++bnum) light_products += pc.bin_products[bnum];
-        S->begin_rec(name, 3, (uint32_t)((m + 7) / 8), S->light_rows, light_products);
-        launch_fused_light(S->max_light_bin, S->window.tiny_quad, S->A, S->B, S->row_begin, m, S->d_flops, S->d_nnz, R->ptr, R->col, R->val,
-                           S->d_tiles, h->d_ctr, s);
+        S->begin_rec(name, 3, S->tile_mode ? (uint32_t)S->t_bound : (uint32_t)((m + 7) / 8), S->light_rows, light_products);
+        if (S->tile_mode) {
+            launch_tile_pass(S->A, S->B, S->row_begin, m, S->d_flops, S->d_nnz, R->ptr, R->col, R->val, S->t_w, S->t_lp,
+                             S->t_idx, S->t_start, S->t_state, S->t_bound, S->d_tiles, h->d_ctr, s);
+            S->kernels += 6;
+        } else {
+            launch_fused_light(S->max_light_bin, S->window.tiny_quad, S->A, S->B, S->row_begin, m, S->d_flops, S->d_nnz,
+                               R->ptr, R->col, R->val, S->d_tiles, h->d_ctr, s);
+            S->kernels += 1;
+        }
         CUT(cudaGetLastError());
-        S->kernels += 1;
         S->end_rec();
         launch_publish(R->ptr + m, h->h_scalar, sizeof(int64_t), s);
     }

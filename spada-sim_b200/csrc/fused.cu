@@ -578,6 +578,204 @@ k_fused_tiny4(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* 
     tiny_tile_finish(tile, m, s_col, s_val, s_nnz, s_off, &s_light, &s_excl, c_ptr, c_col, c_val, tile_state, lane, warp);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Mixed row lengths (heavy-tailed graphs): tiles are cut by WORK, not by row count -- Spada's window [R, L/R] with
+// R adapting along the matrix (rowwise_perf_adjust.rs:36-77 groups consecutive rows of similar length; 121-252 picks
+// R per group): a tile holds as many consecutive rows as fit a fixed budget of sort slots, so a stretch of short rows
+// shares one tile (R up to 64) while a 512-product row has a tile almost to itself (R = 1..4).  Every tile costs about
+// the same, which is what keeps the decoupled look-back flowing: with a fixed row count per tile (k_fused_light) a
+// tile finished with its slowest row and everything placed after it waited (measured 0.9x on the power-law config).
+// A row occupies the sort capacity of its bin (32 << bin slots) inside the tile's shared memory; rows are handed to
+// the tile's warps one at a time; rows with more than 512 products were computed into scratch rows beforehand and only
+// contribute their nnz.
+#ifndef SPADA_TILE_WARPS
+#define SPADA_TILE_WARPS 8
+#endif
+#ifndef SPADA_TILE_CAP
+#define SPADA_TILE_CAP 2048
+#endif
+constexpr int TILE_CAP = SPADA_TILE_CAP;   // sort slots per tile
+constexpr int TILE_CUT = TILE_CAP - 512;   // a tile ends where the running slot count crosses a multiple of this
+constexpr int TILE_MAX_ROWS = 64;
+constexpr int TILE_WARPS = SPADA_TILE_WARPS;
+static_assert(TILE_CUT + 512 <= TILE_CAP, "a row that starts below the cut must fit");
+
+__global__ void k_tile_weights(const uint32_t* __restrict__ flops, int64_t m, uint32_t* __restrict__ w) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const uint32_t f = flops[r];
+    w[r] = (f >= 1u && f <= 512u) ? (uint32_t)bin_capacity(bin_of(f)) : 0u;
+}
+// flag[r] = 1 when row r opens a tile (lp = exclusive scan of the weights)
+__global__ void k_tile_flags(const int64_t* __restrict__ lp, int64_t m, uint32_t* __restrict__ flag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    flag[r] = (r == 0 || (r % TILE_MAX_ROWS) == 0 || lp[r] / TILE_CUT != lp[r - 1] / TILE_CUT) ? 1u : 0u;
+}
+__global__ void k_tile_starts(const uint32_t* __restrict__ flag, const int64_t* __restrict__ tidx, int64_t m,
+                              uint32_t* __restrict__ tile_start) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    if (flag[r]) tile_start[tidx[r]] = (uint32_t)r;
+    if (r == m - 1) tile_start[tidx[m]] = (uint32_t)m;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+k_tile_pass(DevCsr a, DevCsr b, int64_t row_begin, int64_t m, const uint32_t* __restrict__ flops,
+            const uint32_t* __restrict__ pre_nnz, const int64_t* __restrict__ lp, const int64_t* __restrict__ tidx,
+            const uint32_t* __restrict__ tile_start, int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_col,
+            double* __restrict__ c_val, unsigned long long* tile_state, uint32_t* ticket) {
+    constexpr int SBK = 9;   // every key carries (column << 9 | arrival): rows of at most 512 products
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    K* keys = reinterpret_cast<K*>(s_raw);
+    double* vals = reinterpret_cast<double*>(s_raw + sizeof(K) * TILE_CAP);
+    __shared__ uint32_t s_f[TILE_MAX_ROWS], s_roff[TILE_MAX_ROWS], s_nnz[TILE_MAX_ROWS], s_noff[TILE_MAX_ROWS];
+    __shared__ uint32_t s_tile;
+    __shared__ int s_next;
+    __shared__ unsigned long long s_excl;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(ticket, 1u);   // tile id = start order (see k_fused_light)
+        s_next = 0;
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if ((int64_t)tile >= tidx[m]) return;
+    const int64_t r0 = tile_start[tile];
+    const int nr = (int)(tile_start[tile + 1] - (uint32_t)r0);
+    if ((int)threadIdx.x < nr) {
+        s_f[threadIdx.x] = flops[r0 + threadIdx.x];
+        s_roff[threadIdx.x] = (uint32_t)(lp[r0 + threadIdx.x] - lp[r0]);
+    }
+    __syncthreads();
+    // rows go to the warps one at a time
+    for (;;) {
+        int row = 0;
+        if (lane == 0) row = atomicAdd(&s_next, 1);
+        row = __shfl_sync(FULL, row, 0);
+        if (row >= nr) break;
+        const uint32_t f = s_f[row];
+        int nnz = 0;
+        if (f >= 1u && f <= 512u) {
+            const int64_t r = r0 + row;
+            K* rk = keys + s_roff[row];
+            double* rv = vals + s_roff[row];
+            const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
+            int seq = 0;
+            for (int64_t pb = a_begin; pb < a_end; pb += 32) {
+                int bt;
+                expand_batch<true, false>(a, b, pb + lane, a_end, lane, seq, bt, [&](int sq, uint32_t c, double av, double bv) {
+                    rk[sq] = ((K)c << SBK) | (K)sq;
+                    rv[sq] = __dmul_rn(av, bv);
+                });
+                seq += bt;
+            }
+            switch (bin_of(f)) {
+                case 1: nnz = sort_count<K, 1, SBK>(rk, seq, lane); break;
+                case 2: nnz = sort_count<K, 2, SBK>(rk, seq, lane); break;
+                case 3: nnz = sort_count<K, 4, SBK>(rk, seq, lane); break;
+                case 4: nnz = sort_count<K, 8, SBK>(rk, seq, lane); break;
+                default: nnz = sort_count<K, 16, SBK>(rk, seq, lane); break;
+            }
+        } else if (f > 512u) {
+            nnz = (int)pre_nnz[r0 + row];   // computed into a scratch row beforehand
+        }
+        if (lane == 0) s_nnz[row] = (uint32_t)nnz;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the tile's row counts (two rows per lane), then the look-back for the tile's base
+        const uint32_t n0 = 2 * lane < nr ? s_nnz[2 * lane] : 0u, n1 = 2 * lane + 1 < nr ? s_nnz[2 * lane + 1] : 0u;
+        uint32_t x = n0 + n1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        if (2 * lane < nr) s_noff[2 * lane] = x - n0 - n1;
+        if (2 * lane + 1 < nr) s_noff[2 * lane + 1] = x - n1;
+        const unsigned long long tile_total = __shfl_sync(FULL, x, 31);
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(&tile_state[0], FST_PREFIX | tile_total);
+        } else {
+            if (lane == 0) atomicExch(&tile_state[tile], FST_AGG | tile_total);
+            int64_t pidx = (int64_t)tile - 1;
+            while (true) {
+                int64_t idx = pidx - lane;
+                unsigned long long st;
+                do {
+                    st = (idx >= 0) ? *((volatile unsigned long long*)&tile_state[idx]) : FST_PREFIX;
+                } while (__any_sync(FULL, (st & FST_MASK) == 0));
+                unsigned has_prefix = __ballot_sync(FULL, (st & FST_MASK) == FST_PREFIX);
+                unsigned long long val = st & ~FST_MASK;
+                if (has_prefix) {
+                    int first = __ffs(has_prefix) - 1;
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(FULL, val, d);
+                excl += val;
+                if (has_prefix) break;
+                pidx -= 32;
+            }
+            if (lane == 0) atomicExch(&tile_state[tile], FST_PREFIX | (excl + tile_total));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nr) {
+        const int64_t r = r0 + threadIdx.x;
+        const int64_t base = (int64_t)(s_excl + s_noff[threadIdx.x]);
+        c_ptr[r] = base;
+        if (r == m - 1) c_ptr[m] = base + s_nnz[threadIdx.x];
+    }
+    for (int row = warp; row < nr; row += TILE_WARPS) {
+        const uint32_t f = s_f[row];
+        if (f >= 1u && f <= 512u)
+            reduce_store<K, SBK>(keys + s_roff[row], vals + s_roff[row], (int)f, lane, (int64_t)(s_excl + s_noff[row]), c_col,
+                                 c_val);
+    }
+}
+
+int tile_pass_cut() { return TILE_CUT; }
+size_t tile_pass_bound(int64_t m, uint64_t light_slots) { return (size_t)(light_slots / TILE_CUT + (uint64_t)m / TILE_MAX_ROWS + 4); }
+
+// w / lp / tidx / tile_start / tile_state: workspace (m, m + 1, m + 1, bound + 1, bound + 1 entries); scan_state: the
+// look-back state of the two scans
+void launch_tile_pass(const DevCsr& a, const DevCsr& b, int64_t row_begin, int64_t m, const uint32_t* flops,
+                      const uint32_t* pre_nnz, int64_t* c_ptr, int32_t* c_col, double* c_val, uint32_t* w, int64_t* lp,
+                      int64_t* tidx, uint32_t* tile_start, uint64_t* tile_state, size_t bound, uint64_t* scan_state,
+                      PlanCounters* ctr, cudaStream_t s) {
+    if (m <= 0) return;
+    const unsigned g = (unsigned)((m + 255) / 256);
+    k_tile_weights<<<g, 256, 0, s>>>(flops, m, w);
+    launch_scan_u32_i64(w, m, lp, scan_state, ctr, s);
+    k_tile_flags<<<g, 256, 0, s>>>(lp, m, w);
+    launch_scan_u32_i64(w, m, tidx, scan_state, ctr, s);
+    k_tile_starts<<<g, 256, 0, s>>>(w, tidx, m, tile_start);
+    cudaMemsetAsync(tile_state, 0, (bound + 1) * sizeof(uint64_t), s);
+    uint32_t* ticket = &ctr->scan_ticket;
+    cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s);
+    const bool narrow = (uint64_t)b.cols < (1ull << 23);
+    const size_t smem = (narrow ? 12 : 16) * (size_t)TILE_CAP;
+    static PerDeviceOnce attr;
+    if (attr.first()) {
+        cudaFuncSetAttribute(k_tile_pass<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * TILE_CAP);
+        cudaFuncSetAttribute(k_tile_pass<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * TILE_CAP);
+    }
+    if (narrow) {
+        k_tile_pass<uint32_t><<<(unsigned)bound, TILE_WARPS * 32, smem, s>>>(a, b, row_begin, m, flops, pre_nnz, lp, tidx,
+                                                                              tile_start, c_ptr, c_col, c_val,
+                                                                              (unsigned long long*)tile_state, ticket);
+    } else {
+        k_tile_pass<uint64_t><<<(unsigned)bound, TILE_WARPS * 32, smem, s>>>(a, b, row_begin, m, flops, pre_nnz, lp, tidx,
+                                                                              tile_start, c_ptr, c_col, c_val,
+                                                                              (unsigned long long*)tile_state, ticket);
+    }
+}
+
 constexpr int fused_rpw(int nmax) { return nmax <= 32 ? 4 : (nmax <= 64 ? 2 : 1); }
 
 template <typename K, int NMAX>

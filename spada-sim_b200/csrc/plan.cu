@@ -24,6 +24,10 @@ __global__ void k_row_lengths(const int64_t* __restrict__ ptr, int64_t rows, uin
     if (i < rows) len[i] = (uint32_t)(ptr[i + 1] - ptr[i]);
 }
 
+// LPR lanes per row: 1 for short rows (stencils: consecutive threads read consecutive rows), 8 when rows average eight
+// entries or more (eight lanes read consecutive entries of one row: a thread per row then touches a different
+// 32-byte sector with every load, 8x the column-id traffic)
+template <int LPR>
 __global__ void __launch_bounds__(FLOPS_THREADS)
 k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t m,
         uint32_t* __restrict__ flops, uint32_t* __restrict__ long_list, PlanCounters* ctr) {
@@ -39,17 +43,27 @@ k_flops(DevCsr a, const uint32_t* __restrict__ b_len, int64_t row_begin, int64_t
         s_fit = 0;
     }
     __syncthreads();
-    int64_t i = (int64_t)blockIdx.x * FLOPS_THREADS + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * FLOPS_THREADS + threadIdx.x) / LPR;
+    const int sub = threadIdx.x % LPR;
     int b = -1;   // bin of this thread's row, -1: nothing to count here
     bool fits = false;   // a row of bin 1 with at most 8 A entries
     unsigned long long f = 0;
+    int64_t s = 0, e = 0;
     if (i < m) {
-        int64_t s = a.ptr[row_begin + i], e = a.ptr[row_begin + i + 1];
+        s = a.ptr[row_begin + i];
+        e = a.ptr[row_begin + i + 1];
+        if (e - s <= LONG_ROW)
+            for (int64_t p = s + sub; p < e; p += LPR) f += (unsigned long long)__ldg(b_len + ldg_i32(a.col + p));
+    }
+    if (LPR > 1) {
+#pragma unroll
+        for (int d = LPR / 2; d > 0; d >>= 1) f += __shfl_xor_sync(FULL, f, d);
+    }
+    if (i < m && sub == 0) {
         if (e - s > LONG_ROW) {
             uint32_t slot = atomicAdd(&ctr->long_rows, 1u);
             long_list[slot] = (uint32_t)i;
         } else {
-            for (int64_t p = s; p < e; ++p) f += (unsigned long long)__ldg(b_len + ldg_i32(a.col + p));
             uint32_t f32 = f > 0xffffffffull ? 0xffffffffu : (uint32_t)f;
             flops[i] = f32;
             b = bin_of(f32);
@@ -133,8 +147,11 @@ void launch_flops(const DevCsr& a, const int64_t* b_ptr, int64_t b_rows, uint32_
                   uint32_t* flops, uint32_t* long_list, PlanCounters* ctr, cudaStream_t s) {
     if (m <= 0) return;
     if (b_rows > 0) k_row_lengths<<<(unsigned)((b_rows + 255) / 256), 256, 0, s>>>(b_ptr, b_rows, b_len);
+    // one thread per row.  (Eight lanes per row for operands that average >= 8 entries per row were measured: the
+    // column ids coalesce, but the kernel is bound by the gathers of the B-row lengths and the extra threads cost more
+    // than they save -- rect 0.27 -> 0.33 ms, R-MAT 0.26 -> 0.61 ms.)
     unsigned grid = (unsigned)((m + FLOPS_THREADS - 1) / FLOPS_THREADS);
-    k_flops<<<grid, FLOPS_THREADS, 0, s>>>(a, b_len, row_begin, m, flops, long_list, ctr);
+    k_flops<1><<<grid, FLOPS_THREADS, 0, s>>>(a, b_len, row_begin, m, flops, long_list, ctr);
     k_flops_long<<<148 * 2, FLOPS_LONG_THREADS, 0, s>>>(a, b_len, row_begin, flops, long_list, ctr);
 }
 

@@ -417,9 +417,12 @@ def test_signed_zero_survives(engine, oracle):
         b = random_csr(200, n, row_nnz=min(lb, n), seed=95, values="signed")
         a.data[::7] = -0.0
         b.data[::5] = 0.0
+        b.data = np.abs(b.data)
+        a.data[a.indptr[3]:a.indptr[4]] = -0.0      # every product of row 3 is -0.0: so is every sum of that row
         r, _ = run(engine, oracle, a, b)
-        dx = r.to_host()[2]
-        assert np.signbit(dx[dx == 0.0]).any()
+        ip, _, dx = r.to_host()
+        row3 = dx[ip[3]:ip[4]]
+        assert len(row3) and (row3 == 0.0).all() and np.signbit(row3).all()
 
 
 def test_rect_full_size_properties(engine, spada):
@@ -585,5 +588,32 @@ def test_window_choice_follows_the_operand(spada, oracle):
             assert list(st["bins"]) == ["32"], st["bins"]
             assert st["bins"]["32"]["window"] == want, (kw, st["bins"])
             check(r, oracle.spgemm(a, b, threads=oracle.max_threads()), True)
+        finally:
+            e.close()
+
+
+@pytest.mark.parametrize("tile_pass", ["1", "0"])
+def test_single_pass_on_mixed_rows(spada, oracle, monkeypatch, tile_pass):
+    # mixed row lengths in one pass: tiles cut by work (SPADA_B200_TILE_PASS=1) or fixed-size tiles (default); empty rows,
+    # long runs of tiny rows (more than 64 rows per work budget), rows of every light bin and heavier rows in between
+    if spada.device_count() == 0:
+        pytest.skip("no CUDA device")
+    monkeypatch.setenv("SPADA_B200_TILE_PASS", tile_pass)
+    rng = np.random.default_rng(96)
+    lens = rng.choice([0, 1, 2, 5, 11, 23, 40, 90, 300], size=6000, p=[.15, .25, .2, .15, .1, .07, .05, .02, .01])
+    lens[1000:1400] = 1      # a stretch of tiny rows: the row cap of a tile, not the work budget, cuts here
+    lens[2000:2100] = 0
+    a = random_csr(6000, 3000, row_nnz=lens, seed=97, values="signed")
+    for n_cols in (5000, 1 << 24):     # 32-bit and 64-bit keys
+        b = random_csr(3000, n_cols, row_nnz=rng.integers(0, 24, size=3000), seed=98, values="signed")
+        e = spada.Engine(single_pass=True)
+        try:
+            r = e.spgemm(a, b)
+            st = r.stats()
+            names = [L["name"] for L in st["launches"]]
+            assert any(n.startswith("tile_pass" if tile_pass == "1" else "fused") for n in names), names
+            check(r, oracle.spgemm(a, b, threads=oracle.max_threads()), True)
+            if tile_pass == "1":
+                assert st["bins"]["32"]["window"] == [48, 32] and st["bins"]["512"]["window"] == [3, 32]
         finally:
             e.close()
