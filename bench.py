@@ -473,6 +473,51 @@ def main():
                  "nvlink_floor_ms": float(mx[0]) / (NVLINK_PEAK_GBS * 1e9) * 1e3,
                  "note": "value includes the exchange of C; compute_only = same steps storing only into the rank's own buffers"}
 
+    # ---- N > 1 end to end: pinned host operands on rank 0 -> H2D -> NCCL broadcast -> shard plan -> sharded product with
+    # the peer-store gather -> the whole C back in pinned host memory on rank 0; every step repeats all of it ---------
+    e2e = None
+    if world > 1 and pg is not None and args.e2e_steps > 0:
+        pa = pb_ = None
+        o_ptr = o_col = o_val = None
+        if rank == 0:
+            pa = D.PinnedCsr(a)
+            pb_ = pa if same_operand else D.PinnedCsr(b)
+            o_ptr = torch.empty(m + 1, dtype=torch.int64).pin_memory()
+            o_col = torch.empty(nnz_c, dtype=torch.int32).pin_memory()
+            o_val = torch.empty(nnz_c, dtype=torch.float64).pin_memory()
+
+        def e2e_multi():
+            xa, _k1 = D.broadcast_csr(eng, pa, device)
+            xb, _k2 = (xa, _k1) if same_operand else D.broadcast_csr(eng, pb_, device)
+            bnd = D.plan_bounds(eng, xa, xb, world, device)
+            pg.step(xa, xb, int(bnd[rank]), int(bnd[rank + 1]))
+            if rank == 0:
+                g_ptr, g_col, g_val = pg.result()
+                o_ptr.copy_(g_ptr, non_blocking=True)
+                o_col.copy_(g_col[:nnz_c], non_blocking=True)
+                o_val.copy_(g_val[:nnz_c], non_blocking=True)
+            torch.cuda.synchronize()
+            xa.free()
+            if xb is not xa:
+                xb.free()
+        e2e_multi()
+        dist.barrier()
+        f0, f1 = ev(), ev()
+        f0.record()
+        for _ in range(args.e2e_steps):
+            e2e_multi()
+        f1.record()
+        torch.cuda.synchronize()
+        ems = torch.tensor([f0.elapsed_time(f1) / args.e2e_steps], dtype=torch.float64, device=device)
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert int(o_ptr[-1]) == nnz_c
+            e2e = {"value": 2.0 * products / (float(ems[0]) * 1e-3) / 1e9, "unit": "GFLOP/s",
+                   "h2d_bytes_per_step": (8 * (m + 1) + 12 * nnz_a) + (0 if same_operand else 8 * (k + 1) + 12 * nnz_b),
+                   "d2h_bytes_per_step": 8 * (m + 1) + 12 * nnz_c, "ms_per_step": float(ems[0]), "steps": args.e2e_steps,
+                   "note": "rank 0: pinned host CSR -> H2D -> NCCL broadcast of A and B -> shard plan -> sharded product with "
+                           "peer-store gather -> whole C to rank 0's pinned host memory; max over ranks"}
+
     # ---- per-launch durations: the engine overlaps the long rows with the sort bins on a side stream, so the event
     # times of the timed region overlap too.  For the roofline every kernel is timed alone: a second handle with
     # SPADA_B200_FLAG_SERIAL over the same device arrays (this rank's rows), 3 warm-up + 5 recorded steps.
@@ -530,7 +575,6 @@ def main():
                 "launch_ms": {k_: v["ms"] / v["n"] for k_, v in per_launch.items()}}
 
     # ---- e2e: host-level C-ABI call with pinned host operands, C copied back (N = 1) --------------------------
-    e2e = None
     if world == 1 and args.e2e_steps > 0:
         e2e = e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, args.e2e_steps, torch)
 

@@ -379,6 +379,8 @@ struct LongWave {
     uint32_t n_rows;
     uint32_t level_lo[24];       // first list index (inside the wave) that takes part in merge level l (1-based)
     uint32_t level_grid[24];     // upper bound of the merge tiles of level l
+    uint64_t level_products[24]; // upper bound of the products that take part in level l
+    uint64_t products_bound;     // upper bound of the wave's products
     int max_level;
     uint64_t unit_bound;         // upper bound of the wave's chunks
     // workspace (device)
@@ -400,7 +402,7 @@ void launch_long_prefix(const DevCsr& a, int64_t row_begin, const uint32_t* rows
 // t_ptr/t_col/t_val: scratch CSR the finished rows are written to; row_nnz: their nnz.  stages (nullable): called
 // around the sort, the merge levels and the sums so the engine can time them.  Returns the kernels launched.
 struct LongStages {
-    std::function<void(const char*, uint32_t)> on;
+    std::function<void(const char*, uint32_t, uint64_t)> on;   // stage name, grid, products it touches
     std::function<void()> off;
 };
 uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,

@@ -939,6 +939,7 @@ struct WavePlan {
     uint64_t unit_bound;
     uint32_t level_lo[24];
     uint32_t level_grid[24];
+    uint64_t level_products[24];
     int max_level;
 };
 std::vector<WavePlan> plan_waves(const PlanCounters& pc, uint64_t budget_products) {
@@ -991,14 +992,16 @@ std::vector<WavePlan> plan_waves(const PlanCounters& pc, uint64_t budget_product
         }
         for (int l = 1; l <= P.max_level && l < 24; ++l) {
             uint32_t first = P.hi;
-            uint64_t grid = 0;
+            uint64_t grid = 0, prods = 0;
             for (auto& pc_ : w)
                 if (pc_.level >= l) {
                     first = std::min(first, pc_.lo);
                     grid += pc_.ubound;
+                    prods += pc_.pbound;
                 }
             P.level_lo[l] = first - P.lo;
             P.level_grid[l] = (uint32_t)grid;
+            P.level_products[l] = prods;
         }
         out.push_back(P);
     }
@@ -1253,6 +1256,8 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
             W.n_rows = w.hi - w.lo;
             memcpy(W.level_lo, w.level_lo, sizeof(W.level_lo));
             memcpy(W.level_grid, w.level_grid, sizeof(W.level_grid));
+            memcpy(W.level_products, w.level_products, sizeof(W.level_products));
+            W.products_bound = w.products_bound;
             W.max_level = w.max_level;
             W.unit_bound = w.unit_bound;
             W.p = S->w_p;
@@ -1269,22 +1274,22 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
             }
             W.tile_state = S->d_tiles_side;
             LongStages stages;
-            stages.on = [&](const char* what, uint32_t grid) {
+            stages.on = [&](const char* what, uint32_t grid, uint64_t products) {
                 char name[32];
                 if (waves.size() > 1) snprintf(name, sizeof(name), "%s#%d", what, wi);
                 else snprintf(name, sizeof(name), "%s", what);
-                if (waves.size() <= 4) S->begin_rec(name, 2, grid, W.n_rows, w.products_bound, sh);
+                if (waves.size() <= 2) S->begin_rec(name, 2, grid, W.n_rows, products, sh);
             };
             stages.off = [&]() {
-                if (waves.size() <= 4) S->end_rec();
+                if (waves.size() <= 2) S->end_rec();
             };
-            if (waves.size() > 4 && wi == 0) S->begin_rec("long_waves", 2, (uint32_t)w.unit_bound, S->n_long, S->long_products, sh);
+            if (waves.size() > 2 && wi == 0) S->begin_rec("long_waves", 2, (uint32_t)w.unit_bound, S->n_long, S->long_products, sh);
             S->kernels += launch_long_wave(A, B, (int64_t)row_begin, S->d_flops, S->d_aseq, W, S->d_prod_ptr, S->d_tcol,
                                            S->d_tval, S->d_nnz, h->d_ctr_side, sh, &stages);
             CUT(cudaGetLastError());
             ++wi;
         }
-        if (waves.size() > 4) S->end_rec();
+        if (waves.size() > 2) S->end_rec();
     }
     for (int bnum = fused ? 6 : 1; bnum <= 8; ++bnum) {
         const uint32_t rows = pc.bin_rows[bnum];

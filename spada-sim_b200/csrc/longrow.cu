@@ -26,6 +26,7 @@
 //
 // HBM traffic per product: 12 B written by the sort, 24 B per merge level, 4 + 24 B for the sums.
 #include <algorithm>
+#include <cstdio>
 
 #include "cta_common.cuh"
 
@@ -712,13 +713,15 @@ uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, c
                           uint32_t* row_nnz, PlanCounters* ctr, cudaStream_t s, const LongStages* stages) {
     if (w.n_rows == 0) return 0;
     uint32_t kernels = 0;
-    auto on = [&](const char* what, uint32_t grid) { if (stages) stages->on(what, grid); };
+    auto on = [&](const char* what, uint32_t grid, uint64_t products) { if (stages) stages->on(what, grid, products); };
     auto off = [&]() { if (stages) stages->off(); };
-    on("long_sort", (uint32_t)w.unit_bound);
+    on("long_setup", (w.n_rows + 255) / 256, 0);
     k_long_setup<<<(w.n_rows + 255) / 256, 256, 0, s>>>(w.rows_list, w.n_rows, flops, w.p, w.u);
     launch_scan_u32_i64(w.p, w.n_rows, w.prod_off, w.tile_state, ctr, s);
     launch_scan_u32_i64(w.u, w.n_rows, w.unit_off, w.tile_state, ctr, s);
     k_long_units<<<(unsigned)((w.unit_bound + 255) / 256), 256, 0, s>>>(w.unit_off, w.n_rows, w.unit_row);
+    off();
+    on("long_sort", (uint32_t)w.unit_bound, w.products_bound);
     // sort: 32-bit (column << 12 | arrival) keys whenever they fit
     if ((uint64_t)b.cols <= (1ull << (32 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 1>(a, b, row_begin, aseq, w, s);
     else if ((uint64_t)b.cols <= (1ull << (33 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 2>(a, b, row_begin, aseq, w, s);
@@ -737,9 +740,11 @@ uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         merge_ctas = 2 * sms;
     }
-    on("long_merge", w.level_grid[1]);
     for (int l = 1; l <= w.max_level; ++l) {
         if (w.level_grid[l] == 0) continue;
+        char lname[24];
+        snprintf(lname, sizeof(lname), "long_merge_L%d", l);
+        on(lname, w.level_grid[l], w.level_products[l]);
         const unsigned grid = std::min<unsigned>(w.level_grid[l], (unsigned)merge_ctas);
         k_long_partition<<<(w.level_grid[l] + 255) / 256, 256, 0, s>>>(w.unit_row, w.n_rows, w.level_lo[l], l, w.p, w.unit_off,
                                                                        w.prod_off, w.col[(l - 1) & 1],
@@ -748,9 +753,9 @@ uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, c
                                                       w.unit_off, w.n_rows, w.level_lo[l], w.col[(l - 1) & 1],
                                                       w.val[(l - 1) & 1], w.col[l & 1], w.val[l & 1]);
         kernels += 2;
+        off();
     }
-    off();
-    on("long_sums", (uint32_t)w.unit_bound);
+    on("long_sums", (uint32_t)w.unit_bound, w.products_bound);
     cudaMemsetAsync(w.unit_heads, 0, (size_t)w.unit_bound * sizeof(uint32_t), s);
     k_long_count<<<(unsigned)w.unit_bound, LR_THREADS, 0, s>>>(w.rows_list, w.n_rows, w.p, w.unit_row, w.unit_off, w.prod_off,
                                                               w.col[0], w.col[1], w.unit_heads);

@@ -532,11 +532,16 @@ class Simulator {
         o.block_shape[0] = (uint32_t)std::min<size_t>(default_block_shape[0], 0xffffffffu);
         o.block_shape[1] = (uint32_t)std::min<size_t>(default_block_shape[1], 0xffffffffu);
         o.flags = SPADA_B200_FLAG_VALIDATE;
-        check(spada_b200_create(&o, &h_));  // the reference panics on every failure; so does this
+        // SPADA_B200_GPUS=N: every product is sharded over N GPUs of this process (rows of A by equal product count, B
+        // replicated, C gathered by the placement kernels' peer stores): spada_b200_group_* instead of one handle
+        if (const char* e = std::getenv("SPADA_B200_GPUS")) n_gpus_ = std::max(1, std::atoi(e));
+        if (n_gpus_ > 1) check(spada_b200_group_create(&o, (uint32_t)n_gpus_, &g_));
+        else check(spada_b200_create(&o, &h_));  // the reference panics on every failure; so does this
     }
     ~Simulator() {
         if (r_) spada_b200_result_free(r_);
         if (h_) spada_b200_destroy(h_);
+        if (g_) spada_b200_group_destroy(g_);
     }
     Simulator(const Simulator&) = delete;
     Simulator& operator=(const Simulator&) = delete;
@@ -544,7 +549,8 @@ class Simulator {
     void execute() {  // simulator.rs:509-890
         spada_csr_view va{a_.mat_shape[1], a_.mat_shape[0], a_.data.size(), a_.indptr.data(), a_.indices.data(), a_.data.data()};
         spada_csr_view vb{b_.mat_shape[1], b_.mat_shape[0], b_.data.size(), b_.indptr.data(), b_.indices.data(), b_.data.data()};
-        check(spada_b200_spgemm(h_, &va, &vb, &r_));
+        if (g_) check(spada_b200_group_spgemm(g_, &va, &vb, &r_));
+        else check(spada_b200_spgemm(h_, &va, &vb, &r_));
         check(spada_b200_result_stats(r_, &st_));
         st_.nnz_a = a_.data.size();
     }
@@ -576,6 +582,8 @@ class Simulator {
     }
     CsrMatStorage &a_, &b_;
     spada_b200_t* h_ = nullptr;
+    spada_b200_group_t* g_ = nullptr;
+    int n_gpus_ = 1;
     spada_b200_result_t* r_ = nullptr;
     spada_b200_stats st_{};
 };

@@ -15,8 +15,10 @@ from typing import List, Optional
 
 import numpy as np
 
+import os
+
 from . import _abi
-from .engine import Engine, Result
+from .engine import Engine, Group, Result
 from .storage import CsrMatStorage, CsrRow
 
 import ctypes as C
@@ -32,8 +34,13 @@ class Simulator:
         self.accelerator = accelerator
         self.lane_num = lane_num
         self.default_block_shape = list(default_block_shape)
-        self.engine = Engine(device=device, accelerator=accelerator, lane_num=lane_num,
-                             block_shape=default_block_shape)
+        # SPADA_B200_GPUS=N: every product sharded over N GPUs of this process (spada_b200_group_*)
+        self.n_gpus = max(1, int(os.environ.get("SPADA_B200_GPUS", "1")))
+        if self.n_gpus > 1:
+            self.engine = Group(self.n_gpus, accelerator=accelerator, lane_num=lane_num, block_shape=default_block_shape)
+        else:
+            self.engine = Engine(device=device, accelerator=accelerator, lane_num=lane_num,
+                                 block_shape=default_block_shape)
         self._result: Optional[Result] = None
         self._stats = None
 
@@ -50,7 +57,8 @@ class Simulator:
         same = (self.b_matrix.indptr is self.a_matrix.indptr and self.b_matrix.indices is self.a_matrix.indices
                 and self.b_matrix.data is self.a_matrix.data)
         vb = va if same else self._view(self.b_matrix)
-        _abi.check(_abi.lib().spada_b200_spgemm(self.engine._h, C.byref(va), C.byref(vb), C.byref(out)))
+        call = _abi.lib().spada_b200_group_spgemm if self.n_gpus > 1 else _abi.lib().spada_b200_spgemm
+        _abi.check(call(self.engine._h, C.byref(va), C.byref(vb), C.byref(out)))
         self._result = Result(self.engine, out)
         self._stats = self._result.stats()
 

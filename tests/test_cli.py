@@ -97,7 +97,29 @@ def test_cli_cari_transcript(workdir, oracle, cari, spada, acc, extra):
         assert m and int(m.group(1)) == r
         assert [int(x) for x in m.group(2).split(", ")] == cj[cp[r]:cp[r] + 5].tolist()
         vals = np.array([float(x) for x in m.group(3).split(", ")])
-        assert np.allclose(vals, cx[cp[r]:cp[r] + 5], rtol=1e-12, atol=0)   # -p never changes C (simulator.rs:1039-1060)
+        assert np.array_equal(vals, cx[cp[r]:cp[r] + 5])   # bit-exact; -p never changes C (simulator.rs:1039-1060)
+
+
+@pytest.mark.gpu
+def test_cli_on_all_gpus_of_the_process(workdir, oracle, cari, spada):
+    # SPADA_B200_GPUS=2: the same transcript with every product sharded over two GPUs (spada_b200_group_*), both hosts
+    if spada.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    g = spada.GEMM.from_mat("cari", cari)
+    cp, cj, cx = oracle.spgemm(g.a, g.b)
+    env = dict(os.environ, PYTHONPATH=ROOT, SPADA_B200_GPUS="2", SPADA_B200_DUMP_C=str(workdir / "c2.mtx"))
+    cmds = [[sys.executable, "-W", "ignore", "-m", "spada-sim_b200"]]
+    binary = os.path.join(ROOT, "spada-sim_b200", "bin", "spada-sim")
+    if os.path.exists(binary):
+        cmds.append([binary])
+    for cmd in cmds:
+        p = subprocess.run(cmd + ["accuratesimu", "spada", "ss", "cari", "config/config_1mb_row1.json"], cwd=workdir, env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout.startswith(HEAD)
+        c = scipy.io.mmread(str(workdir / "c2.mtx")).tocsr(); c.sort_indices()
+        assert np.array_equal(c.indptr, cp) and np.array_equal(c.indices, cj)
+        assert np.array_equal(c.data.view(np.uint64), cx.view(np.uint64))
 
 
 def test_result_sink_roundtrip(tmp_path, spada):
@@ -137,4 +159,4 @@ def test_cli_result_sink(workdir, oracle, cari, spada):
     for path in outs:
         c = scipy.io.mmread(str(path)).tocsr(); c.sort_indices()
         assert c.shape == (400, 400) and np.array_equal(c.indptr, cp) and np.array_equal(c.indices, cj)
-        assert (np.abs(c.data - cx) <= 1e-12 * np.abs(cx)).all()
+        assert np.array_equal(c.data.view(np.uint64), cx.view(np.uint64))

@@ -617,3 +617,22 @@ def test_single_pass_on_mixed_rows(spada, oracle, monkeypatch, tile_pass):
                 assert st["bins"]["32"]["window"] == [48, 32] and st["bins"]["512"]["window"] == [3, 32]
         finally:
             e.close()
+
+
+def test_narrow_outputs_both_long_row_paths(spada, oracle, cari, monkeypatch):
+    # cari (400 output columns): the dense-accumulator path (default for B.cols <= 16384) and, with SPADA_B200_NO_DENSE=1,
+    # the chunk-sort + merge path (every chunk carries every column: runs of ~361 equal columns across 36 chunks)
+    if spada.device_count() == 0:
+        pytest.skip("no CUDA device")
+    g = spada.GEMM.from_mat("cari", cari)
+    ref = oracle.spgemm(g.a, g.b, threads=oracle.max_threads())
+    for no_dense, kernel in (("", "long_dense"), ("1", "long_sort")):
+        if no_dense:
+            monkeypatch.setenv("SPADA_B200_NO_DENSE", no_dense)
+        e = spada.Engine()
+        try:
+            r = e.spgemm(g.a, g.b)
+            assert kernel in [L["name"] for L in r.stats()["launches"]]
+            check(r, ref, True)
+        finally:
+            e.close()

@@ -1,10 +1,12 @@
 #!/bin/bash
-# usage: gpurun_retry.sh <timeout> <cmd...>  -- retries while the pod has no free slot (exit code 3)
+# usage: gpurun_retry.sh [-g N] <timeout> <cmd...>  -- retries while the pod has no free slot (exit code 3)
+G=""
+if [ "$1" = "-g" ]; then G="--gpus $2"; shift 2; fi
 T=$1; shift
-for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout $T "$@" > /tmp/gpurun_last.log 2>&1
+for i in $(seq 1 60); do
+  /usr/local/graft/bin/gpurun $G --timeout $T "$@" > /tmp/gpurun_last.log 2>&1
   rc=$?
-  if [ $rc -ne 3 ]; then cat /tmp/gpurun_last.log | tail -80; exit $rc; fi
-  sleep 90
+  if [ $rc -ne 3 ]; then cat /tmp/gpurun_last.log | tail -120; exit $rc; fi
+  sleep 75
 done
 echo "gave up"; exit 3
