@@ -633,6 +633,7 @@ def e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, steps, torch
         else:
             abi.check(lib.spada_b200_upload32(eng._h, C.byref(vb), C.byref(pb)))
         try:
+            abi.check(lib.spada_b200_csr_set_one_shot(pb))    # operands of one product: no fiber store
             abi.check(lib.spada_b200_spgemm_to_host(eng._h, pa, pb, 0, o_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
                                                     o_col.ctypes.data_as(C.POINTER(C.c_int32)),
                                                     o_val.ctypes.data_as(C.POINTER(C.c_double)), len(o_col), None))

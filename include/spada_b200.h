@@ -170,6 +170,9 @@ SPADA_B200_API int spada_b200_csr_wrap_device(spada_b200_t *h, uint64_t rows, ui
  * 460-).  Uploaded operands get it automatically the first time they are used as B; call this for wrapped device
  * arrays (it snapshots them: call again after changing them -- free and re-wrap).  ms_or_null: device time. */
 SPADA_B200_API int spada_b200_csr_prepare(spada_b200_t *h, spada_b200_csr_t *m, float *ms_or_null);
+/* Marks an operand as used once: no fiber store is built for it (re-laying B costs about as much as one product saves:
+ * rect 3 ms of build against 0.1 ms of kernel time), the kernels gather its rows through row_ptr. */
+SPADA_B200_API int spada_b200_csr_set_one_shot(spada_b200_csr_t *m);
 /* B = A^T as a new device operand (canonical CSR: ascending column ids = A's row ids).  Replaces the host-side
  * transpose of GEMM::from_mat for non-square SS workloads (gemm.rs:41-53: `transpose_into().to_csr()`); values are
  * moved, not computed, so the result is bit-identical to the reference's / scipy's. */

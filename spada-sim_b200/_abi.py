@@ -85,6 +85,7 @@ SYMBOLS = {
     "spada_b200_upload32": (C.c_int, [_vp, C.POINTER(CsrView32), _vpp]),
     "spada_b200_csr_wrap_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vpp]),
     "spada_b200_csr_prepare": (C.c_int, [_vp, _vp, C.POINTER(C.c_float)]),
+    "spada_b200_csr_set_one_shot": (C.c_int, [_vp]),
     "spada_b200_transpose": (C.c_int, [_vp, _vp, _vpp]),
     "spada_b200_csr_shape": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "spada_b200_csr_device_ptrs": (C.c_int, [_vp, _vpp, _vpp, _vpp]),

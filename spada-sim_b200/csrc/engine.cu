@@ -634,6 +634,12 @@ extern "C" int spada_b200_csr_prepare(spada_b200_t* h, spada_b200_csr_t* m, floa
     return rc;
 }
 
+extern "C" int spada_b200_csr_set_one_shot(spada_b200_csr_t* m) {
+    if (!m) return fail(SPADA_B200_INVALID_ARG, "matrix is NULL");
+    m->fib_ready = true;   // build_fibers() will not run for it: the kernels gather through row_ptr
+    return 0;
+}
+
 // ---- B = A^T on the device: replaces GEMM::from_mat's transpose_into().to_csr() (gemm.rs:44-46) --------------
 extern "C" int spada_b200_transpose(spada_b200_t* h, const spada_b200_csr_t* a, spada_b200_csr_t** out) {
     if (!h || !a || !out) return fail(SPADA_B200_INVALID_ARG, "NULL argument");

@@ -49,6 +49,10 @@ class DeviceCsr:
         check(lib().spada_b200_csr_download32(self._h, _ptr(ip, C.c_int64), _ptr(ix, C.c_int32), _ptr(dx, C.c_double)))
         return sp.csr_matrix((dx[:self.nnz], ix[:self.nnz], ip), shape=self.shape)
 
+    def set_one_shot(self):
+        """No fiber store for this operand (it is used for one product only)."""
+        check(lib().spada_b200_csr_set_one_shot(self._h))
+
     def prepare(self) -> float:
         """Builds the fiber store the kernels gather B rows from (automatic for uploaded operands on their first
         use as B; needed for wrapped device arrays).  Returns the device time in ms."""

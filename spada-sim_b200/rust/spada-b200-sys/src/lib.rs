@@ -126,6 +126,7 @@ extern "C" {
         d_data: *const f64, out: *mut *mut spada_b200_csr_t,
     ) -> c_int;
     pub fn spada_b200_csr_prepare(h: *mut spada_b200_t, m: *mut spada_b200_csr_t, ms_or_null: *mut f32) -> c_int;
+    pub fn spada_b200_csr_set_one_shot(m: *mut spada_b200_csr_t) -> c_int;
     pub fn spada_b200_transpose(h: *mut spada_b200_t, a: *const spada_b200_csr_t, out: *mut *mut spada_b200_csr_t) -> c_int;
     pub fn spada_b200_csr_shape(m: *const spada_b200_csr_t, rows: *mut u64, cols: *mut u64, nnz: *mut u64) -> c_int;
     pub fn spada_b200_csr_device_ptrs(
