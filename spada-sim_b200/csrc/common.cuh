@@ -377,42 +377,51 @@ void launch_bitonic_cta_numeric(int bin, const DevCsr& a, const DevCsr& b, int64
                                 uint32_t rows, const int64_t* c_ptr, int32_t* c_col, double* c_val, cudaStream_t s,
                                 uint32_t* row_nnz_out = nullptr);
 // long rows (bins >= BIN_LONG0), longrow.cu: K-tiled chunk sorts + merge levels + left-to-right sums, all in the
-// oracle's ascending-k order (no atomics).  One WAVE = a contiguous slice of the long-row list whose products fit
-// the two ping-pong buffers.
-struct LongWave {
-    const uint32_t* rows_list;   // the wave's slice of perm[] (long rows, ascending merge-level count)
+// oracle's ascending-k order (no atomics).  LongPlan = the tables of the whole long-row list; a WAVE = a contiguous slice
+// of the list whose products fit the pong buffer.
+struct LongPlan {
+    const uint32_t* rows_list;   // perm[] slice of the long rows, ascending merge-level count
     uint32_t n_rows;
-    uint32_t level_lo[24];       // first list index (inside the wave) that takes part in merge level l (1-based)
-    uint32_t level_grid[24];     // upper bound of the merge tiles of level l
-    uint64_t level_products[24]; // upper bound of the products that take part in level l
-    uint64_t products_bound;     // upper bound of the wave's products
-    int max_level;
-    uint64_t unit_bound;         // upper bound of the wave's chunks
-    // workspace (device)
+    uint64_t unit_bound;         // upper bound of all chunks
     uint32_t* p;                 // [n_rows]   products per row
     uint32_t* u;                 // [n_rows]   chunks per row
-    int64_t* prod_off;           // [n_rows+1] start of the row inside the ping-pong buffers
+    int64_t* prod_off;           // [n_rows+1] prefix of p (origin of a row inside its wave's pong buffer)
     int64_t* unit_off;           // [n_rows+1] first chunk of the row
-    uint32_t* unit_row;          // [unit_bound] row (index inside the wave) of every chunk / tile
-    void* tiles;                 // [unit_bound] x 32 B: merge-tile descriptors of the level in flight
-    uint32_t* unit_heads;        // [unit_bound] distinct columns that start inside the chunk
+    uint32_t* unit_row;          // [unit_bound] row (index inside the list) of every chunk / tile
+    uint32_t* unit_heads;        // [unit_bound] distinct columns that start inside the tile
     int64_t* unit_hoff;          // [unit_bound+1]
-    int32_t* col[2];             // ping-pong buffers, one entry per product of the wave
-    double* val[2];
-    uint64_t* tile_state;        // look-back state of the wave's scans
+    const int64_t* t_ptr;        // scratch CSR: a long row's scratch row holds its sorted products (buffer 0)
+    int32_t* s_col;
+    double* s_val;
+    int32_t* pong_col;           // buffer 1: one wave
+    double* pong_val;
+    void* tiles;                 // [wave units] x 32 B: merge-tile descriptors of the level in flight
+    uint64_t* tile_state;        // look-back state of the scans
+};
+struct LongWaveRange {
+    uint32_t lo, hi;             // slice of the list
+    uint32_t level_lo[24];       // first list index that takes part in merge level l (1-based)
+    uint32_t level_grid[24];     // upper bound of the merge tiles of level l
+    uint64_t level_products[24]; // upper bound of the products that take part in level l
+    int max_level;
+    uint64_t unit_bound;         // upper bound of the wave's chunks
+    uint64_t products_bound;     // upper bound of the wave's products
 };
 // aseq[e] (one u32 per nonzero of A, written for long rows only) = arrival number of the first product of entry e
 void launch_long_prefix(const DevCsr& a, int64_t row_begin, const uint32_t* rows_list, uint32_t n_rows,
                         const uint32_t* b_len, uint32_t* aseq, cudaStream_t s);
-// t_ptr/t_col/t_val: scratch CSR the finished rows are written to; row_nnz: their nnz.  stages (nullable): called
-// around the sort, the merge levels and the sums so the engine can time them.  Returns the kernels launched.
+// stages (nullable): called around the sort, the merge levels and the count so the engine can time them.  All return
+// the number of kernels launched.
 struct LongStages {
     std::function<void(const char*, uint32_t, uint64_t)> on;   // stage name, grid, products it touches
     std::function<void()> off;
 };
-uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
-                          const uint32_t* aseq, const LongWave& w, const int64_t* t_ptr, int32_t* t_col, double* t_val,
-                          uint32_t* row_nnz, PlanCounters* ctr, cudaStream_t s, const LongStages* stages = nullptr);
+struct CopyDst;
+uint32_t launch_long_setup(const LongPlan& P, const uint32_t* flops, PlanCounters* ctr, cudaStream_t s);
+uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* aseq, const LongPlan& P,
+                          const LongWaveRange& w, uint32_t* row_nnz, cudaStream_t s, const LongStages* stages = nullptr);
+uint32_t launch_long_heads_scan(const LongPlan& P, PlanCounters* ctr, cudaStream_t s);
+uint32_t launch_long_reduce(const LongPlan& P, const int64_t* c_ptr, const CopyDst& dst, cudaStream_t s);
 // long rows of a product with few columns (B.cols <= DENSE_MAX_COLS): dense accumulator in shared memory, B rows applied
 // one after the other in ascending k (longrow.cu)
 constexpr int64_t DENSE_MAX_COLS = 16384;

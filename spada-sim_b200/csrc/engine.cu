@@ -892,11 +892,14 @@ struct spada_b200_shard {
     int64_t *t_lp = nullptr, *t_idx = nullptr;
     uint64_t* t_state = nullptr;
     size_t t_bound = 0;
+    // long rows: tables of the whole list, the pong buffer of one wave, merge-tile descriptors
     uint32_t *w_p = nullptr, *w_u = nullptr, *w_heads = nullptr, *w_unit_row = nullptr;
     uint64_t* w_tiles = nullptr;
     int64_t *w_prod_off = nullptr, *w_unit_off = nullptr, *w_hoff = nullptr;
-    int32_t* w_col[2] = {nullptr, nullptr};
-    double* w_val[2] = {nullptr, nullptr};
+    int32_t* w_col = nullptr;
+    double* w_val = nullptr;
+    bool dense_long = false;
+    LongPlan long_plan{};
     std::vector<LaunchRec> recs;
     cudaStream_t rec_stream = nullptr;
     uint32_t kernels = 0;
@@ -927,10 +930,8 @@ struct spada_b200_shard {
         for (auto pp : i64s) { dfree(h, *pp); *pp = nullptr; }
         dfree(h, d_tcol); d_tcol = nullptr;
         dfree(h, d_tval); d_tval = nullptr;
-        for (int i = 0; i < 2; ++i) {
-            dfree(h, w_col[i]); w_col[i] = nullptr;
-            dfree(h, w_val[i]); w_val[i] = nullptr;
-        }
+        dfree(h, w_col); w_col = nullptr;
+        dfree(h, w_val); w_val = nullptr;
     }
 };
 
@@ -1005,7 +1006,7 @@ std::vector<WavePlan> plan_waves(const PlanCounters& pc, uint64_t budget_product
                     grid += pc_.ubound;
                     prods += pc_.pbound;
                 }
-            P.level_lo[l] = first - P.lo;
+            P.level_lo[l] = first;
             P.level_grid[l] = (uint32_t)grid;
             P.level_products[l] = prods;
         }
@@ -1173,19 +1174,20 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
 
     // long rows: wave plan + workspace
     std::vector<WavePlan> waves;
-    uint64_t wave_products = 0, wave_units = 0, wave_rows = 0;
+    uint64_t wave_products = 0, wave_units = 0;
     // few output columns: the long rows keep a dense accumulator in shared memory instead (no merge levels)
     const bool dense_long = S->n_long && dense_rows_fit(B.cols) && !getenv("SPADA_B200_NO_DENSE");
+    S->dense_long = dense_long;
+    const uint64_t all_units = S->long_products / LONG_UNIT + S->n_long;   // upper bound of the chunks of all long rows
     if (S->n_long && !dense_long) {
-        waves = plan_waves(pc, std::max<uint64_t>(h->long_ws_budget / 24, (uint64_t)LONG_UNIT));
+        waves = plan_waves(pc, std::max<uint64_t>(h->long_ws_budget / 12, (uint64_t)LONG_UNIT));
         for (auto& w : waves) {
             wave_products = std::max(wave_products, w.products_bound);
             wave_units = std::max(wave_units, w.unit_bound);
-            wave_rows = std::max<uint64_t>(wave_rows, w.hi - w.lo);
         }
     }
     {
-        const double need = (double)S->scratch_products * 12.0 + (double)wave_products * 24.0 +
+        const double need = (double)S->scratch_products * 12.0 + (double)wave_products * 12.0 +
                             (fused ? (double)pc.total_products * 12.0 : 0.0);
         if (need > 0.92 * (double)h->dev_total_mem) {
             shard_free(S);
@@ -1219,19 +1221,17 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
     }
     if (S->n_long && !dense_long) {
         TRY(dalloc(h, &S->d_aseq, (size_t)std::max<int64_t>(A.nnz, 1)));
-        TRY(dalloc(h, &S->w_p, (size_t)wave_rows));
-        TRY(dalloc(h, &S->w_u, (size_t)wave_rows));
-        TRY(dalloc(h, &S->w_prod_off, (size_t)wave_rows + 1));
-        TRY(dalloc(h, &S->w_unit_off, (size_t)wave_rows + 1));
-        TRY(dalloc(h, &S->w_heads, (size_t)wave_units));
-        TRY(dalloc(h, &S->w_unit_row, (size_t)wave_units));
+        TRY(dalloc(h, &S->w_p, (size_t)S->n_long));
+        TRY(dalloc(h, &S->w_u, (size_t)S->n_long));
+        TRY(dalloc(h, &S->w_prod_off, (size_t)S->n_long + 1));
+        TRY(dalloc(h, &S->w_unit_off, (size_t)S->n_long + 1));
+        TRY(dalloc(h, &S->w_heads, (size_t)all_units));
+        TRY(dalloc(h, &S->w_unit_row, (size_t)all_units));
+        TRY(dalloc(h, &S->w_hoff, (size_t)all_units + 1));
         TRY(dalloc(h, &S->w_tiles, (size_t)wave_units * 4));   // 32-byte merge-tile descriptors
-        TRY(dalloc(h, &S->w_hoff, (size_t)wave_units + 1));
-        TRY(dalloc(h, &S->d_tiles_side, scan_tile_state_words((int64_t)std::max<uint64_t>(wave_units, wave_rows))));
-        for (int i = 0; i < 2; ++i) {
-            TRY(dalloc(h, &S->w_col[i], (size_t)wave_products));
-            TRY(dalloc(h, &S->w_val[i], (size_t)wave_products));
-        }
+        TRY(dalloc(h, &S->d_tiles_side, scan_tile_state_words((int64_t)std::max<uint64_t>(all_units, S->n_long))));
+        TRY(dalloc(h, &S->w_col, (size_t)wave_products));
+        TRY(dalloc(h, &S->w_val, (size_t)wave_products));
     }
 
     // ---- first pass: every scratch row is expanded, sorted and summed exactly once ---------------------------
@@ -1255,47 +1255,58 @@ int shard_begin(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr
         CUT(cudaGetLastError());
         S->kernels += 1;
         S->end_rec();
+        LongPlan& LP = S->long_plan;
+        LP.rows_list = long_list;
+        LP.n_rows = S->n_long;
+        LP.unit_bound = all_units;
+        LP.p = S->w_p;
+        LP.u = S->w_u;
+        LP.prod_off = S->w_prod_off;
+        LP.unit_off = S->w_unit_off;
+        LP.unit_row = S->w_unit_row;
+        LP.unit_heads = S->w_heads;
+        LP.unit_hoff = S->w_hoff;
+        LP.t_ptr = S->d_prod_ptr;
+        LP.s_col = S->d_tcol;
+        LP.s_val = S->d_tval;
+        LP.pong_col = S->w_col;
+        LP.pong_val = S->w_val;
+        LP.tiles = S->w_tiles;
+        LP.tile_state = S->d_tiles_side;
+        S->begin_rec("long_setup", 2, (S->n_long + 255) / 256, S->n_long, 0, sh);
+        S->kernels += launch_long_setup(LP, S->d_flops, h->d_ctr_side, sh);
+        CUT(cudaGetLastError());
+        S->end_rec();
+        const bool detail = waves.size() <= 2;   // per-stage records; beyond two waves one record for all of them
         int wi = 0;
         for (auto& w : waves) {
-            LongWave W{};
-            W.rows_list = long_list + w.lo;
-            W.n_rows = w.hi - w.lo;
+            LongWaveRange W{};
+            W.lo = w.lo;
+            W.hi = w.hi;
             memcpy(W.level_lo, w.level_lo, sizeof(W.level_lo));
             memcpy(W.level_grid, w.level_grid, sizeof(W.level_grid));
             memcpy(W.level_products, w.level_products, sizeof(W.level_products));
             W.products_bound = w.products_bound;
             W.max_level = w.max_level;
             W.unit_bound = w.unit_bound;
-            W.p = S->w_p;
-            W.u = S->w_u;
-            W.prod_off = S->w_prod_off;
-            W.unit_off = S->w_unit_off;
-            W.unit_heads = S->w_heads;
-            W.unit_row = S->w_unit_row;
-            W.tiles = S->w_tiles;
-            W.unit_hoff = S->w_hoff;
-            for (int i = 0; i < 2; ++i) {
-                W.col[i] = S->w_col[i];
-                W.val[i] = S->w_val[i];
-            }
-            W.tile_state = S->d_tiles_side;
             LongStages stages;
             stages.on = [&](const char* what, uint32_t grid, uint64_t products) {
                 char name[32];
                 if (waves.size() > 1) snprintf(name, sizeof(name), "%s#%d", what, wi);
                 else snprintf(name, sizeof(name), "%s", what);
-                if (waves.size() <= 2) S->begin_rec(name, 2, grid, W.n_rows, products, sh);
+                if (detail) S->begin_rec(name, 2, grid, W.hi - W.lo, products, sh);
             };
             stages.off = [&]() {
-                if (waves.size() <= 2) S->end_rec();
+                if (detail) S->end_rec();
             };
-            if (waves.size() > 2 && wi == 0) S->begin_rec("long_waves", 2, (uint32_t)w.unit_bound, S->n_long, S->long_products, sh);
-            S->kernels += launch_long_wave(A, B, (int64_t)row_begin, S->d_flops, S->d_aseq, W, S->d_prod_ptr, S->d_tcol,
-                                           S->d_tval, S->d_nnz, h->d_ctr_side, sh, &stages);
+            if (!detail && wi == 0) S->begin_rec("long_waves", 2, (uint32_t)w.unit_bound, S->n_long, S->long_products, sh);
+            S->kernels += launch_long_wave(A, B, (int64_t)row_begin, S->d_aseq, LP, W, S->d_nnz, sh, &stages);
             CUT(cudaGetLastError());
             ++wi;
         }
-        if (waves.size() > 2) S->end_rec();
+        if (!detail) S->end_rec();
+        S->kernels += launch_long_heads_scan(LP, h->d_ctr_side, sh);
+        CUT(cudaGetLastError());
     }
     for (int bnum = fused ? 6 : 1; bnum <= 8; ++bnum) {
         const uint32_t rows = pc.bin_rows[bnum];
@@ -1397,12 +1408,20 @@ int shard_finish(spada_b200_shard* S, const CopyDst* dst, const RowPtrDst* row_p
         S->begin_rec(D.n > 1 ? "copy_gather" : "copy_rows", 3, (uint32_t)((m + 7) / 8), (uint64_t)m, S->scratch_products);
         launch_copy_rows(S->d_flops, m, S->scratch_lo, ESC_MAX_PRODUCTS, S->d_prod_ptr, S->d_tcol, S->d_tval, R->ptr, D, s);
         S->kernels += 1;
-        if (S->n_long) {   // long rows: one CTA per row
+        if (S->n_long && S->dense_long) {   // long rows finished by the dense path: one CTA per scratch row
             launch_copy_rows_list(S->perm_of(BIN_LONG0), S->n_long, S->d_prod_ptr, S->d_tcol, S->d_tval, R->ptr, D, s);
             S->kernels += 1;
         }
         CUT(cudaGetLastError());
         S->end_rec();
+        if (S->n_long && !S->dense_long) {
+            // long rows: their scratch rows hold the sorted products; the left-to-right sums go straight into C
+            S->begin_rec(D.n > 1 ? "long_reduce_gather" : "long_reduce", 3, (uint32_t)S->long_plan.unit_bound, S->n_long,
+                         S->long_products);
+            S->kernels += launch_long_reduce(S->long_plan, R->ptr, D, s);
+            CUT(cudaGetLastError());
+            S->end_rec();
+        }
     }
     if (dst && row_ptr_dst) {
         S->begin_rec("row_ptr_gather", 3, (uint32_t)((m + 255) / 256), (uint64_t)m, 0);

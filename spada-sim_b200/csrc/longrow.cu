@@ -21,10 +21,15 @@
 //           partition on the two runs (binary search on a diagonal, ties X-before-Y = earlier k first, which
 //           keeps equal columns in arrival order: a stable merge), both input slices staged in shared memory,
 //           every thread merges 16 outputs serially, the tile is written back with coalesced stores.
-//   sum     heads (first entry of every run of equal columns) are counted per 4096 outputs and scanned; every head
-//           sums its run left to right and the finished row goes to its scratch row, nnz recorded.
+//   sum     heads (first entry of every run of equal columns) are counted per 4096 outputs (that is the row's nnz);
+//           after the row_ptr scan every head sums its run left to right straight into C -- and, in a sharded run,
+//           into every peer's C: for long rows the sums ARE the placement.
 //
-// HBM traffic per product: 12 B written by the sort, 24 B per merge level, 4 + 24 B for the sums.
+// Buffers: a long row's scratch row (capacity = its products) holds its sorted products; the merge levels ping-pong
+// between it and a pong buffer that only has to hold one WAVE of rows.  A row with L levels starts in buffer L & 1
+// (0 = scratch row, 1 = pong), so that its last level lands in the scratch row.
+//
+// HBM traffic per product: 12 B written by the sort, 24 B per merge level, 4 B for the count, 12 + 12 B for the sums.
 #include <algorithm>
 #include <cstdio>
 
@@ -96,30 +101,39 @@ k_long_prefix(DevCsr a, int64_t row_begin, const uint32_t* __restrict__ rows_lis
 
 // which row of the wave a chunk / tile belongs to, found once per CTA by warp 0
 struct UnitInfo {
-    uint32_t i;        // index inside the wave
+    uint32_t i;        // index inside the long-row list
     uint32_t row;      // row of A (relative to row_begin)
     uint32_t P;        // products of the row
     uint32_t t;        // chunk / tile number inside the row
-    int64_t base;      // start of the row inside the ping-pong buffers
+    int64_t base0;     // start of the row's scratch row (buffer 0)
+    int64_t base1;     // start of the row inside the pong buffer of its wave (buffer 1)
 };
-__device__ __forceinline__ bool find_unit(int64_t g, const uint32_t* __restrict__ unit_row,
-                                          const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
-                                          const uint32_t* __restrict__ p, const uint32_t* __restrict__ rows_list, uint32_t n,
-                                          UnitInfo* s_info) {
-    if (g >= unit_off[n]) return false;   // uniform over the CTA
+// the tables of the whole long-row list + the two buffers (see the header comment)
+struct LongDev {
+    const uint32_t* rows_list;
+    const uint32_t* p;
+    const uint32_t* unit_row;
+    const int64_t* unit_off;
+    const int64_t* prod_off;
+    const int64_t* t_ptr;
+    int32_t* col[2];
+    double* val[2];
+    uint32_t wave_lo;   // first list index of the wave in flight (origin of the pong buffer)
+};
+__device__ __forceinline__ void find_unit(int64_t g, const LongDev& D, UnitInfo* s_info) {
     if (threadIdx.x == 0) {
-        const uint32_t i = unit_row[g];
+        const uint32_t i = D.unit_row[g];
         s_info->i = i;
-        s_info->row = rows_list[i];
-        s_info->P = p[i];
-        s_info->t = (uint32_t)(g - unit_off[i]);
-        s_info->base = prod_off[i];
+        s_info->row = D.rows_list[i];
+        s_info->P = D.p[i];
+        s_info->t = (uint32_t)(g - D.unit_off[i]);
+        s_info->base0 = D.t_ptr[s_info->row];
+        s_info->base1 = D.prod_off[i] - D.prod_off[D.wave_lo];
     }
     __syncthreads();
-    return true;
 }
 
-// unit_row[g] = row (index inside the wave) of chunk / tile g: one binary search per unit, once per wave
+// unit_row[g] = row (index inside the list) of chunk / tile g: one binary search per unit
 __global__ void k_long_units(const int64_t* __restrict__ unit_off, uint32_t n, uint32_t* __restrict__ unit_row) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= unit_off[n]) return;
@@ -136,10 +150,7 @@ __global__ void k_long_units(const int64_t* __restrict__ unit_off, uint32_t n, u
 // (columns up to 2^21 without 64-bit keys: the 64-bit network measured 3.2x slower per product)
 template <typename K, int G>
 __global__ void __launch_bounds__(LR_THREADS)
-k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restrict__ rows_list, uint32_t n,
-                  const uint32_t* __restrict__ p, const uint32_t* __restrict__ unit_row, const int64_t* __restrict__ unit_off,
-                  const int64_t* __restrict__ prod_off, const uint32_t* __restrict__ aseq,
-                  int32_t* __restrict__ out_col, double* __restrict__ out_val) {
+k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_hi, const uint32_t* __restrict__ aseq) {
     constexpr int N = LONG_UNIT;
     constexpr int SBG = Log2<N / G>::v;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -148,8 +159,13 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restr
     __shared__ CtaStage st;
     __shared__ UnitInfo info;
     __shared__ int64_t s_e[2];
-    if (!find_unit(blockIdx.x, unit_row, unit_off, prod_off, p, rows_list, n, &info)) return;
+    const int64_t g = D.unit_off[D.wave_lo] + blockIdx.x;
+    if (g >= D.unit_off[i_hi]) return;   // uniform over the CTA
+    find_unit(g, D, &info);
     const int lane = lane_id();
+    const int buf = long_levels(info.P) & 1;   // where the row's chunks go so that its last level ends in the scratch row
+    int32_t* __restrict__ out_col = D.col[buf];
+    double* __restrict__ out_val = D.val[buf];
     const uint32_t s0 = info.t << LONG_UNIT_LOG;
     const uint32_t cnt = info.P - s0 < (uint32_t)N ? info.P - s0 : (uint32_t)N;
     const int64_t a0 = a.ptr[row_begin + info.row], a1 = a.ptr[row_begin + info.row + 1];
@@ -226,7 +242,7 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __restr
     for (int t = (int)cnt + threadIdx.x; t < N; t += LR_THREADS) keys[t] = KeyTraits<K>::sentinel;
     __syncthreads();
     bitonic_cta_sort<K, N, G>(keys);
-    const int64_t dst = info.base + s0;
+    const int64_t dst = (buf ? info.base1 : info.base0) + s0;
     if constexpr (G == 2) {
         cta_merge_groups2<N>(keys, vals, (int)cnt);
         for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
@@ -269,52 +285,54 @@ struct MergeStage {
     double val[LONG_UNIT + MG_PAD];
 };
 struct __align__(16) MergeTile {
-    int64_t ax, ay;       // element index (inside the buffers) of the first X / Y element the tile consumes
-    int64_t out;          // where the tile's outputs go
-    int32_t cx, cy;       // elements taken from X and from Y
+    int64_t ax, ay;       // element index (inside the input buffer) of the first X / Y element the tile consumes
+    int64_t out;          // where the tile's outputs go (inside the other buffer)
+    int32_t cx, cy;       // elements taken from X and from Y; cy < 0: the input is buffer 1 and cy = -1 - count
 };
 
 __global__ void __launch_bounds__(256)
-k_long_partition(const uint32_t* __restrict__ unit_row, uint32_t n, uint32_t i_lo, int level, const uint32_t* __restrict__ p,
-                 const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
-                 const int32_t* __restrict__ in_col, MergeTile* __restrict__ tiles) {
-    const int64_t g0 = unit_off[i_lo];
+k_long_partition(LongDev D, uint32_t i_lo, uint32_t i_hi, int level, MergeTile* __restrict__ tiles) {
+    const int64_t g0 = D.unit_off[i_lo];
     const int64_t g = g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= unit_off[n]) return;
-    const uint32_t i = unit_row[g];
-    const uint32_t P = p[i];
-    const int64_t base = prod_off[i];
+    if (g >= D.unit_off[i_hi]) return;
+    const uint32_t i = D.unit_row[g];
+    const uint32_t P = D.p[i];
+    const int L = long_levels(P);
     MergeTile T{};
-    if (level <= long_levels(P)) {   // rows finished by an earlier level take no part (cannot happen inside level bins)
+    if (level <= L) {   // rows finished by an earlier level take no part (cannot happen inside level bins)
+        const int bin = (L - level + 1) & 1;   // buffer the level reads; it writes the other one
+        const int64_t base[2] = {D.t_ptr[D.rows_list[i]], D.prod_off[i] - D.prod_off[D.wave_lo]};
         const uint64_t RL = (uint64_t)LONG_UNIT << (level - 1);
-        const uint64_t o0 = (uint64_t)(g - unit_off[i]) << LONG_UNIT_LOG;
+        const uint64_t o0 = (uint64_t)(g - D.unit_off[i]) << LONG_UNIT_LOG;
         const uint64_t o1 = o0 + LONG_UNIT < P ? o0 + LONG_UNIT : P;
         const uint64_t pbase = o0 / (2 * RL) * (2 * RL);
         const uint64_t xe = pbase + RL < P ? pbase + RL : P;
         const uint64_t ye = pbase + 2 * RL < P ? pbase + 2 * RL : P;
         const int nx = (int)(xe - pbase), ny = (int)(ye - xe);
-        const int32_t* X = in_col + base + pbase;
-        const int32_t* Y = in_col + base + xe;
+        const int32_t* X = D.col[bin] + base[bin] + pbase;
+        const int32_t* Y = D.col[bin] + base[bin] + xe;
         const int d0 = (int)(o0 - pbase), d1 = (int)(o1 - pbase);
         const int i0 = merge_path(X, nx, Y, ny, d0);
         const int i1 = (d1 == nx + ny) ? nx : merge_path(X, nx, Y, ny, d1);
-        T.ax = base + (int64_t)pbase + i0;
-        T.ay = base + (int64_t)xe + (d0 - i0);
-        T.out = base + (int64_t)o0;
+        T.ax = base[bin] + (int64_t)pbase + i0;
+        T.ay = base[bin] + (int64_t)xe + (d0 - i0);
+        T.out = base[bin ^ 1] + (int64_t)o0;
         T.cx = i1 - i0;
-        T.cy = (d1 - i1) - (d0 - i0);
+        const int cy = (d1 - i1) - (d0 - i0);
+        T.cy = bin ? -1 - cy : cy;
+    } else {
+        T.cx = 0;
+        T.cy = 0;
     }
     tiles[g - g0] = T;
 }
 
 __global__ void __launch_bounds__(MG_THREADS, 2)
-k_long_merge(const MergeTile* __restrict__ tiles, int64_t n_tiles_bound, const int64_t* __restrict__ unit_off, uint32_t n,
-             uint32_t i_lo, const int32_t* __restrict__ in_col, const double* __restrict__ in_val,
-             int32_t* __restrict__ out_col, double* __restrict__ out_val) {
-    extern __shared__ __align__(128) unsigned char s_raw[];
+k_long_merge(const MergeTile* __restrict__ tiles, LongDev D, uint32_t i_lo, uint32_t i_hi) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
     MergeStage* stage = reinterpret_cast<MergeStage*>(s_raw);
     __shared__ __align__(8) uint64_t bar[2];
-    const int64_t n_tiles = unit_off[n] - unit_off[i_lo];
+    const int64_t n_tiles = D.unit_off[i_hi] - D.unit_off[i_lo];
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -334,8 +352,18 @@ k_long_merge(const MergeTile* __restrict__ tiles, int64_t n_tiles_bound, const i
         xv = dxv;
         yv = nxv + dyv;
     };
-    auto issue = [&](const MergeTile& T, int sidx) {   // thread 0 only
+    // descriptors carry the input buffer in the sign of cy
+    auto decode = [](MergeTile T, int& bin) {
+        bin = T.cy < 0;
+        if (bin) T.cy = -1 - T.cy;
+        return T;
+    };
+    auto issue = [&](const MergeTile& T0, int sidx) {   // thread 0 only
+        int bin;
+        const MergeTile T = decode(T0, bin);
         if (T.cx + T.cy == 0) return;
+        const int32_t* in_col = D.col[bin];
+        const double* in_val = D.val[bin];
         int xc, yc, xv, yv, nxc, nyc, nxv, nyv;
         layout(T, xc, yc, xv, yv, nxc, nyc, nxv, nyv);
         MergeStage& st = stage[sidx];
@@ -359,7 +387,10 @@ k_long_merge(const MergeTile* __restrict__ tiles, int64_t n_tiles_bound, const i
     uint32_t phase[2] = {0u, 0u};
     for (int k = 0; t < n_tiles; ++k, t += G) {
         const int cur = k & 1;
-        const MergeTile T = tiles[t];
+        int bin;
+        const MergeTile T = decode(tiles[t], bin);
+        int32_t* __restrict__ out_col = D.col[bin ^ 1];
+        double* __restrict__ out_val = D.val[bin ^ 1];
         MergeTile ahead{};   // descriptor of the tile two ahead: loaded now, used when this stage is free again
         const bool has_ahead = threadIdx.x == 0 && t + 2 * G < n_tiles;
         if (has_ahead) ahead = tiles[t + 2 * G];
@@ -423,15 +454,16 @@ k_long_merge(const MergeTile* __restrict__ tiles, int64_t n_tiles_bound, const i
 }
 
 // ---- sums ---------------------------------------------------------------------------------------------------
-// heads (first entry of a run of equal columns) that start inside every tile of 4096 sorted products
+// heads (first entry of a run of equal columns) that start inside every tile of 4096 sorted products; their sum over a
+// row is the row's nnz (integer atomics: deterministic)
 __global__ void __launch_bounds__(LR_THREADS)
-k_long_count(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t* __restrict__ p,
-             const uint32_t* __restrict__ unit_row, const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
-             const int32_t* __restrict__ col0, const int32_t* __restrict__ col1, uint32_t* __restrict__ unit_heads) {
+k_long_count(LongDev D, uint32_t i_hi, uint32_t* __restrict__ unit_heads, uint32_t* __restrict__ row_nnz) {
     __shared__ UnitInfo info;
     __shared__ int s_w[LR_THREADS / 32];
-    if (!find_unit(blockIdx.x, unit_row, unit_off, prod_off, p, rows_list, n, &info)) return;
-    const int32_t* col = ((long_levels(info.P) & 1) ? col1 : col0) + info.base;
+    const int64_t g = D.unit_off[D.wave_lo] + blockIdx.x;
+    if (g >= D.unit_off[i_hi]) return;
+    find_unit(g, D, &info);
+    const int32_t* col = D.col[0] + info.base0;   // every row ends in its scratch row
     const uint32_t o0 = info.t << LONG_UNIT_LOG;
     const uint32_t o1 = info.P - o0 < (uint32_t)LONG_UNIT ? info.P : o0 + LONG_UNIT;
     int cnt = 0;
@@ -444,7 +476,8 @@ k_long_count(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t*
     if (threadIdx.x == 0) {
         int t = 0;
         for (int w = 0; w < LR_THREADS / 32; ++w) t += s_w[w];
-        unit_heads[blockIdx.x] = (uint32_t)t;
+        unit_heads[g] = (uint32_t)t;
+        atomicAdd(row_nnz + info.row, (uint32_t)t);
     }
 }
 
@@ -454,12 +487,29 @@ k_long_count(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t*
 // heads of the tile run side by side: warp w owns the positions [512 w, 512 (w + 1)), lanes interleaved.  A run that
 // leaves the tile (at most one: the tile's last) is streamed by the whole CTA, 4096 products at a time, with one
 // thread doing the adds in order -- the diagonal of A x A^T is one run of nnz(A row) products.
+// ND = 1: one destination (this GPU's C); otherwise every destination of dst_all (sharded runs: the peers' C too)
+template <int ND>
+__device__ __forceinline__ void reduce_store_col(const CopyDst& dst_all, int64_t o, int32_t c) {
+    if (ND == 1) {
+        st_out(dst_all.col[0] + o, c);
+    } else {
+#pragma unroll 1
+        for (int d = dst_all.n - 1; d >= 0; --d) st_out(dst_all.col[d] + o, c);
+    }
+}
+template <int ND>
+__device__ __forceinline__ void reduce_store_val(const CopyDst& dst_all, int64_t o, double v) {
+    if (ND == 1) {
+        st_out(dst_all.val[0] + o, v);
+    } else {
+#pragma unroll 1
+        for (int d = dst_all.n - 1; d >= 0; --d) st_out(dst_all.val[d] + o, v);
+    }
+}
+
+template <int ND>
 __global__ void __launch_bounds__(LR_THREADS)
-k_long_reduce(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t* __restrict__ p,
-              const uint32_t* __restrict__ unit_row, const int64_t* __restrict__ unit_off, const int64_t* __restrict__ prod_off,
-              const int32_t* __restrict__ col0, const int32_t* __restrict__ col1, const double* __restrict__ val0,
-              const double* __restrict__ val1, const int64_t* __restrict__ unit_hoff, const int64_t* __restrict__ t_ptr,
-              int32_t* __restrict__ t_col, double* __restrict__ t_val, uint32_t* __restrict__ row_nnz) {
+k_long_reduce(LongDev D, uint32_t n, const int64_t* __restrict__ unit_hoff, const int64_t* __restrict__ c_ptr, CopyDst dst_all) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     int32_t* s_col = reinterpret_cast<int32_t*>(s_raw);
     double* s_val = reinterpret_cast<double*>(s_raw + sizeof(int32_t) * LONG_UNIT);
@@ -471,20 +521,19 @@ k_long_reduce(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t
     __shared__ int s_end;
     // rows are listed by ascending product count: the tiles are taken from the far end, so that the longest runs
     // (strictly sequential sums, e.g. the diagonal of A x A^T) start first and the short tiles fill in beside them
-    const int64_t n_units = unit_off[n];
+    const int64_t n_units = D.unit_off[n];
     const int64_t unit = n_units - 1 - (int64_t)blockIdx.x;
     if (unit < 0) return;
-    find_unit(unit, unit_row, unit_off, prod_off, p, rows_list, n, &info);
+    find_unit(unit, D, &info);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const bool odd = long_levels(info.P) & 1;
-    const int32_t* col = (odd ? col1 : col0) + info.base;
-    const double* val = (odd ? val1 : val0) + info.base;
+    const int32_t* __restrict__ col = D.col[0] + info.base0;
+    const double* __restrict__ val = D.val[0] + info.base0;
     const uint32_t P = info.P;
     const uint32_t o0 = info.t << LONG_UNIT_LOG;
     const int cnt = (int)(P - o0 < (uint32_t)LONG_UNIT ? P - o0 : (uint32_t)LONG_UNIT);
-    const int64_t row_h0 = unit_hoff[unit_off[info.i]];
-    const int64_t dst = t_ptr[info.row] + (unit_hoff[unit] - row_h0);
-    if (info.t == 0 && threadIdx.x == 0) row_nnz[info.row] = (uint32_t)(unit_hoff[unit_off[info.i + 1]] - row_h0);
+    const int64_t row_h0 = unit_hoff[D.unit_off[info.i]];
+    const int64_t dst = c_ptr[info.row] + (unit_hoff[unit] - row_h0) +
+                        shard_offset(dst_all.off, dst_all.shard_nnz, dst_all.shard_idx);
     for (int t = threadIdx.x; t < cnt; t += LR_THREADS) {
         s_col[t] = col[o0 + t];
         s_val[t] = val[o0 + t];
@@ -527,12 +576,12 @@ k_long_reduce(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t
                 ++j;
             }
             const int o = rank + __popc(hm[it] & ((1u << lane) - 1u));
-            st_out(t_col + dst + o, c);
+            reduce_store_col<ND>(dst_all, dst + o, c);
             if (j == cnt && o0 + (uint32_t)cnt < P) {   // the run may go on in the next tile: finished below
                 s_open_rank = o;
                 s_open_sum = sum;
             } else {
-                st_out(t_val + dst + o, sum);
+                reduce_store_val<ND>(dst_all, dst + o, sum);
             }
         }
         rank += __popc(hm[it]);
@@ -573,7 +622,7 @@ k_long_reduce(const uint32_t* __restrict__ rows_list, uint32_t n, const uint32_t
         }
         if (e < len) break;   // uniform: s_end is shared
     }
-    if (threadIdx.x == 0) st_out(t_val + dst + s_open_rank, sum);
+    if (threadIdx.x == 0) reduce_store_val<ND>(dst_all, dst + s_open_rank, sum);
 }
 
 // ---- narrow outputs: long rows of a product with few columns ------------------------------------------------
@@ -696,40 +745,59 @@ void launch_long_prefix(const DevCsr& a, int64_t row_begin, const uint32_t* rows
     if (n_rows) k_long_prefix<<<n_rows, LR_THREADS, 0, s>>>(a, row_begin, rows_list, b_len, aseq);
 }
 
+static LongDev long_dev(const LongPlan& P, uint32_t wave_lo) {
+    LongDev D{};
+    D.rows_list = P.rows_list;
+    D.p = P.p;
+    D.unit_row = P.unit_row;
+    D.unit_off = P.unit_off;
+    D.prod_off = P.prod_off;
+    D.t_ptr = P.t_ptr;
+    D.col[0] = P.s_col;
+    D.val[0] = P.s_val;
+    D.col[1] = P.pong_col;
+    D.val[1] = P.pong_val;
+    D.wave_lo = wave_lo;
+    return D;
+}
+
+// tables of the whole long-row list: products and chunks per row, their prefix sums, chunk -> row
+uint32_t launch_long_setup(const LongPlan& P, const uint32_t* flops, PlanCounters* ctr, cudaStream_t s) {
+    if (P.n_rows == 0) return 0;
+    k_long_setup<<<(P.n_rows + 255) / 256, 256, 0, s>>>(P.rows_list, P.n_rows, flops, P.p, P.u);
+    launch_scan_u32_i64(P.p, P.n_rows, P.prod_off, P.tile_state, ctr, s);
+    launch_scan_u32_i64(P.u, P.n_rows, P.unit_off, P.tile_state, ctr, s);
+    k_long_units<<<(unsigned)((P.unit_bound + 255) / 256), 256, 0, s>>>(P.unit_off, P.n_rows, P.unit_row);
+    cudaMemsetAsync(P.unit_heads, 0, (size_t)P.unit_bound * sizeof(uint32_t), s);
+    return 5;
+}
+
 template <typename K, int G>
-static void chunk_sort_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* aseq, const LongWave& w,
-                              cudaStream_t s) {
+static void chunk_sort_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* aseq, const LongDev& D,
+                              const LongWaveRange& w, cudaStream_t s) {
     const size_t smem = (sizeof(K) + sizeof(double)) * LONG_UNIT;
     static PerDeviceOnce attr;
     if (attr.first())
         cudaFuncSetAttribute(k_long_chunk_sort<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_long_chunk_sort<K, G><<<(unsigned)w.unit_bound, LR_THREADS, smem, s>>>(a, b, row_begin, w.rows_list, w.n_rows, w.p,
-                                                                         w.unit_row, w.unit_off, w.prod_off, aseq, w.col[0],
-                                                                         w.val[0]);
+    k_long_chunk_sort<K, G><<<(unsigned)w.unit_bound, LR_THREADS, smem, s>>>(a, b, row_begin, D, w.hi, aseq);
 }
 
-uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* flops,
-                          const uint32_t* aseq, const LongWave& w, const int64_t* t_ptr, int32_t* t_col, double* t_val,
-                          uint32_t* row_nnz, PlanCounters* ctr, cudaStream_t s, const LongStages* stages) {
-    if (w.n_rows == 0) return 0;
+// one wave: chunk sorts, merge levels (the rows of the wave end in their scratch rows), head counts -> row_nnz
+uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* aseq, const LongPlan& P,
+                          const LongWaveRange& w, uint32_t* row_nnz, cudaStream_t s, const LongStages* stages) {
+    if (w.hi <= w.lo) return 0;
     uint32_t kernels = 0;
     auto on = [&](const char* what, uint32_t grid, uint64_t products) { if (stages) stages->on(what, grid, products); };
     auto off = [&]() { if (stages) stages->off(); };
-    on("long_setup", (w.n_rows + 255) / 256, 0);
-    k_long_setup<<<(w.n_rows + 255) / 256, 256, 0, s>>>(w.rows_list, w.n_rows, flops, w.p, w.u);
-    launch_scan_u32_i64(w.p, w.n_rows, w.prod_off, w.tile_state, ctr, s);
-    launch_scan_u32_i64(w.u, w.n_rows, w.unit_off, w.tile_state, ctr, s);
-    k_long_units<<<(unsigned)((w.unit_bound + 255) / 256), 256, 0, s>>>(w.unit_off, w.n_rows, w.unit_row);
-    off();
+    const LongDev D = long_dev(P, w.lo);
     on("long_sort", (uint32_t)w.unit_bound, w.products_bound);
     // sort: 32-bit (column << 12 | arrival) keys whenever they fit
-    if ((uint64_t)b.cols <= (1ull << (32 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 1>(a, b, row_begin, aseq, w, s);
-    else if ((uint64_t)b.cols <= (1ull << (33 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 2>(a, b, row_begin, aseq, w, s);
-    else chunk_sort_launch<uint64_t, 1>(a, b, row_begin, aseq, w, s);
-    kernels += 5;
+    if ((uint64_t)b.cols <= (1ull << (32 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 1>(a, b, row_begin, aseq, D, w, s);
+    else if ((uint64_t)b.cols <= (1ull << (33 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 2>(a, b, row_begin, aseq, D, w, s);
+    else chunk_sort_launch<uint64_t, 1>(a, b, row_begin, aseq, D, w, s);
+    kernels += 1;
     off();
     // merge levels: rows are listed by ascending level count, level l takes the list from level_lo[l] on
-    const size_t msmem = (sizeof(int32_t) + sizeof(double)) * LONG_UNIT;
     const size_t mgsmem = 2 * sizeof(MergeStage);
     static PerDeviceOnce attr;
     if (attr.first()) cudaFuncSetAttribute(k_long_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mgsmem);
@@ -740,34 +808,46 @@ uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         merge_ctas = 2 * sms;
     }
+    MergeTile* tiles = reinterpret_cast<MergeTile*>(P.tiles);
     for (int l = 1; l <= w.max_level; ++l) {
         if (w.level_grid[l] == 0) continue;
         char lname[24];
         snprintf(lname, sizeof(lname), "long_merge_L%d", l);
         on(lname, w.level_grid[l], w.level_products[l]);
         const unsigned grid = std::min<unsigned>(w.level_grid[l], (unsigned)merge_ctas);
-        k_long_partition<<<(w.level_grid[l] + 255) / 256, 256, 0, s>>>(w.unit_row, w.n_rows, w.level_lo[l], l, w.p, w.unit_off,
-                                                                       w.prod_off, w.col[(l - 1) & 1],
-                                                                       reinterpret_cast<MergeTile*>(w.tiles));
-        k_long_merge<<<grid, MG_THREADS, mgsmem, s>>>(reinterpret_cast<const MergeTile*>(w.tiles), (int64_t)w.level_grid[l],
-                                                      w.unit_off, w.n_rows, w.level_lo[l], w.col[(l - 1) & 1],
-                                                      w.val[(l - 1) & 1], w.col[l & 1], w.val[l & 1]);
+        k_long_partition<<<(w.level_grid[l] + 255) / 256, 256, 0, s>>>(D, w.level_lo[l], w.hi, l, tiles);
+        k_long_merge<<<grid, MG_THREADS, mgsmem, s>>>(tiles, D, w.level_lo[l], w.hi);
         kernels += 2;
         off();
     }
-    on("long_sums", (uint32_t)w.unit_bound, w.products_bound);
-    cudaMemsetAsync(w.unit_heads, 0, (size_t)w.unit_bound * sizeof(uint32_t), s);
-    k_long_count<<<(unsigned)w.unit_bound, LR_THREADS, 0, s>>>(w.rows_list, w.n_rows, w.p, w.unit_row, w.unit_off, w.prod_off,
-                                                              w.col[0], w.col[1], w.unit_heads);
-    launch_scan_u32_i64(w.unit_heads, (int64_t)w.unit_bound, w.unit_hoff, w.tile_state, ctr, s);
-    static PerDeviceOnce rattr;
-    if (rattr.first()) cudaFuncSetAttribute(k_long_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-    k_long_reduce<<<(unsigned)w.unit_bound, LR_THREADS, msmem, s>>>(w.rows_list, w.n_rows, w.p, w.unit_row, w.unit_off, w.prod_off,
-                                                               w.col[0], w.col[1], w.val[0], w.val[1], w.unit_hoff, t_ptr,
-                                                               t_col, t_val, row_nnz);
-    kernels += 3;
+    on("long_count", (uint32_t)w.unit_bound, w.products_bound);
+    k_long_count<<<(unsigned)w.unit_bound, LR_THREADS, 0, s>>>(D, w.hi, P.unit_heads, row_nnz);
+    kernels += 1;
     off();
     return kernels;
+}
+
+// after the last wave: where every tile's run heads go inside its row
+uint32_t launch_long_heads_scan(const LongPlan& P, PlanCounters* ctr, cudaStream_t s) {
+    if (P.n_rows == 0) return 0;
+    launch_scan_u32_i64(P.unit_heads, (int64_t)P.unit_bound, P.unit_hoff, P.tile_state, ctr, s);
+    return 1;
+}
+
+// second half: every head sums its run left to right straight into C (every destination of dst)
+uint32_t launch_long_reduce(const LongPlan& P, const int64_t* c_ptr, const CopyDst& dst, cudaStream_t s) {
+    if (P.n_rows == 0) return 0;
+    const size_t msmem = (sizeof(int32_t) + sizeof(double)) * LONG_UNIT;
+    static PerDeviceOnce rattr;
+    if (rattr.first()) {
+        cudaFuncSetAttribute(k_long_reduce<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+        cudaFuncSetAttribute(k_long_reduce<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+    }
+    if (dst.n == 1)
+        k_long_reduce<1><<<(unsigned)P.unit_bound, LR_THREADS, msmem, s>>>(long_dev(P, 0), P.n_rows, P.unit_hoff, c_ptr, dst);
+    else
+        k_long_reduce<8><<<(unsigned)P.unit_bound, LR_THREADS, msmem, s>>>(long_dev(P, 0), P.n_rows, P.unit_hoff, c_ptr, dst);
+    return 1;
 }
 
 }  // namespace spada

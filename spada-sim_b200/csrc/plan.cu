@@ -338,6 +338,7 @@ __device__ __forceinline__ void copy_store(const CopyDst& dst, int64_t o, int32_
         st_out(dst.val[0] + o, v);
     } else {
         // the peers first: their stores cross NVLink and take longest to drain
+#pragma unroll 1
         for (int d = dst.n - 1; d >= 0; --d) {
             st_out(dst.col[d] + o, c);
             st_out(dst.val[d] + o, v);
