@@ -516,7 +516,8 @@ def main():
                    "h2d_bytes_per_step": (8 * (m + 1) + 12 * nnz_a) + (0 if same_operand else 8 * (k + 1) + 12 * nnz_b),
                    "d2h_bytes_per_step": 8 * (m + 1) + 12 * nnz_c, "ms_per_step": float(ems[0]), "steps": args.e2e_steps,
                    "note": "rank 0: pinned host CSR -> H2D -> NCCL broadcast of A and B -> shard plan -> sharded product with "
-                           "peer-store gather -> whole C to rank 0's pinned host memory; max over ranks"}
+                           "peer-store gather -> whole C to rank 0's pinned host memory; max over ranks; one-shot operands "
+                           "(no fiber store), like the N = 1 leg"}
 
     # ---- per-launch durations: the engine overlaps the long rows with the sort bins on a side stream, so the event
     # times of the timed region overlap too.  For the roofline every kernel is timed alone: a second handle with
@@ -654,7 +655,9 @@ def e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, steps, torch
     out = {"value": 2.0 * products / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": steps,
            "note": "spada_b200_upload32 x2 + spada_b200_spgemm_to_host: pinned host CSR in, validation, C computed in row "
-                   "panels whose D2H copies overlap the next panel's kernels, whole C in pinned host arrays"}
+                   "panels whose D2H copies overlap the next panel's kernels, whole C in pinned host arrays.  Operands of "
+                   "one product are marked one-shot (spada_b200_csr_set_one_shot): B is gathered through row_ptr, no fiber "
+                   "store is built (the resident-operand steps above build it once, outside the step: setup.prepare_ms)"}
     for p in keep:
         lib.spada_b200_host_free(p)
     return out

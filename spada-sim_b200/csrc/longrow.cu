@@ -146,41 +146,13 @@ __global__ void k_long_units(const int64_t* __restrict__ unit_off, uint32_t n, u
 }
 
 // ---- sort: one CTA per chunk ---------------------------------------------------------------------------------
-// G = 2: the chunk is sorted as two groups of 2048 with 32-bit keys and the groups are merged in shared memory
-// (columns up to 2^21 without 64-bit keys: the 64-bit network measured 3.2x slower per product)
-template <typename K, int G>
-__global__ void __launch_bounds__(LR_THREADS)
-k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_hi, const uint32_t* __restrict__ aseq) {
-    constexpr int N = LONG_UNIT;
+// N = sort capacity of this chunk: 4096, or 2048 / 1024 for a row's last chunk when it is that short (a row of 5000
+// products is one full chunk and one of 904: sorting the second one at full width would waste a quarter of the work)
+template <typename K, int G, int N>
+__device__ __forceinline__ void chunk_body(const DevCsr a, const DevCsr b, const uint32_t* __restrict__ aseq,
+                                           uint32_t s0, uint32_t cnt, int64_t e0, int64_t e1, K* keys, double* vals,
+                                           CtaStage& st, int32_t* __restrict__ out_col, double* __restrict__ out_val, int64_t dst) {
     constexpr int SBG = Log2<N / G>::v;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    K* keys = reinterpret_cast<K*>(s_raw);
-    double* vals = reinterpret_cast<double*>(s_raw + sizeof(K) * N);
-    __shared__ CtaStage st;
-    __shared__ UnitInfo info;
-    __shared__ int64_t s_e[2];
-    const int64_t g = D.unit_off[D.wave_lo] + blockIdx.x;
-    if (g >= D.unit_off[i_hi]) return;   // uniform over the CTA
-    find_unit(g, D, &info);
-    const int lane = lane_id();
-    const int buf = long_levels(info.P) & 1;   // where the row's chunks go so that its last level ends in the scratch row
-    int32_t* __restrict__ out_col = D.col[buf];
-    double* __restrict__ out_val = D.val[buf];
-    const uint32_t s0 = info.t << LONG_UNIT_LOG;
-    const uint32_t cnt = info.P - s0 < (uint32_t)N ? info.P - s0 : (uint32_t)N;
-    const int64_t a0 = a.ptr[row_begin + info.row], a1 = a.ptr[row_begin + info.row + 1];
-    // A entries that meet the chunk: e0 = last entry starting at or before s0 (the last of a tie is the non-empty
-    // one), e1 = first entry starting at or after s0 + cnt
-    if (threadIdx.x < 32) {
-        const int64_t e0 = warp_search_le<uint32_t, uint32_t>(aseq + a0, a1 - a0, s0, lane);
-        const int64_t e1 = warp_search_le<uint32_t, uint32_t>(aseq + a0, a1 - a0, s0 + cnt - 1u, lane) + 1;
-        if (lane == 0) {
-            s_e[0] = a0 + e0;
-            s_e[1] = a0 + e1;
-        }
-    }
-    __syncthreads();
-    const int64_t e0 = s_e[0], e1 = s_e[1];
     for (int64_t pb = e0; pb < e1; pb += LR_THREADS) {
         const int64_t e = pb + threadIdx.x;
         int off = (int)cnt;
@@ -242,7 +214,6 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_h
     for (int t = (int)cnt + threadIdx.x; t < N; t += LR_THREADS) keys[t] = KeyTraits<K>::sentinel;
     __syncthreads();
     bitonic_cta_sort<K, N, G>(keys);
-    const int64_t dst = (buf ? info.base1 : info.base0) + s0;
     if constexpr (G == 2) {
         cta_merge_groups2<N>(keys, vals, (int)cnt);
         for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
@@ -252,10 +223,49 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_h
     } else {
         for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
             const K key = keys[t];
-            out_col[dst + t] = (int32_t)(uint32_t)(key >> LONG_UNIT_LOG);
+            out_col[dst + t] = (int32_t)(uint32_t)(key >> Log2<N>::v);
             out_val[dst + t] = vals[(int)(key & (K)(N - 1))];
         }
     }
+}
+
+// G = 2: the chunk is sorted as two groups with 32-bit keys and the groups are merged in shared memory (columns up to
+// 2^21 without 64-bit keys: the 64-bit network measured 3.2x slower per product)
+template <typename K, int G>
+__global__ void __launch_bounds__(LR_THREADS)
+k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_hi, const uint32_t* __restrict__ aseq) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    K* keys = reinterpret_cast<K*>(s_raw);
+    double* vals = reinterpret_cast<double*>(s_raw + sizeof(K) * LONG_UNIT);
+    __shared__ CtaStage st;
+    __shared__ UnitInfo info;
+    __shared__ int64_t s_e[2];
+    const int64_t g = D.unit_off[D.wave_lo] + blockIdx.x;
+    if (g >= D.unit_off[i_hi]) return;   // uniform over the CTA
+    find_unit(g, D, &info);
+    const int lane = lane_id();
+    const int buf = long_levels(info.P) & 1;   // where the row's chunks go so that its last level ends in the scratch row
+    const uint32_t s0 = info.t << LONG_UNIT_LOG;
+    const uint32_t cnt = info.P - s0 < (uint32_t)LONG_UNIT ? info.P - s0 : (uint32_t)LONG_UNIT;
+    const int64_t a0 = a.ptr[row_begin + info.row], a1 = a.ptr[row_begin + info.row + 1];
+    // A entries that meet the chunk: e0 = last entry starting at or before s0 (the last of a tie is the non-empty
+    // one), e1 = first entry starting at or after s0 + cnt
+    if (threadIdx.x < 32) {
+        const int64_t e0 = warp_search_le<uint32_t, uint32_t>(aseq + a0, a1 - a0, s0, lane);
+        const int64_t e1 = warp_search_le<uint32_t, uint32_t>(aseq + a0, a1 - a0, s0 + cnt - 1u, lane) + 1;
+        if (lane == 0) {
+            s_e[0] = a0 + e0;
+            s_e[1] = a0 + e1;
+        }
+    }
+    __syncthreads();
+    const int64_t dst = (buf ? info.base1 : info.base0) + s0;
+    if (cnt <= 1024u)
+        chunk_body<K, G, 1024>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
+    else if (cnt <= 2048u)
+        chunk_body<K, G, 2048>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
+    else
+        chunk_body<K, G, LONG_UNIT>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
 }
 
 // ---- merge: one CTA per 4096 outputs of one level --------------------------------------------------------------
@@ -301,7 +311,9 @@ k_long_partition(LongDev D, uint32_t i_lo, uint32_t i_hi, int level, MergeTile* 
     MergeTile T{};
     if (level <= L) {   // rows finished by an earlier level take no part (cannot happen inside level bins)
         const int bin = (L - level + 1) & 1;   // buffer the level reads; it writes the other one
-        const int64_t base[2] = {D.t_ptr[D.rows_list[i]], D.prod_off[i] - D.prod_off[D.wave_lo]};
+        const int64_t b0 = D.t_ptr[D.rows_list[i]], b1 = D.prod_off[i] - D.prod_off[D.wave_lo];
+        const int64_t base_in = bin ? b1 : b0, base_out = bin ? b0 : b1;
+        const int32_t* in_col = bin ? D.col[1] : D.col[0];
         const uint64_t RL = (uint64_t)LONG_UNIT << (level - 1);
         const uint64_t o0 = (uint64_t)(g - D.unit_off[i]) << LONG_UNIT_LOG;
         const uint64_t o1 = o0 + LONG_UNIT < P ? o0 + LONG_UNIT : P;
@@ -309,14 +321,14 @@ k_long_partition(LongDev D, uint32_t i_lo, uint32_t i_hi, int level, MergeTile* 
         const uint64_t xe = pbase + RL < P ? pbase + RL : P;
         const uint64_t ye = pbase + 2 * RL < P ? pbase + 2 * RL : P;
         const int nx = (int)(xe - pbase), ny = (int)(ye - xe);
-        const int32_t* X = D.col[bin] + base[bin] + pbase;
-        const int32_t* Y = D.col[bin] + base[bin] + xe;
+        const int32_t* X = in_col + base_in + pbase;
+        const int32_t* Y = in_col + base_in + xe;
         const int d0 = (int)(o0 - pbase), d1 = (int)(o1 - pbase);
         const int i0 = merge_path(X, nx, Y, ny, d0);
         const int i1 = (d1 == nx + ny) ? nx : merge_path(X, nx, Y, ny, d1);
-        T.ax = base[bin] + (int64_t)pbase + i0;
-        T.ay = base[bin] + (int64_t)xe + (d0 - i0);
-        T.out = base[bin ^ 1] + (int64_t)o0;
+        T.ax = base_in + (int64_t)pbase + i0;
+        T.ay = base_in + (int64_t)xe + (d0 - i0);
+        T.out = base_out + (int64_t)o0;
         T.cx = i1 - i0;
         const int cy = (d1 - i1) - (d0 - i0);
         T.cy = bin ? -1 - cy : cy;
@@ -362,8 +374,8 @@ k_long_merge(const MergeTile* __restrict__ tiles, LongDev D, uint32_t i_lo, uint
         int bin;
         const MergeTile T = decode(T0, bin);
         if (T.cx + T.cy == 0) return;
-        const int32_t* in_col = D.col[bin];
-        const double* in_val = D.val[bin];
+        const int32_t* in_col = bin ? D.col[1] : D.col[0];
+        const double* in_val = bin ? D.val[1] : D.val[0];
         int xc, yc, xv, yv, nxc, nyc, nxv, nyv;
         layout(T, xc, yc, xv, yv, nxc, nyc, nxv, nyv);
         MergeStage& st = stage[sidx];
@@ -389,8 +401,8 @@ k_long_merge(const MergeTile* __restrict__ tiles, LongDev D, uint32_t i_lo, uint
         const int cur = k & 1;
         int bin;
         const MergeTile T = decode(tiles[t], bin);
-        int32_t* __restrict__ out_col = D.col[bin ^ 1];
-        double* __restrict__ out_val = D.val[bin ^ 1];
+        int32_t* __restrict__ out_col = bin ? D.col[0] : D.col[1];
+        double* __restrict__ out_val = bin ? D.val[0] : D.val[1];
         MergeTile ahead{};   // descriptor of the tile two ahead: loaded now, used when this stage is free again
         const bool has_ahead = threadIdx.x == 0 && t + 2 * G < n_tiles;
         if (has_ahead) ahead = tiles[t + 2 * G];
