@@ -626,22 +626,12 @@ def e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, steps, torch
     d2h = 8 * (m + 1) + 12 * nnz_c
 
     def e2e_step():
-        # upload (H2D, validation) -> row panels computed while the previous panel's D2H runs -> operands freed
-        pa, pb = C.c_void_p(), C.c_void_p()
-        abi.check(lib.spada_b200_upload32(eng._h, C.byref(va), C.byref(pa)))
-        if vb is va:
-            pb = pa
-        else:
-            abi.check(lib.spada_b200_upload32(eng._h, C.byref(vb), C.byref(pb)))
-        try:
-            abi.check(lib.spada_b200_csr_set_one_shot(pb))    # operands of one product: no fiber store
-            abi.check(lib.spada_b200_spgemm_to_host(eng._h, pa, pb, 0, o_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
-                                                    o_col.ctypes.data_as(C.POINTER(C.c_int32)),
-                                                    o_val.ctypes.data_as(C.POINTER(C.c_double)), len(o_col), None))
-        finally:
-            if pb is not pa:
-                lib.spada_b200_csr_free(pb)
-            lib.spada_b200_csr_free(pa)
+        # ONE ABI call: B up, then A up in row panels while the panels already there are computed and their results
+        # come down (validation included)
+        abi.check(lib.spada_b200_spgemm32_host_to_host(eng._h, C.byref(va), C.byref(vb),
+                                                       o_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                       o_col.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       o_val.ctypes.data_as(C.POINTER(C.c_double)), len(o_col), None))
     e2e_step()
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -654,10 +644,11 @@ def e2e_single(pkg, eng, a, b, m, k, nnz_a, nnz_b, nnz_c, products, steps, torch
     assert int(o_ptr[-1]) == nnz_c
     out = {"value": 2.0 * products / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": steps,
-           "note": "spada_b200_upload32 x2 + spada_b200_spgemm_to_host: pinned host CSR in, validation, C computed in row "
-                   "panels whose D2H copies overlap the next panel's kernels, whole C in pinned host arrays.  Operands of "
-                   "one product are marked one-shot (spada_b200_csr_set_one_shot): B is gathered through row_ptr, no fiber "
-                   "store is built (the resident-operand steps above build it once, outside the step: setup.prepare_ms)"}
+           "note": "spada_b200_spgemm32_host_to_host: pinned host CSR in (B first, A in row panels on an upload stream), "
+                   "validation, C computed panel by panel while the next panel's entries go up and the previous panel's "
+                   "result comes down, whole C in pinned host arrays.  Operands of one product get no fiber store: B is "
+                   "gathered through row_ptr (the resident-operand steps above build it once, outside the step: "
+                   "setup.prepare_ms)"}
     for p in keep:
         lib.spada_b200_host_free(p)
     return out

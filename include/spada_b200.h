@@ -274,6 +274,15 @@ SPADA_B200_API int spada_b200_spgemm_to_host(spada_b200_t *h, const spada_b200_c
                               uint64_t panel_products, int64_t *indptr, int32_t *indices, double *data,
                               uint64_t capacity_nnz, spada_b200_stream_stats *stats_or_null);
 
+/* Host operands in, whole C in caller-allocated host arrays -- one call for Simulator::new + execute + get_exec_result
+ * (main.rs:74-100) that overlaps everything PCIe allows: B is uploaded first (every row of C needs all of it), A's
+ * entries follow in row panels while the panels already on the device are computed and their results travel down.
+ * Arrays as for spada_b200_spgemm_to_host; pinned host memory on both sides for full PCIe speed.  A non-canonical A is
+ * reported (UNSORTED_INPUT) after the run, when all of it is on the device. */
+SPADA_B200_API int spada_b200_spgemm32_host_to_host(spada_b200_t *h, const spada_csr_view32 *a, const spada_csr_view32 *b,
+                                     int64_t *indptr, int32_t *indices, double *data, uint64_t capacity_nnz,
+                                     spada_b200_stream_stats *stats_or_null);
+
 /* ---- results: replaces get_exec_result (simulator.rs:1034-1062) ----------------------- */
 SPADA_B200_API int spada_b200_result_shape(const spada_b200_result_t *r, uint64_t *rows, uint64_t *cols,
                             uint64_t *nnz);

@@ -113,6 +113,9 @@ SYMBOLS = {
     "spada_b200_spgemm_stream": (C.c_int, [_vp, _vp, _vp, C.c_uint64, PANEL_SINK, _vp, C.POINTER(StreamStats)]),
     "spada_b200_spgemm_to_host": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                             C.POINTER(C.c_double), C.c_uint64, C.POINTER(StreamStats)]),
+    "spada_b200_spgemm32_host_to_host": (C.c_int, [_vp, C.POINTER(CsrView32), C.POINTER(CsrView32), C.POINTER(C.c_int64),
+                                                   C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_uint64,
+                                                   C.POINTER(StreamStats)]),
     "spada_b200_result_shape": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "spada_b200_result_copy": (C.c_int, [_vp, _u64p, _u64p, C.POINTER(C.c_double)]),
     "spada_b200_result_copy32": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),

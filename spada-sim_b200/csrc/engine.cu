@@ -1676,42 +1676,51 @@ struct PanelBuf {
 namespace {
 // dst_*: nullable.  With destination arrays the panels are copied straight into them at their global offsets (no
 // staging, no sink); otherwise into two pinned staging buffers that take turns and are handed to the sink.
+// feed (nullable, direct mode only): panel bounds fixed by the caller and a hook that runs before panel p is computed
+// (the host-to-host entry point makes the engine's stream wait for the upload of A's rows of that panel there).
+struct PanelFeed {
+    std::vector<uint64_t> bounds;
+    std::function<int(size_t)> before;
+};
 int stream_panels(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_csr_t* b, uint64_t panel_products,
                   spada_b200_panel_sink sink, void* user, int64_t* dst_ptr, int32_t* dst_col, double* dst_val,
-                  uint64_t dst_capacity, spada_b200_stream_stats* stats) {
+                  uint64_t dst_capacity, spada_b200_stream_stats* stats, const PanelFeed* feed = nullptr) {
     if (a->d.cols != b->d.rows)
         return fail(SPADA_B200_DIM_MISMATCH, "A is %lld x %lld but B has %lld rows", (long long)a->d.rows,
                     (long long)a->d.cols, (long long)b->d.rows);
     DeviceGuard g(h->device);
     const bool direct = dst_ptr != nullptr;
     const uint64_t m = (uint64_t)a->d.rows;
-    std::vector<uint64_t> f((size_t)m);
-    uint64_t total = 0;
-    int rc = spada_b200_flops(h, a, b, &total, f.data());
-    if (rc) return rc;
-    // panels: consecutive rows up to panel_products intermediate products each (a row heavier than that is a panel of
-    // its own).  Default: what keeps scratch rows + C + staging of a panel within a quarter of the device, at least
-    // eight panels so that the copies have something to overlap with.
-    if (panel_products == 0) {
-        const uint64_t by_mem = (uint64_t)(0.25 * (double)h->dev_total_mem / 36.0);
-        panel_products = std::max<uint64_t>(1u << 20, std::min<uint64_t>(by_mem, total / 8 + 1));
-    }
     std::vector<uint64_t> bounds{0};
-    uint64_t acc = 0, max_panel = 0, max_rows = 0;
-    for (uint64_t r = 0; r < m; ++r) {
-        if (acc && acc + f[(size_t)r] > panel_products) {
-            max_panel = std::max(max_panel, acc);
-            max_rows = std::max(max_rows, r - bounds.back());
-            bounds.push_back(r);
-            acc = 0;
+    uint64_t total = 0, max_panel = 0, max_rows = 0;
+    int rc = 0;
+    if (feed) {
+        bounds = feed->bounds;
+        for (size_t p = 0; p + 1 < bounds.size(); ++p) max_rows = std::max(max_rows, bounds[p + 1] - bounds[p]);
+    } else {
+        std::vector<uint64_t> f((size_t)m);
+        if ((rc = spada_b200_flops(h, a, b, &total, f.data()))) return rc;
+        // panels: consecutive rows up to panel_products intermediate products each (a row heavier than that is a panel
+        // of its own).  Default: what keeps scratch rows + C + staging of a panel within a quarter of the device, at
+        // least eight panels so that the copies have something to overlap with.
+        if (panel_products == 0) {
+            const uint64_t by_mem = (uint64_t)(0.25 * (double)h->dev_total_mem / 36.0);
+            panel_products = std::max<uint64_t>(1u << 20, std::min<uint64_t>(by_mem, total / 8 + 1));
         }
-        acc += f[(size_t)r];
+        uint64_t acc = 0;
+        for (uint64_t r = 0; r < m; ++r) {
+            if (acc && acc + f[(size_t)r] > panel_products) {
+                max_panel = std::max(max_panel, acc);
+                max_rows = std::max(max_rows, r - bounds.back());
+                bounds.push_back(r);
+                acc = 0;
+            }
+            acc += f[(size_t)r];
+        }
+        max_panel = std::max(max_panel, acc);
+        max_rows = std::max(max_rows, m - bounds.back());
+        bounds.push_back(m);
     }
-    max_panel = std::max(max_panel, acc);
-    max_rows = std::max(max_rows, m - bounds.back());
-    bounds.push_back(m);
-    f.clear();
-    f.shrink_to_fit();
     const size_t n_panels = bounds.size() - 1;
     cudaStream_t cs = nullptr;
     PanelBuf buf[2];
@@ -1767,7 +1776,9 @@ int stream_panels(spada_b200_t* h, const spada_b200_csr_t* a, const spada_b200_c
             int rc2 = drain(B);    // the buffer's previous panel (p - 2): its copy ran beside the computation of p - 1
             if (rc2) return rc2;
             spada_b200_result* R = nullptr;
+            if (feed && feed->before && (rc2 = feed->before(p))) return rc2;
             if ((rc2 = spada_b200_spgemm_dev(h, a, b, bounds[p], bounds[p + 1], &R))) return rc2;   // synchronous
+            total += feed ? R->stats.products : 0;
             B.R = R;
             B.row_begin = bounds[p];
             B.row_end = bounds[p + 1];
@@ -1835,6 +1846,102 @@ extern "C" int spada_b200_spgemm_to_host(spada_b200_t* h, const spada_b200_csr_t
                                          uint64_t capacity_nnz, spada_b200_stream_stats* stats) {
     if (!h || !a || !b || !indptr || (capacity_nnz && (!indices || !data))) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
     return stream_panels(h, a, b, panel_products, nullptr, nullptr, indptr, indices, data, capacity_nnz, stats);
+}
+
+// Host operands in, whole C in host arrays, everything overlapped that PCIe allows: B goes up first (every row needs all
+// of it), then A's column ids and values follow in row panels on an upload stream while the panels already there are
+// computed and their results travel down (PCIe is full duplex) -- what the Rust wrapper calls for one product.
+extern "C" int spada_b200_spgemm32_host_to_host(spada_b200_t* h, const spada_csr_view32* a, const spada_csr_view32* b,
+                                                int64_t* indptr, int32_t* indices, double* data, uint64_t capacity_nnz,
+                                                spada_b200_stream_stats* stats) {
+    if (!h || !a || !b || !indptr || (capacity_nnz && (!indices || !data))) return fail(SPADA_B200_INVALID_ARG, "NULL argument");
+    if (a->cols != b->rows)
+        return fail(SPADA_B200_DIM_MISMATCH, "A is %llu x %llu but B has %llu rows", (unsigned long long)a->rows,
+                    (unsigned long long)a->cols, (unsigned long long)b->rows);
+    DeviceGuard g(h->device);
+    int rc;
+    const bool alias = (const void*)a == (const void*)b || (a->indptr == b->indptr && a->indices == b->indices &&
+                                                            a->data == b->data && a->rows == b->rows && a->cols == b->cols);
+    spada_b200_csr_t *da = nullptr, *db = nullptr;
+    if ((rc = spada_b200_upload32(h, b, &db))) return rc;
+    db->fib_ready = true;   // one product: no fiber store
+    if (alias || a->nnz == 0 || a->rows == 0) {
+        // A is B (or empty): nothing to overlap
+        if (!alias && (rc = spada_b200_upload32(h, a, &da))) {
+            spada_b200_csr_free(db);
+            return rc;
+        }
+        rc = stream_panels(h, alias ? db : da, db, 0, nullptr, nullptr, indptr, indices, data, capacity_nnz, stats);
+        if (da) spada_b200_csr_free(da);
+        spada_b200_csr_free(db);
+        return rc;
+    }
+    if ((rc = check_csr_args(a->rows, a->cols, a->nnz, a->indptr, a->indices, a->data)) ||
+        (a->nnz >= (1ull << 31) ? (rc = fail(SPADA_B200_TOO_LARGE, "nnz >= 2^31 needs the 64-bit view")) : 0) ||
+        ((uint64_t)(int64_t)a->indptr[a->rows] != a->nnz ? (rc = fail(SPADA_B200_INVALID_ARG, "indptr[rows] != nnz")) : 0)) {
+        spada_b200_csr_free(db);
+        return rc;
+    }
+    int64_t* ptr;
+    int32_t* col;
+    double* val;
+    if ((rc = make_csr(h, a->rows, a->cols, a->nnz, &da, &ptr, &col, &val))) {
+        spada_b200_csr_free(db);
+        return rc;
+    }
+    da->fib_ready = true;
+    cudaStream_t up = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int32_t* tmp = nullptr;
+    auto body = [&]() -> int {
+        int rc2;
+        if ((rc2 = dalloc(h, &tmp, a->rows + 1))) return rc2;
+        CU(cudaMemcpyAsync(tmp, a->indptr, (a->rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        launch_widen_i32(tmp, (int64_t)a->rows + 1, ptr, h->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        // panels of equal nnz(A): 8 or more, cut on the host from the row pointers it already holds
+        const uint64_t n_panels = std::max<uint64_t>(8, std::min<uint64_t>(64, a->nnz / (8u << 20) + 1));
+        PanelFeed feed;
+        feed.bounds.push_back(0);
+        for (uint64_t p = 1; p < n_panels; ++p) {
+            const int32_t target = (int32_t)(a->nnz * p / n_panels);
+            const int32_t* it = std::lower_bound(a->indptr, a->indptr + a->rows + 1, target);
+            const uint64_t r = std::min<uint64_t>((uint64_t)(it - a->indptr), a->rows);
+            if (r > feed.bounds.back()) feed.bounds.push_back(r);
+        }
+        if (feed.bounds.back() < a->rows) feed.bounds.push_back(a->rows);
+        CU(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+        ev.resize(feed.bounds.size() - 1, nullptr);
+        for (size_t p = 0; p + 1 < feed.bounds.size(); ++p) {
+            const int64_t lo = a->indptr[feed.bounds[p]], hi = a->indptr[feed.bounds[p + 1]];
+            if (hi > lo) {
+                CU(cudaMemcpyAsync(col + lo, a->indices + lo, (size_t)(hi - lo) * sizeof(int32_t), cudaMemcpyHostToDevice, up));
+                CU(cudaMemcpyAsync(val + lo, a->data + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, up));
+            }
+            CU(cudaEventCreateWithFlags(&ev[p], cudaEventDisableTiming));
+            CU(cudaEventRecord(ev[p], up));
+        }
+        feed.before = [&](size_t p) -> int {
+            CU(cudaStreamWaitEvent(h->stream, ev[p], 0));
+            return 0;
+        };
+        if ((rc2 = stream_panels(h, da, db, 0, nullptr, nullptr, indptr, indices, data, capacity_nnz, stats, &feed))) return rc2;
+        // the reference's loaders hand over canonical CSR; a violation is reported once all of A is on the device
+        if (h->opts.flags & SPADA_B200_FLAG_VALIDATE) return validate_device_csr(h, da->d);
+        return 0;
+    };
+    rc = body();
+    if (up) {
+        cudaStreamSynchronize(up);
+        cudaStreamDestroy(up);
+    }
+    for (cudaEvent_t e : ev)
+        if (e) cudaEventDestroy(e);
+    dfree(h, tmp);
+    spada_b200_csr_free(da);
+    spada_b200_csr_free(db);
+    return rc;
 }
 
 // ---- all GPUs of one process (what the spada-sim CLI, a single process, drives: SURVEY.md 8b) -----------------------

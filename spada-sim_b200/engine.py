@@ -381,6 +381,16 @@ class Engine:
                                               _ptr(indices, C.c_int32), _ptr(data, C.c_double), len(indices), C.byref(st)))
         return {k: getattr(st, k) for k in ("panels", "products", "nnz_c", "max_panel_products", "ms_total")}
 
+    def spgemm_host_to_host(self, a: sp.csr_matrix, b: sp.csr_matrix, indptr: np.ndarray, indices: np.ndarray,
+                            data: np.ndarray) -> dict:
+        """Host CSR operands in, the whole C in host arrays, uploads / kernels / downloads overlapped (one ABI call)."""
+        va, ka = self._view32(a)
+        vb, kb = (va, ka) if b is a else self._view32(b)
+        st = _abi.StreamStats()
+        check(lib().spada_b200_spgemm32_host_to_host(self._h, C.byref(va), C.byref(vb), _ptr(indptr, C.c_int64),
+                                                     _ptr(indices, C.c_int32), _ptr(data, C.c_double), len(indices), C.byref(st)))
+        return {k: getattr(st, k) for k in ("panels", "products", "nnz_c", "max_panel_products", "ms_total")}
+
     # -- sharded runs --
     def cbuf_create(self, rows: int, cols: int, capacity_nnz: int) -> CBuf:
         out = C.c_void_p()

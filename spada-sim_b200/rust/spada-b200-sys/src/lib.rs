@@ -196,6 +196,10 @@ extern "C" {
         indptr: *mut i64, indices: *mut i32, data: *mut f64, capacity_nnz: u64,
         stats_or_null: *mut spada_b200_stream_stats,
     ) -> c_int;
+    pub fn spada_b200_spgemm32_host_to_host(
+        h: *mut spada_b200_t, a: *const spada_csr_view32, b: *const spada_csr_view32, indptr: *mut i64, indices: *mut i32,
+        data: *mut f64, capacity_nnz: u64, stats_or_null: *mut spada_b200_stream_stats,
+    ) -> c_int;
     pub fn spada_b200_result_shape(r: *const spada_b200_result_t, rows: *mut u64, cols: *mut u64, nnz: *mut u64) -> c_int;
     pub fn spada_b200_result_copy(r: *const spada_b200_result_t, indptr: *mut u64, indices: *mut u64, data: *mut f64) -> c_int;
     pub fn spada_b200_result_copy32(r: *const spada_b200_result_t, indptr: *mut i64, indices: *mut i32, data: *mut f64) -> c_int;

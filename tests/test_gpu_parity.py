@@ -636,3 +636,31 @@ def test_narrow_outputs_both_long_row_paths(spada, oracle, cari, monkeypatch):
             check(r, ref, True)
         finally:
             e.close()
+
+
+def test_host_to_host_one_call(engine, oracle, spada):
+    # host CSR in, whole C in host arrays, uploads / kernels / downloads overlapped: A != B (A goes up in row panels),
+    # A is B (alias), an empty A, and a non-canonical A (reported once all of it is on the device)
+    rng = np.random.default_rng(99)
+    lens = rng.choice([0, 2, 9, 40, 150, 900], size=5000, p=[.1, .3, .3, .2, .07, .03])
+    a = random_csr(5000, 1500, row_nnz=lens, seed=100, values="signed")
+    b = random_csr(1500, 20000, row_nnz=rng.integers(0, 50, size=1500), seed=101, values="signed")
+    sq = random_csr(1500, 1500, row_nnz=rng.integers(0, 30, size=1500), seed=102, values="signed")
+    for x, y in ((a, b), (sq, sq), (sp.csr_matrix((7, 1500)), b)):
+        ref = oracle.spgemm(x, y, threads=oracle.max_threads())
+        ip = np.zeros(x.shape[0] + 1, dtype=np.int64); ix = np.zeros(len(ref[1]) + 3, dtype=np.int32); dx = np.zeros(len(ref[1]) + 3)
+        st = engine.spgemm_host_to_host(x, y, ip, ix, dx)
+        n = st["nnz_c"]
+        assert n == len(ref[1]) and st["products"] == int(oracle.flops(x, y).sum())
+        assert np.array_equal(ip, ref[0]) and np.array_equal(ix[:n], ref[1])
+        assert np.array_equal(dx[:n].view(np.uint64), ref[2].view(np.uint64))
+    bad = a.copy()
+    rows2 = np.flatnonzero(np.diff(bad.indptr) >= 2)
+    r = rows2[len(rows2) // 2]
+    s0 = bad.indptr[r]
+    bad.indices[s0], bad.indices[s0 + 1] = bad.indices[s0 + 1], bad.indices[s0]
+    cap = int(oracle.flops(a, b).sum())
+    ip = np.zeros(a.shape[0] + 1, dtype=np.int64); ix = np.zeros(cap, dtype=np.int32); dx = np.zeros(cap)
+    with pytest.raises(spada.SpadaB200Error) as e:
+        engine.spgemm_host_to_host(bad, b, ip, ix, dx)
+    assert e.value.status == "UNSORTED_INPUT"
