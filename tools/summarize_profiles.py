@@ -8,7 +8,10 @@ bench_n<N>_peer.log / bench_n<N>_nccl.log, launches_<workload>.csv (ncu launch l
 """
 import collections, csv, io, json, os, re, subprocess, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G = os.path.join(R, "gpurun_out"); P = os.path.join(R, "profiles"); TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
+G = os.path.join(R, "gpurun_out"); TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
+# on the GPU box the summaries are written next to the raw files (only gpurun_out/ travels back); here into profiles/
+P = sys.argv[2] if len(sys.argv) > 2 else os.path.join(R, "profiles")
+os.makedirs(P, exist_ok=True)
 
 
 def bench(name):
