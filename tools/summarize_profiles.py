@@ -121,8 +121,10 @@ def record_name(kn):
         return "fused<32>"
     if "k_long_chunk_sort" in kn:
         return "long_sort"
-    if "k_long_reduce" in kn or "k_long_count" in kn:
-        return "long_sums"
+    if "k_long_reduce" in kn:
+        return "long_reduce"
+    if "k_long_count" in kn:
+        return "long_count"
     if "k_copy_rows" in kn:
         return "copy_rows"
     if "k_flops" in kn:
@@ -132,7 +134,7 @@ def record_name(kn):
 
 named = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the largest captured of that kernel) from the "
                      f"`ncu --set full` captures (profiles/{TAG}_ncu_full.md); keys are the engine's launch-record names; "
-                     "records that span several kernels (copy_rows, long_sums) add their kernels"}
+                     "records that span several kernels (copy_rows) add their kernels"}
 for wl, ks in traffic.items():
     per = collections.defaultdict(float)
     for kn, ts in ks.items():
