@@ -148,11 +148,15 @@ __global__ void k_long_units(const int64_t* __restrict__ unit_off, uint32_t n, u
 // ---- sort: one CTA per chunk ---------------------------------------------------------------------------------
 // N = sort capacity of this chunk: 4096, or 2048 / 1024 for a row's last chunk when it is that short (a row of 5000
 // products is one full chunk and one of 904: sorting the second one at full width would waste a quarter of the work)
-template <typename K, int G, int N>
+template <typename K, bool SPLIT, int N>
 __device__ __forceinline__ void chunk_body(const DevCsr a, const DevCsr b, const uint32_t* __restrict__ aseq,
                                            uint32_t s0, uint32_t cnt, int64_t e0, int64_t e1, K* keys, double* vals,
-                                           CtaStage& st, int32_t* __restrict__ out_col, double* __restrict__ out_val, int64_t dst) {
-    constexpr int SBG = Log2<N / G>::v;
+                                           CtaStage& st, uint32_t* top, int32_t* __restrict__ out_col,
+                                           double* __restrict__ out_val, int64_t dst) {
+    constexpr int SB = Log2<N>::v;
+    const int lane = lane_id();
+    if constexpr (SPLIT)
+        for (int t = threadIdx.x; t < N / 32 + 1; t += LR_THREADS) top[t] = 0u;   // the loop below syncs before it writes
     for (int64_t pb = e0; pb < e1; pb += LR_THREADS) {
         const int64_t e = pb + threadIdx.x;
         int off = (int)cnt;
@@ -205,33 +209,29 @@ __device__ __forceinline__ void chunk_body(const DevCsr a, const DevCsr b, const
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (t[u] < end) {
-                    keys[t[u]] = ((K)c[u] << SBG) | (K)(t[u] & (N / G - 1));
+                    keys[KeySlot<K, N>::at(t[u])] = ((K)c[u] << SB) | (K)t[u];   // SPLIT: the top bit falls off
                     vals[t[u]] = __dmul_rn(st.av[j[u]], bv[u]);
+                    if constexpr (SPLIT) top_bit_mark(top, t[u], (c[u] >> (32 - SB)) & 1u, lane);
                 }
         }
         __syncthreads();
     }
-    for (int t = (int)cnt + threadIdx.x; t < N; t += LR_THREADS) keys[t] = KeyTraits<K>::sentinel;
+    for (int t = (int)cnt + threadIdx.x; t < N; t += LR_THREADS) keys[KeySlot<K, N>::at(t)] = KeyTraits<K>::sentinel;
     __syncthreads();
-    bitonic_cta_sort<K, N, G>(keys);
-    if constexpr (G == 2) {
-        cta_merge_groups2<N>(keys, vals, (int)cnt);
-        for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
-            out_col[dst + t] = (int32_t)keys[t];
-            out_val[dst + t] = vals[t];
-        }
-    } else {
-        for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
-            const K key = keys[t];
-            out_col[dst + t] = (int32_t)(uint32_t)(key >> Log2<N>::v);
-            out_val[dst + t] = vals[(int)(key & (K)(N - 1))];
-        }
+    bitonic_cta_sort<K, N>(keys);
+    int n0 = 0x7fffffff;
+    if constexpr (SPLIT) n0 = cta_split_top<N>(keys, (int)cnt, top, st);
+    constexpr uint32_t TOP = sizeof(K) == 4 ? 1u << (32 - SB) : 0u;
+    for (int t = threadIdx.x; t < (int)cnt; t += LR_THREADS) {
+        const K key = keys[KeySlot<K, N>::at(t)];
+        out_col[dst + t] = (int32_t)((uint32_t)(key >> SB) | (t >= n0 ? TOP : 0u));
+        out_val[dst + t] = vals[(int)(key & (K)(N - 1))];
     }
 }
 
-// G = 2: the chunk is sorted as two groups with 32-bit keys and the groups are merged in shared memory (columns up to
-// 2^21 without 64-bit keys: the 64-bit network measured 3.2x slower per product)
-template <typename K, int G>
+// SPLIT: columns up to 2^21 with 32-bit keys -- sorted without their top bit, then split by it (cta_split_top; the
+// 64-bit network measured 3.2x slower per product)
+template <typename K, bool SPLIT>
 __global__ void __launch_bounds__(LR_THREADS)
 k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_hi, const uint32_t* __restrict__ aseq) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -240,6 +240,7 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_h
     __shared__ CtaStage st;
     __shared__ UnitInfo info;
     __shared__ int64_t s_e[2];
+    __shared__ uint32_t top[SPLIT ? LONG_UNIT / 32 + 1 : 1];
     const int64_t g = D.unit_off[D.wave_lo] + blockIdx.x;
     if (g >= D.unit_off[i_hi]) return;   // uniform over the CTA
     find_unit(g, D, &info);
@@ -261,11 +262,11 @@ k_long_chunk_sort(DevCsr a, DevCsr b, int64_t row_begin, LongDev D, uint32_t i_h
     __syncthreads();
     const int64_t dst = (buf ? info.base1 : info.base0) + s0;
     if (cnt <= 1024u)
-        chunk_body<K, G, 1024>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
+        chunk_body<K, SPLIT, 1024>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, top, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
     else if (cnt <= 2048u)
-        chunk_body<K, G, 2048>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
+        chunk_body<K, SPLIT, 2048>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, top, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
     else
-        chunk_body<K, G, LONG_UNIT>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
+        chunk_body<K, SPLIT, LONG_UNIT>(a, b, aseq, s0, cnt, s_e[0], s_e[1], keys, vals, st, top, buf ? D.col[1] : D.col[0], buf ? D.val[1] : D.val[0], dst);
 }
 
 // ---- merge: one CTA per 4096 outputs of one level --------------------------------------------------------------
@@ -287,18 +288,29 @@ __device__ __forceinline__ int merge_path(P x, int nx, P y, int ny, int d) {
 // while tile k is merged; completion is counted by the stage's mbarrier.  Bulk copies need 16-byte aligned addresses
 // and sizes: every slice is fetched from the aligned address below its start to the aligned address above its end,
 // the merge indexes past the few extra elements.
+constexpr int RD_PAD = 4;   // spare elements of k_long_reduce's stage for the bulk copies' alignment
 constexpr int MG_THREADS = 512;
 constexpr int MG_ITEMS = LONG_UNIT / MG_THREADS;   // outputs per thread
 constexpr int MG_PAD = 16;
+// The merged tile goes back through the stage for coalesced stores.  Every thread writes MG_ITEMS consecutive outputs:
+// one spare word per 32 column ids and one spare double per 16 values spread the lanes of a warp over all banks
+// (unpadded: 8-way conflicts on the columns, 16-way on the values).
+__device__ __forceinline__ int mg_col_at(int e) { return e + (e >> 5); }
+__device__ __forceinline__ int mg_val_at(int e) { return e + (e >> 4); }
 struct MergeStage {
-    int32_t col[LONG_UNIT + MG_PAD];
-    double val[LONG_UNIT + MG_PAD];
+    int32_t col[LONG_UNIT + LONG_UNIT / 32 + MG_PAD];
+    double val[LONG_UNIT + LONG_UNIT / 16 + MG_PAD];
 };
 struct __align__(16) MergeTile {
     int64_t ax, ay;       // element index (inside the input buffer) of the first X / Y element the tile consumes
     int64_t out;          // where the tile's outputs go (inside the other buffer)
-    int32_t cx, cy;       // elements taken from X and from Y; cy < 0: the input is buffer 1 and cy = -1 - count
+    uint32_t cnt;         // elements taken from X (bits 0-12) and from Y (13-25); bit 26: the input is buffer 1;
+                          // bit 27: the row's last level -- the tile also counts the run heads that start inside it
+    int32_t prev;         // last level only: column of the output element before the tile, -1: the tile opens the row
 };
+constexpr uint32_t MT_BUF1 = 1u << 26, MT_LAST = 1u << 27;
+__device__ __forceinline__ int mt_cx(const MergeTile& T) { return (int)(T.cnt & 0x1fffu); }
+__device__ __forceinline__ int mt_cy(const MergeTile& T) { return (int)((T.cnt >> 13) & 0x1fffu); }
 
 __global__ void __launch_bounds__(256)
 k_long_partition(LongDev D, uint32_t i_lo, uint32_t i_hi, int level, MergeTile* __restrict__ tiles) {
@@ -329,62 +341,62 @@ k_long_partition(LongDev D, uint32_t i_lo, uint32_t i_hi, int level, MergeTile* 
         T.ax = base_in + (int64_t)pbase + i0;
         T.ay = base_in + (int64_t)xe + (d0 - i0);
         T.out = base_out + (int64_t)o0;
-        T.cx = i1 - i0;
-        const int cy = (d1 - i1) - (d0 - i0);
-        T.cy = bin ? -1 - cy : cy;
-    } else {
-        T.cx = 0;
-        T.cy = 0;
+        T.cnt = (uint32_t)(i1 - i0) | (uint32_t)((d1 - i1) - (d0 - i0)) << 13 | (bin ? MT_BUF1 : 0u);
+        if (level == L) {   // the output of this level is the row in its final order
+            int32_t prev = -1;
+            if (i0 > 0) prev = X[i0 - 1];
+            if (d0 - i0 > 0) prev = max(prev, Y[d0 - i0 - 1]);   // the later of the two in merge order has the larger column
+            T.prev = prev;
+            T.cnt |= MT_LAST;
+        }
     }
     tiles[g - g0] = T;
 }
 
 __global__ void __launch_bounds__(MG_THREADS, 2)
-k_long_merge(const MergeTile* __restrict__ tiles, LongDev D, uint32_t i_lo, uint32_t i_hi) {
+k_long_merge(const MergeTile* __restrict__ tiles, LongDev D, uint32_t i_lo, uint32_t i_hi,
+             uint32_t* __restrict__ unit_heads, uint32_t* __restrict__ row_nnz) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     MergeStage* stage = reinterpret_cast<MergeStage*>(s_raw);
     __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int s_heads;
     const int64_t n_tiles = D.unit_off[i_hi] - D.unit_off[i_lo];
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        s_heads = 0;
     }
     __syncthreads();
 
     // where the X and Y slices of a tile sit inside a stage (both start on 16-byte boundaries of the source)
     auto layout = [](const MergeTile& T, int& xc, int& yc, int& xv, int& yv, int& nxc, int& nyc, int& nxv, int& nyv) {
+        const int cx = mt_cx(T), cy = mt_cy(T);
         const int dxc = (int)(T.ax & 3), dyc = (int)(T.ay & 3);
-        nxc = T.cx ? (dxc + T.cx + 3) & ~3 : 0;
-        nyc = T.cy ? (dyc + T.cy + 3) & ~3 : 0;
+        nxc = cx ? (dxc + cx + 3) & ~3 : 0;
+        nyc = cy ? (dyc + cy + 3) & ~3 : 0;
         xc = dxc;
         yc = nxc + dyc;
         const int dxv = (int)(T.ax & 1), dyv = (int)(T.ay & 1);
-        nxv = T.cx ? (dxv + T.cx + 1) & ~1 : 0;
-        nyv = T.cy ? (dyv + T.cy + 1) & ~1 : 0;
+        nxv = cx ? (dxv + cx + 1) & ~1 : 0;
+        nyv = cy ? (dyv + cy + 1) & ~1 : 0;
         xv = dxv;
         yv = nxv + dyv;
     };
-    // descriptors carry the input buffer in the sign of cy
-    auto decode = [](MergeTile T, int& bin) {
-        bin = T.cy < 0;
-        if (bin) T.cy = -1 - T.cy;
-        return T;
-    };
-    auto issue = [&](const MergeTile& T0, int sidx) {   // thread 0 only
-        int bin;
-        const MergeTile T = decode(T0, bin);
-        if (T.cx + T.cy == 0) return;
+    auto issue = [&](const MergeTile& T, int sidx) {   // thread 0 only
+        const int cx = mt_cx(T), cy = mt_cy(T);
+        if (cx + cy == 0) return;
+        const bool bin = T.cnt & MT_BUF1;
         const int32_t* in_col = bin ? D.col[1] : D.col[0];
         const double* in_val = bin ? D.val[1] : D.val[0];
         int xc, yc, xv, yv, nxc, nyc, nxv, nyv;
         layout(T, xc, yc, xv, yv, nxc, nyc, nxv, nyv);
         MergeStage& st = stage[sidx];
         mbar_expect_tx(&bar[sidx], (uint32_t)(nxc + nyc) * 4u + (uint32_t)(nxv + nyv) * 8u);
-        if (T.cx) {
+        if (cx) {
             tma_load_1d(st.col, in_col + (T.ax - xc), (uint32_t)nxc * 4u, &bar[sidx]);
             tma_load_1d(st.val, in_val + (T.ax - xv), (uint32_t)nxv * 8u, &bar[sidx]);
         }
-        if (T.cy) {
+        if (cy) {
             tma_load_1d(st.col + nxc, in_col + (T.ay - (yc - nxc)), (uint32_t)nyc * 4u, &bar[sidx]);
             tma_load_1d(st.val + nxv, in_val + (T.ay - (yv - nxv)), (uint32_t)nyv * 8u, &bar[sidx]);
         }
@@ -399,14 +411,14 @@ k_long_merge(const MergeTile* __restrict__ tiles, LongDev D, uint32_t i_lo, uint
     uint32_t phase[2] = {0u, 0u};
     for (int k = 0; t < n_tiles; ++k, t += G) {
         const int cur = k & 1;
-        int bin;
-        const MergeTile T = decode(tiles[t], bin);
+        const MergeTile T = tiles[t];
+        const bool bin = T.cnt & MT_BUF1, last = T.cnt & MT_LAST;
         int32_t* __restrict__ out_col = bin ? D.col[0] : D.col[1];
         double* __restrict__ out_val = bin ? D.val[0] : D.val[1];
         MergeTile ahead{};   // descriptor of the tile two ahead: loaded now, used when this stage is free again
         const bool has_ahead = threadIdx.x == 0 && t + 2 * G < n_tiles;
         if (has_ahead) ahead = tiles[t + 2 * G];
-        const int cx = T.cx, cy = T.cy, tot = cx + cy;
+        const int cx = mt_cx(T), cy = mt_cy(T), tot = cx + cy;
         if (tot == 0) {                       // uniform; nothing was issued for this tile
             if (has_ahead) issue(ahead, cur);
             continue;
@@ -449,50 +461,39 @@ k_long_merge(const MergeTile* __restrict__ tiles, LongDev D, uint32_t i_lo, uint
 #pragma unroll
             for (int q = 0; q < MG_ITEMS; ++q)
                 if (d + q < tot) {
-                    st.col[d + q] = oc[q];
-                    st.val[d + q] = ov[q];
+                    st.col[mg_col_at(d + q)] = oc[q];
+                    st.val[mg_val_at(d + q)] = ov[q];
                 }
         }
         __syncthreads();
+        int heads = 0;   // last level: run heads (first product of a column) among this thread's outputs
         for (int e = threadIdx.x; e < tot; e += MG_THREADS) {
-            out_col[T.out + e] = st.col[e];
-            out_val[T.out + e] = st.val[e];
+            const int32_t c = st.col[mg_col_at(e)];
+            out_col[T.out + e] = c;
+            out_val[T.out + e] = st.val[mg_val_at(e)];
+            if (last) heads += c != (e ? st.col[mg_col_at(e - 1)] : T.prev);
+        }
+        if (last) {   // uniform
+            heads = (int)__reduce_add_sync(FULL, (unsigned)heads);
+            if (heads && (threadIdx.x & 31) == 0) atomicAdd(&s_heads, heads);
         }
         // the stage goes back to the async proxy: the bulk copies of the tile two ahead write it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (has_ahead) issue(ahead, cur);
+        if (last && threadIdx.x == 32) {
+            // the tile is unit g of the wave: its head count places the row's sums later; the row's nnz is their total
+            // (integer atomics: deterministic).  s_heads is clear again before the next tile's barrier lets anybody add.
+            const int64_t g = D.unit_off[i_lo] + t;
+            const uint32_t h = (uint32_t)s_heads;
+            s_heads = 0;
+            unit_heads[g] = h;
+            atomicAdd(row_nnz + D.rows_list[D.unit_row[g]], h);
+        }
     }
 }
 
 // ---- sums ---------------------------------------------------------------------------------------------------
-// heads (first entry of a run of equal columns) that start inside every tile of 4096 sorted products; their sum over a
-// row is the row's nnz (integer atomics: deterministic)
-__global__ void __launch_bounds__(LR_THREADS)
-k_long_count(LongDev D, uint32_t i_hi, uint32_t* __restrict__ unit_heads, uint32_t* __restrict__ row_nnz) {
-    __shared__ UnitInfo info;
-    __shared__ int s_w[LR_THREADS / 32];
-    const int64_t g = D.unit_off[D.wave_lo] + blockIdx.x;
-    if (g >= D.unit_off[i_hi]) return;
-    find_unit(g, D, &info);
-    const int32_t* col = D.col[0] + info.base0;   // every row ends in its scratch row
-    const uint32_t o0 = info.t << LONG_UNIT_LOG;
-    const uint32_t o1 = info.P - o0 < (uint32_t)LONG_UNIT ? info.P : o0 + LONG_UNIT;
-    int cnt = 0;
-    for (uint32_t pos = o0 + threadIdx.x; pos < o1; pos += LR_THREADS)
-        if (pos == 0 || col[pos] != col[pos - 1]) ++cnt;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-    if (lane_id() == 0) s_w[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < LR_THREADS / 32; ++w) t += s_w[w];
-        unit_heads[g] = (uint32_t)t;
-        atomicAdd(row_nnz + info.row, (uint32_t)t);
-    }
-}
-
 // Every head sums its run left to right (the oracle's order: ascending k) and writes the entry of the finished row.
 // The tile's 4096 sorted products are staged in shared memory first (coalesced loads, all in flight at once), so
 // the dependent chain of a run (compare the next column, add the next value) runs at shared-memory latency, and all
@@ -524,7 +525,8 @@ __global__ void __launch_bounds__(LR_THREADS)
 k_long_reduce(LongDev D, uint32_t n, const int64_t* __restrict__ unit_hoff, const int64_t* __restrict__ c_ptr, CopyDst dst_all) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     int32_t* s_col = reinterpret_cast<int32_t*>(s_raw);
-    double* s_val = reinterpret_cast<double*>(s_raw + sizeof(int32_t) * LONG_UNIT);
+    double* s_val = reinterpret_cast<double*>(s_raw + sizeof(int32_t) * (LONG_UNIT + RD_PAD));
+    __shared__ __align__(8) uint64_t bar;
     __shared__ UnitInfo info;
     __shared__ int s_w[LR_THREADS / 32];
     __shared__ int s_prev;            // column of the product before the tile
@@ -546,15 +548,22 @@ k_long_reduce(LongDev D, uint32_t n, const int64_t* __restrict__ unit_hoff, cons
     const int64_t row_h0 = unit_hoff[D.unit_off[info.i]];
     const int64_t dst = c_ptr[info.row] + (unit_hoff[unit] - row_h0) +
                         shard_offset(dst_all.off, dst_all.shard_nnz, dst_all.shard_idx);
-    for (int t = threadIdx.x; t < cnt; t += LR_THREADS) {
-        s_col[t] = col[o0 + t];
-        s_val[t] = val[o0 + t];
-    }
+    // the whole tile in flight at once: two bulk copies (from the 16-byte boundary below the tile's first product to
+    // the one above its last; sc / sv index past the few extra elements) instead of 32 loads per thread in batches
+    const int dxc = (int)((reinterpret_cast<uintptr_t>(col + o0) >> 2) & 3), dxv = (int)((reinterpret_cast<uintptr_t>(val + o0) >> 3) & 1);
+    const int32_t* sc = s_col + dxc;
+    const double* sv = s_val + dxv;
     if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        const uint32_t bc = (uint32_t)((dxc + cnt + 3) & ~3) * 4u, bv = (uint32_t)((dxv + cnt + 1) & ~1) * 8u;
+        mbar_expect_tx(&bar, bc + bv);
+        tma_load_1d(s_col, col + o0 - dxc, bc, &bar);
+        tma_load_1d(s_val, val + o0 - dxv, bv, &bar);
         s_prev = o0 ? col[o0 - 1] : -1;
         s_open_rank = -1;
     }
     __syncthreads();
+    mbar_wait(&bar, 0);
     constexpr int SEG = LONG_UNIT / (LR_THREADS / 32);   // positions per warp
     constexpr int ITERS = SEG / 32;
     unsigned hm[ITERS];
@@ -564,8 +573,8 @@ k_long_reduce(LongDev D, uint32_t n, const int64_t* __restrict__ unit_hoff, cons
         const int t = warp * SEG + it * 32 + lane;
         bool head = false;
         if (t < cnt) {
-            const int32_t c = s_col[t];
-            head = (t == 0) ? (s_prev != c) : (s_col[t - 1] != c);
+            const int32_t c = sc[t];
+            head = (t == 0) ? (s_prev != c) : (sc[t - 1] != c);
         }
         hm[it] = __ballot_sync(FULL, head);
         mine += __popc(hm[it]);
@@ -580,11 +589,11 @@ k_long_reduce(LongDev D, uint32_t n, const int64_t* __restrict__ unit_hoff, cons
     for (int it = 0; it < ITERS; ++it) {
         if ((hm[it] >> lane) & 1u) {
             const int t = warp * SEG + it * 32 + lane;
-            const int32_t c = s_col[t];
-            double sum = s_val[t];
+            const int32_t c = sc[t];
+            double sum = sv[t];
             int j = t + 1;
-            while (j < cnt && s_col[j] == c) {
-                sum = __dadd_rn(sum, s_val[j]);
+            while (j < cnt && sc[j] == c) {
+                sum = __dadd_rn(sum, sv[j]);
                 ++j;
             }
             const int o = rank + __popc(hm[it] & ((1u << lane) - 1u));
@@ -600,7 +609,7 @@ k_long_reduce(LongDev D, uint32_t n, const int64_t* __restrict__ unit_hoff, cons
     }
     __syncthreads();
     if (s_open_rank < 0) return;   // uniform
-    const int32_t c = s_col[cnt - 1];
+    const int32_t c = sc[cnt - 1];
     double sum = s_open_sum;
     for (uint32_t q0 = o0 + (uint32_t)cnt; q0 < P; q0 += LONG_UNIT) {
         const int len = (int)(P - q0 < (uint32_t)LONG_UNIT ? P - q0 : (uint32_t)LONG_UNIT);
@@ -784,14 +793,14 @@ uint32_t launch_long_setup(const LongPlan& P, const uint32_t* flops, PlanCounter
     return 5;
 }
 
-template <typename K, int G>
+template <typename K, bool SPLIT>
 static void chunk_sort_launch(const DevCsr& a, const DevCsr& b, int64_t row_begin, const uint32_t* aseq, const LongDev& D,
                               const LongWaveRange& w, cudaStream_t s) {
     const size_t smem = (sizeof(K) + sizeof(double)) * LONG_UNIT;
     static PerDeviceOnce attr;
     if (attr.first())
-        cudaFuncSetAttribute(k_long_chunk_sort<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_long_chunk_sort<K, G><<<(unsigned)w.unit_bound, LR_THREADS, smem, s>>>(a, b, row_begin, D, w.hi, aseq);
+        cudaFuncSetAttribute(k_long_chunk_sort<K, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_long_chunk_sort<K, SPLIT><<<(unsigned)w.unit_bound, LR_THREADS, smem, s>>>(a, b, row_begin, D, w.hi, aseq);
 }
 
 // one wave: chunk sorts, merge levels (the rows of the wave end in their scratch rows), head counts -> row_nnz
@@ -804,9 +813,9 @@ uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, c
     const LongDev D = long_dev(P, w.lo);
     on("long_sort", (uint32_t)w.unit_bound, w.products_bound);
     // sort: 32-bit (column << 12 | arrival) keys whenever they fit
-    if ((uint64_t)b.cols <= (1ull << (32 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 1>(a, b, row_begin, aseq, D, w, s);
-    else if ((uint64_t)b.cols <= (1ull << (33 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, 2>(a, b, row_begin, aseq, D, w, s);
-    else chunk_sort_launch<uint64_t, 1>(a, b, row_begin, aseq, D, w, s);
+    if ((uint64_t)b.cols <= (1ull << (32 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, false>(a, b, row_begin, aseq, D, w, s);
+    else if ((uint64_t)b.cols <= (1ull << (33 - LONG_UNIT_LOG))) chunk_sort_launch<uint32_t, true>(a, b, row_begin, aseq, D, w, s);
+    else chunk_sort_launch<uint64_t, false>(a, b, row_begin, aseq, D, w, s);
     kernels += 1;
     off();
     // merge levels: rows are listed by ascending level count, level l takes the list from level_lo[l] on
@@ -828,14 +837,10 @@ uint32_t launch_long_wave(const DevCsr& a, const DevCsr& b, int64_t row_begin, c
         on(lname, w.level_grid[l], w.level_products[l]);
         const unsigned grid = std::min<unsigned>(w.level_grid[l], (unsigned)merge_ctas);
         k_long_partition<<<(w.level_grid[l] + 255) / 256, 256, 0, s>>>(D, w.level_lo[l], w.hi, l, tiles);
-        k_long_merge<<<grid, MG_THREADS, mgsmem, s>>>(tiles, D, w.level_lo[l], w.hi);
+        k_long_merge<<<grid, MG_THREADS, mgsmem, s>>>(tiles, D, w.level_lo[l], w.hi, P.unit_heads, row_nnz);
         kernels += 2;
         off();
     }
-    on("long_count", (uint32_t)w.unit_bound, w.products_bound);
-    k_long_count<<<(unsigned)w.unit_bound, LR_THREADS, 0, s>>>(D, w.hi, P.unit_heads, row_nnz);
-    kernels += 1;
-    off();
     return kernels;
 }
 
@@ -849,7 +854,7 @@ uint32_t launch_long_heads_scan(const LongPlan& P, PlanCounters* ctr, cudaStream
 // second half: every head sums its run left to right straight into C (every destination of dst)
 uint32_t launch_long_reduce(const LongPlan& P, const int64_t* c_ptr, const CopyDst& dst, cudaStream_t s) {
     if (P.n_rows == 0) return 0;
-    const size_t msmem = (sizeof(int32_t) + sizeof(double)) * LONG_UNIT;
+    const size_t msmem = (sizeof(int32_t) + sizeof(double)) * (LONG_UNIT + RD_PAD);
     static PerDeviceOnce rattr;
     if (rattr.first()) {
         cudaFuncSetAttribute(k_long_reduce<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);

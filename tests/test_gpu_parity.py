@@ -65,12 +65,34 @@ def test_each_bin(engine, oracle, ka, lb, expect_bin):
 
 @pytest.mark.parametrize("n_cols", [1 << 10, 1 << 20, 1 << 21, 1 << 22, 1 << 23, (1 << 28) + 5])
 def test_key_width_paths(engine, oracle, n_cols):
-    # 32-bit packed (column, arrival) keys when they fit; one bit short: two 32-bit groups merged in shared memory;
-    # 64-bit keys otherwise
+    # 32-bit packed (column, arrival) keys when they fit; one bit short: sorted without the top bit of the column, then
+    # split by it; 64-bit keys otherwise
     for ka, lb in [(4, 6), (16, 16), (30, 30), (40, 50), (60, 60), (80, 90), (200, 120)]:
         a = random_csr(130, 300, row_nnz=ka, seed=3, values="signed")
         b = random_csr(300, n_cols, row_nnz=lb, seed=4, values="signed")
         run(engine, oracle, a, b)
+
+
+@pytest.mark.parametrize("n_cols,ka,lb", [(1 << 23, 30, 30), (1 << 22, 40, 50), (1 << 21, 60, 60), (1 << 21, 80, 90),
+                                          (1 << 21, 300, 230), ((1 << 21) - 3, 64, 64)])
+def test_top_bit_split_with_sums(engine, oracle, n_cols, ka, lb):
+    # the one-bit-short path on every sort width (1024 / 2048 / 4096 / chunks of long rows): B's columns come from a
+    # small pool on both sides of the bit the key drops, so runs of equal columns exist in both halves of the split,
+    # and columns that differ only in that bit must not be summed together
+    rng = np.random.default_rng(n_cols % 1000 + ka)
+    half = n_cols // 2 if n_cols & (n_cols - 1) == 0 else 1 << (n_cols.bit_length() - 1)
+    pool = np.unique(np.concatenate([rng.choice(700, 400, replace=False), half + rng.choice(700, 400, replace=False),
+                                     [0, half - 1, half, n_cols - 1]]))
+    pool = pool[pool < n_cols]
+    k = 300
+    rows = np.repeat(np.arange(k), lb)
+    cols = np.concatenate([rng.choice(pool, lb, replace=False) for _ in range(k)])
+    b = sp.csr_matrix((rng.uniform(-1, 1, len(rows)), (rows, cols)), shape=(k, n_cols))
+    b.sort_indices()
+    a = random_csr(70, k, row_nnz=ka, seed=5, values="signed")
+    run(engine, oracle, a, b)
+    b_low = b[:, :half].tocsr()   # no top bits at all / only top bits
+    run(engine, oracle, a, sp.csr_matrix((b_low.data, b_low.indices, b_low.indptr), shape=(k, n_cols)))
 
 
 def test_mixed_bins_and_permutation(engine, oracle):
