@@ -8,6 +8,10 @@
 namespace spada {
 
 constexpr int ESC_CTA_THREADS = 256;
+#ifndef SPADA_CTA_EXPAND_UNROLL
+#define SPADA_CTA_EXPAND_UNROLL 2
+#endif
+constexpr int CTA_EXPAND_UNROLL = SPADA_CTA_EXPAND_UNROLL;   // products a thread expands per step (B gathers in flight)
 
 // Where key e of a CTA-wide sort lives in shared memory.  The register phases move every lane's N/256 consecutive keys
 // as 16-byte vectors: with U vectors per lane the eight lanes of a quarter-warp (one 128-byte transaction) would meet
@@ -85,9 +89,9 @@ __device__ __forceinline__ void top_bit_mark(uint32_t* top, int idx, bool is_top
     }
 }
 
-// PACKED: keys carry the arrival index (column << log2 N | arrival); LOAD_COL = false: values only.
-// top != nullptr (32-bit keys only): the column's bit 32 - log2 N is recorded there instead of in the key.
-template <typename K, int N, bool NUMERIC, bool PACKED = NUMERIC, bool LOAD_COL = true, bool SPLIT = false>
+// Keys carry the arrival index (column << log2 N | arrival).
+// SPLIT (32-bit keys only): the column's bit 32 - log2 N is recorded in `top` instead of in the key.
+template <typename K, int N, bool SPLIT = false>
 __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr& b, int64_t a_begin, int64_t a_end,
                                                   K* keys, double* vals, CtaStage& st, uint32_t* top = nullptr) {
     constexpr int SB = Log2<N>::v;
@@ -100,7 +104,7 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
         double av = 0.0;
         if (p < a_end) {
             int32_t k = ldg_i32(a.col + p);
-            if (NUMERIC) av = ldg_f64(a.val + p);
+            av = ldg_f64(a.val + p);
             b_row(b, k, bs, len);
         }
         int wtotal;
@@ -116,17 +120,19 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
         }
         st.off[threadIdx.x] = base + woff;
         st.bs[threadIdx.x] = bs;
-        if (NUMERIC) st.av[threadIdx.x] = av;
+        st.av[threadIdx.x] = av;
         if (threadIdx.x == 0) st.off[ESC_CTA_THREADS] = all;
         __syncthreads();
         const int n_ent = (int)((a_end - pb) < ESC_CTA_THREADS ? (a_end - pb) : ESC_CTA_THREADS);
-        for (int t0 = threadIdx.x; t0 < all; t0 += 2 * ESC_CTA_THREADS) {
-            // two products per step: independent searches and gathers in flight
-            int t[2] = {t0, t0 + ESC_CTA_THREADS};
-            int64_t q[2];
-            int j[2];
+        for (int t0 = threadIdx.x; t0 < all; t0 += CTA_EXPAND_UNROLL * ESC_CTA_THREADS) {
+            // several products per step: independent searches and gathers in flight
+            int t[CTA_EXPAND_UNROLL];
+            int64_t q[CTA_EXPAND_UNROLL];
+            int j[CTA_EXPAND_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u) t[u] = t0 + u * ESC_CTA_THREADS;
+#pragma unroll
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u) {
                 int lo = 0, hi = n_ent;  // largest j in [0, n_ent) with off[j] <= t
                 if (t[u] < all) {
                     while (hi - lo > 1) {
@@ -137,23 +143,23 @@ __device__ __forceinline__ int bitonic_cta_expand(const DevCsr& a, const DevCsr&
                 j[u] = lo;
                 q[u] = st.bs[lo] + (t[u] - st.off[lo]);
             }
-            uint32_t c[2];
-            double bv[2];
+            uint32_t c[CTA_EXPAND_UNROLL];
+            double bv[CTA_EXPAND_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u) {
                 c[u] = 0;
                 bv[u] = 0.0;
                 if (t[u] < all) {
-                    if (LOAD_COL) c[u] = (uint32_t)ldg_i32(b.col + q[u]);
-                    if (NUMERIC) bv[u] = ldg_f64(b.val + q[u]);
+                    c[u] = (uint32_t)ldg_i32(b.col + q[u]);
+                    bv[u] = ldg_f64(b.val + q[u]);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u) {
                 if (t[u] < all) {
                     int sq = seq_base + t[u];
-                    if (LOAD_COL) keys[KeySlot<K, N>::at(sq)] = PACKED ? (((K)c[u] << SB) | (K)(sq & (N - 1))) : (K)c[u];   // SPLIT: the top bit falls off
-                    if (NUMERIC) vals[sq] = __dmul_rn(st.av[j[u]], bv[u]);
+                    keys[KeySlot<K, N>::at(sq)] = ((K)c[u] << SB) | (K)(sq & (N - 1));   // SPLIT: the top bit falls off
+                    vals[sq] = __dmul_rn(st.av[j[u]], bv[u]);
                     if constexpr (SPLIT) top_bit_mark(top, sq, (c[u] >> (32 - SB)) & 1u, lane);
                 }
             }

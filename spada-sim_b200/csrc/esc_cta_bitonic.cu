@@ -23,7 +23,7 @@ k_bitonic_numeric_cta(DevCsr a, DevCsr b, int64_t row_begin, const uint32_t* __r
     const int64_t a_begin = a.ptr[row_begin + r], a_end = a.ptr[row_begin + r + 1];
     if constexpr (SPLIT)
         for (int t = threadIdx.x; t < N / 32 + 1; t += ESC_CTA_THREADS) top[t] = 0u;   // the expansion syncs before it writes
-    const int p = bitonic_cta_expand<K, N, true, true, true, SPLIT>(a, b, a_begin, a_end, keys, vals, st, top);
+    const int p = bitonic_cta_expand<K, N, SPLIT>(a, b, a_begin, a_end, keys, vals, st, top);
     for (int t = p + threadIdx.x; t < N; t += ESC_CTA_THREADS) keys[KeySlot<K, N>::at(t)] = KeyTraits<K>::sentinel;
     __syncthreads();
     bitonic_cta_sort<K, N>(keys);

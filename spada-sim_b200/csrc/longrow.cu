@@ -179,12 +179,14 @@ __device__ __forceinline__ void chunk_body(const DevCsr a, const DevCsr b, const
         __syncthreads();
         const int n_ent = (int)((e1 - pb) < LR_THREADS ? (e1 - pb) : LR_THREADS);
         const int first = st.off[0], end = st.off[LR_THREADS];
-        for (int t0 = first + (int)threadIdx.x; t0 < end; t0 += 2 * LR_THREADS) {
-            int t[2] = {t0, t0 + LR_THREADS};
-            int64_t q[2];
-            int j[2];
+        for (int t0 = first + (int)threadIdx.x; t0 < end; t0 += CTA_EXPAND_UNROLL * LR_THREADS) {
+            int t[CTA_EXPAND_UNROLL];
+            int64_t q[CTA_EXPAND_UNROLL];
+            int j[CTA_EXPAND_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u) t[u] = t0 + u * LR_THREADS;
+#pragma unroll
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u) {
                 int lo = 0, hi = n_ent;   // largest j with off[j] <= t
                 if (t[u] < end) {
                     while (hi - lo > 1) {
@@ -195,10 +197,10 @@ __device__ __forceinline__ void chunk_body(const DevCsr a, const DevCsr b, const
                 j[u] = lo;
                 q[u] = st.bs[lo] + (t[u] - st.off[lo]);
             }
-            uint32_t c[2];
-            double bv[2];
+            uint32_t c[CTA_EXPAND_UNROLL];
+            double bv[CTA_EXPAND_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u) {
                 c[u] = 0;
                 bv[u] = 0.0;
                 if (t[u] < end) {
@@ -207,7 +209,7 @@ __device__ __forceinline__ void chunk_body(const DevCsr a, const DevCsr b, const
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < CTA_EXPAND_UNROLL; ++u)
                 if (t[u] < end) {
                     keys[KeySlot<K, N>::at(t[u])] = ((K)c[u] << SB) | (K)t[u];   // SPLIT: the top bit falls off
                     vals[t[u]] = __dmul_rn(st.av[j[u]], bv[u]);

@@ -10,7 +10,9 @@ rng = np.random.default_rng(7)
 for mode in ({"two_phase": True}, {"single_pass": True}):
     e = pkg.Engine(**mode)
     for ka, lb, n in [(3, 4, 300), (5, 5, 5000), (12, 2, 64), (8, 8, 5000), (16, 16, 5000), (20, 25, 5000), (32, 32, 5000),
-                      (64, 64, 5000), (70, 100, 5000), (300, 230, 3000), (120, 300, 40)]:
+                      (64, 64, 5000), (70, 100, 5000), (300, 230, 3000), (120, 300, 40),
+                      # one bit short of 32-bit keys (top-bit split) on the 2048 / 4096 sorts and the chunks of long rows; 64-bit keys
+                      (40, 50, 1 << 22), (64, 64, 1 << 21), (70, 100, 1 << 21), (64, 64, 1 << 23), (70, 100, 1 << 23)]:
         a = random_csr(40, 600, row_nnz=rng.integers(max(ka - 2, 0), ka + 1, size=40), seed=ka, values="signed")
         b = random_csr(600, n, row_nnz=np.minimum(rng.integers(max(lb - 2, 0), lb + 1, size=600), n), seed=lb, values="signed")
         r = e.spgemm(a, b)
