@@ -566,7 +566,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get(dom_name)
+        traffic = json.load(open(tp)).get(args.workload, {}).get(dom_name.split("#")[0])   # "#k": wave k of the long rows
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": dom_name, "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
                 "peak_source": peak_src, "timing": timing_note,

@@ -28,7 +28,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_f
   python bench.py --workload er --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_b.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:"k_fused_tiny4" -s 3 -c 1 -f -o gpurun_out/prof_poisson_tiny \
   python bench.py --workload poisson --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_c.log 2>&1
-timeout 1200 ncu --set full --clock-control none -k regex:"k_long_chunk_sort|k_long_merge|k_long_reduce|k_long_count" -s 40 -c 8 -f -o gpurun_out/prof_rmat_long \
+timeout 1200 ncu --set full --clock-control none -k regex:"k_long_chunk_sort|k_long_merge|k_long_reduce" -s 40 -c 8 -f -o gpurun_out/prof_rmat_long \
   python bench.py --workload rmat --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_rmat_long.log 2>&1
 ls -la gpurun_out/*.ncu-rep
 python tools/summarize_profiles.py r02 gpurun_out/profiles > gpurun_out/summarize.log 2>&1; tail -3 gpurun_out/summarize.log

@@ -133,8 +133,6 @@ def sec_full():
             return "long_sort"
         if "k_long_reduce" in kn:
             return "long_reduce"
-        if "k_long_count" in kn:
-            return "long_count"
         if "k_copy_rows" in kn:
             return "copy_rows"
         if "k_flops" in kn:
