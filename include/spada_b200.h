@@ -98,13 +98,14 @@ typedef struct spada_b200_opts {
 } spada_b200_opts;
 
 #define SPADA_B200_FLAG_VALIDATE 1u  /* check canonical CSR on upload (UNSORTED_INPUT) */
-#define SPADA_B200_FLAG_TWO_PHASE 2u /* always run the separate symbolic + numeric passes (exact-size C) */
+#define SPADA_B200_FLAG_TWO_PHASE 2u /* always take the scratch pass: every row sorted and summed once into a scratch CSR,
+                                        then placed into an exact-size C */
 #define SPADA_B200_FLAG_SINGLE_PASS 4u /* always do rows with <= 512 products in one fused pass (C is then
                                           allocated with capacity = intermediate-product count).  With neither
                                           flag the engine picks: single pass when one bin holds >= 80 % of the rows */
 
-#define SPADA_B200_FLAG_SERIAL 8u     /* every kernel on the one stream (the engine otherwise runs the heavy / huge bins
-                                          on a side stream beside the sort bins): clean per-launch times for profiling */
+#define SPADA_B200_FLAG_SERIAL 8u     /* every kernel on the one stream (the engine otherwise runs the long rows, > 4096
+                                          products, on a side stream beside the sort bins): clean per-launch times */
 
 typedef struct spada_b200 spada_b200_t;               /* engine handle (streams, workspace pool) */
 typedef struct spada_b200_csr spada_b200_csr_t;       /* device-resident operand */
