@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of build-time knobs (variants built by tools/build_variant.sh): usage gpu_knobs.sh "<variant:workload:steps> ..."
+# A/B of library variants (build-time knobs or an older checkout) (variants built by tools/build_variant.sh): usage gpu_knobs.sh "<variant:workload:steps> ..."
 mkdir -p gpurun_out
 for spec in $1; do
   IFS=: read v w n <<< "$spec"; [ "$v" = new ] && v=""

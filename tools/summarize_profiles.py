@@ -3,7 +3,7 @@
 
     python tools/summarize_profiles.py r02
 
-Inputs (written by tools/gpu_final.sh and tools/gpu_r2j.sh on the GPU box): bench_<workload>.log, bench_reference.log,
+Inputs (written by tools/gpu_final.sh and tools/gpu_scale.sh on the GPU box): bench_<workload>.log, bench_reference.log,
 bench_n<N>_peer.log / bench_n<N>_nccl.log, launches_<workload>.csv (ncu launch lists), prof_*.ncu-rep (ncu --set full).
 """
 import collections, csv, io, json, os, re, subprocess, sys
