@@ -14,6 +14,7 @@ libspada_b200.so.
 """
 from __future__ import annotations
 
+import collections
 from typing import Optional, Tuple
 
 import numpy as np
@@ -108,10 +109,28 @@ def plan_bounds(engine, da, db, world: int, device, src: int = 0, group=None) ->
     return t.cpu().numpy()
 
 
+# (event, owners): engine Results whose pool blocks torch's stream may still be reading
+_inflight: "collections.deque" = collections.deque()
+
+
+def _keep_until_done(tensors) -> None:
+    """The views of ``result_views`` alias pool blocks of the engine; the copies and collectives enqueued on torch's
+    stream return before they have run.  Hold the owning Results until an event recorded behind that work has
+    completed, so that dropping the Result right after the call cannot hand its blocks to the next product early."""
+    while _inflight and _inflight[0][0].query():
+        _inflight.popleft()
+    owners = [o for o in (getattr(t, "_spada_owner", None) for t in tensors) if o is not None]
+    if owners:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        _inflight.append((ev, owners))
+
+
 def allgather_csr(local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: torch.Tensor,
                   group=None, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
     """All ranks end with the whole C.  Shard r holds rows [b_r, b_{r+1}) with a row_ptr that
-    starts at 0; the global row_ptr is local + (nnz of the shards before)."""
+    starts at 0; the global row_ptr is local + (nnz of the shards before).  The work is enqueued on torch's current
+    stream; inputs that are ``result_views`` keep their Result alive until that work has run (``_keep_until_done``)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = local_ptr.device
@@ -156,6 +175,7 @@ def allgather_csr(local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: t
             g_ptr[rs + 1:rs + 1 + rows[r]] = pad_ptr[r, :rows[r]]
             g_col[ns:ns + nnzs[r]] = pad_col[r, :nnzs[r]]
             g_val[ns:ns + nnzs[r]] = pad_val[r, :nnzs[r]]
+        _keep_until_done((local_ptr, local_col, local_val))
         return g_ptr, g_col, g_val
     # Two ranks (or CPU/gloo): every rank sends its shard to every peer and receives theirs in ONE
     # grouped batch (ncclGroupStart/End).
@@ -181,6 +201,8 @@ def allgather_csr(local_ptr: torch.Tensor, local_col: torch.Tensor, local_val: t
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+    if dev.type == "cuda":
+        _keep_until_done((local_ptr, local_col, local_val))
     return g_ptr, g_col, g_val
 
 
