@@ -217,6 +217,12 @@ class PeerGather:
     offset from that device array and stores every row into ALL ranks' buffers -- its own through HBM, the peers'
     over NVLink -- so the exchange overlaps the placement instead of following it.  A one-element all-reduce
     afterwards is the barrier that makes every rank's C complete before anybody reads it.
+
+    Ordering between the engine's kernels and the two collectives: when the engine was created on torch's current
+    stream (``Engine(stream=torch.cuda.current_stream().cuda_stream)`` inside a ``torch.cuda.stream`` context) the
+    stream orders them.  Otherwise -- an engine-owned stream, which is also what handle 0, torch's default stream,
+    selects -- the engine's stream and torch's do not see each other, and ``step`` waits on the host at the two
+    hand-overs (the local nnz before the all-gather reads it, the gathered nnz before the placement reads them).
     """
 
     def __init__(self, engine, rows: int, cols: int, capacity: int, device, group=None):
@@ -232,13 +238,19 @@ class PeerGather:
         self.shard_nnz = torch.zeros(self.world, dtype=torch.int64, device=device)
         self.local_nnz = torch.zeros(1, dtype=torch.int64, device=device)
         self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        es = getattr(engine, "stream", None)
+        self.stream_shared = es is not None and es == torch.cuda.current_stream(device).cuda_stream
         dist.barrier(group=group)
 
     def step(self, da, db, row_begin: int, row_end: int, compute_only: bool = False) -> dict:
         """One sharded product; returns the engine's stats of this rank's shard.  On return (after the barrier
         collective, stream-ordered) every rank's buffers hold the whole C."""
         shard = self.engine.shard_begin(da, db, row_begin, row_end, d_nnz_local=self.local_nnz.data_ptr())
+        if not self.stream_shared:
+            self.engine.synchronize()                       # local_nnz is written before NCCL reads it
         dist.all_gather_into_tensor(self.shard_nnz, self.local_nnz, group=self.group)
+        if not self.stream_shared:
+            torch.cuda.current_stream(self.dev).synchronize()   # shard_nnz is complete before the placement reads it
         bufs = [self.own] if compute_only else self.bufs
         st = shard.finish(bufs, 0, self.shard_nnz.data_ptr(), self.rank)
         dist.all_reduce(self.flag, group=self.group)   # every rank's stores have landed when this completes

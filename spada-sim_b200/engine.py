@@ -262,6 +262,9 @@ class Engine:
         h = C.c_void_p()
         check(lib().spada_b200_create(C.byref(opts), C.byref(h)))
         self._h = h
+        # the stream the kernels run on, None = engine-owned (also for handle 0, CUDA's legacy default stream -- what
+        # torch.cuda.current_stream().cuda_stream is outside a stream context: the ABI reads NULL as "engine-owned")
+        self.stream = stream if stream else None
 
     # -- lifetime --
     def close(self):
@@ -277,6 +280,7 @@ class Engine:
 
     def set_stream(self, stream: Optional[int]):
         check(lib().spada_b200_set_stream(self._h, stream))
+        self.stream = stream if stream else None
 
     def synchronize(self):
         check(lib().spada_b200_synchronize(self._h))
