@@ -418,8 +418,11 @@ def main():
     launches = 0
     t_wall0 = time.time()
     e0.record()
+    engine_ms = 0.0
     for _ in range(args.steps):
-        launches += step()["n_launches"]
+        st_k = step()
+        launches += st_k["n_launches"]
+        engine_ms += float(st_k.get("ms_total", 0.0))
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -595,6 +598,10 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "setup": setup, "multi_gpu": multi, "bins": st["bins"],
+        # cross-check of the timed region: every product ends with a sync of the engine's stream, so the events around
+        # the K steps bracket all of their kernels; this is the engine's own CUDA-event span (first kernel of a product to
+        # its last, on the stream the kernels run on), mean over this rank's timed steps
+        "engine_ms_per_step": engine_ms / max(args.steps, 1),
     }
     print(json.dumps(line))
     if world > 1:
