@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rect|poisson|er|rmat|cari]
     python bench.py --impl reference ...     # the CPU restatement timed on the host cores
 
-One "step" = one pass of the hot path (flop count + binning, symbolic, scan, numeric) over one
+One "step" = one pass of the hot path (flop count + binning, sort passes, long rows, scan, placement) over one
 synthetic operand pair that is already resident in HBM.  Default workload: BASELINE.json
 configs[4], the rectangular power-law 1M x 4M matrix, A x A^T -- the configuration the metric's
 "1/2/4/8 B200" clause is quoted on; it fits one GPU, so the same

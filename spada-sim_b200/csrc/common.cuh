@@ -157,8 +157,7 @@ constexpr int EXPAND_UNROLL = SPADA_EXPAND_UNROLL;  // independent B gathers in 
 // of EXPAND_UNROLL consecutive steps are issued back to back before any of them is consumed, so a
 // warp keeps several HBM/L2 round trips in flight instead of one.
 // expand_batch_long: B rows of at least `long_len` elements are taken out of the dealt stream and handed,
-// one at a time and warp-uniformly, to on_long(b_row_start, length, a_val) -- the TMA-staged path of the
-// huge bin hooks in here.
+// one at a time and warp-uniformly, to on_long(b_row_start, length, a_val) (rows too long for the 32-bit scan).
 template <bool NUMERIC, bool BIG, bool LOAD_COL, typename F, typename L>
 __device__ __forceinline__ void expand_batch_long(const DevCsr& a, const DevCsr& b, int64_t p, int64_t a_end,
                                                   int lane, int seq_base, int& batch_total, int long_len, F&& emit,

@@ -1,4 +1,5 @@
-// cta_common.cuh -- pieces shared by the CTA-per-row sort kernels (esc_cta_bitonic.cu, esc_tiled.cu):
+// cta_common.cuh -- pieces shared by the CTA-wide sort kernels (esc_cta_bitonic.cu: one row per CTA; longrow.cu: one
+// chunk of a long row per CTA):
 // the CTA-wide flattened product expansion, the hybrid bitonic sort (register chunks merged through
 // shared memory) and the ballot-based segmented reduce + store.
 #pragma once

@@ -55,7 +55,7 @@ def cari():
 
 @pytest.fixture(scope="session", params=["fused", "two_phase"])
 def engine(spada, request):
-    """Both engine modes: single-pass (fused light rows + look-back) and separate symbolic/numeric passes."""
+    """Both engine modes: single pass (fused light rows + look-back) and the scratch pass (rows sorted once, then placed)."""
     if spada.device_count() == 0:
         pytest.skip("no CUDA device")
     e = spada.Engine(two_phase=(request.param == "two_phase"), single_pass=(request.param == "fused"))

@@ -213,14 +213,14 @@ def _widen(b, n_cols, shift=0):
 @pytest.mark.parametrize("ka,lb,width", [(30, 30, 64), (50, 40, 300), (100, 90, 700), (200, 60, 2000), (90, 80, 1 << 14)])
 def test_skewed_columns(engine, oracle, ka, lb, width):
     # every product of a row lands in a narrow band of a 2^20-wide B: long runs of equal columns in the sort bins,
-    # a handful of hot words in the heavy bin's bitmap
+    # many equal keys per merge tile in the long rows
     a = random_csr(120, 400, row_nnz=ka, seed=ka + 1)
     b = _widen(random_csr(400, width, row_nnz=min(lb, width), seed=lb + 2), 1 << 20, shift=(1 << 19) + 77)
     run(engine, oracle, a, b)
 
 
 def test_long_rows_mixed_lengths(engine, oracle):
-    # rows of 513 .. ~40000 products side by side: CTA-per-row sort bins and the heavy bin in one call
+    # rows of 513 .. ~40000 products side by side: CTA-per-row sort bins and long rows in one call
     rng = np.random.default_rng(21)
     lens = rng.choice([0, 30, 70, 130, 260, 520, 900, 2500], size=400, p=[.05, .2, .2, .2, .15, .1, .07, .03])
     a = random_csr(400, 6000, row_nnz=lens, seed=22, values="signed")
