@@ -70,17 +70,23 @@ def main():
     if rank == 0:
         cap[0] = eng.flops(da, db)
     dist.broadcast(cap, src=0)
+    # a second product with the rows of A in reverse order: other shard bounds and other nnz per shard, so that a step
+    # which picked up anything of the step before it (a stale nnz, a stale offset) cannot come out right
+    a2 = a[::-1].tocsr() if rank == 0 else None
+    da2, _ka2 = D.broadcast_csr(eng, a2, dev)
+    bounds2 = D.plan_bounds(eng, da2, db, world, dev)
     pg = D.PeerGather(eng, da.shape[0], db.shape[1], int(cap[0]), dev)
-    ref = eng.spgemm_dev(da, db).to_host()
+    cases = [(da, bounds, eng.spgemm_dev(da, db).to_host()), (da2, bounds2, eng.spgemm_dev(da2, db).to_host())]
     ok = True
-    for it in range(3):
-        pg.step(da, db, int(bounds[rank]), int(bounds[rank + 1]))
+    for it in range(4):
+        xa, bnd, ref = cases[it % 2]
+        pg.step(xa, db, int(bnd[rank]), int(bnd[rank + 1]))
         torch.cuda.synchronize()
         got = pg.own.to_host()
         same_bits = all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(got, ref))
         ok = ok and same_bits
-        print(f"rank {rank}/{world} step {it}: gathered nnz {len(got[1])}, rows [{bounds[rank]}, {bounds[rank + 1]}), "
-              f"identical to one GPU: {same_bits}", flush=True)
+        print(f"rank {rank}/{world} step {it} ({'A' if it % 2 == 0 else 'A reversed'}): gathered nnz {len(got[1])}, "
+              f"rows [{bnd[rank]}, {bnd[rank + 1]}), identical to one GPU: {same_bits}", flush=True)
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     pg.close()
